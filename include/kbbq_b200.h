@@ -1,0 +1,167 @@
+/*
+ * kbbq_b200.h -- C ABI of the B200-native kbbq recalibration hot path (libkbbq_b200.so).
+ *
+ * The reference (adamjorr/kbbq-py) has no FFI layer: its boundary is the Python function surface of
+ * kbbq/recalibrate.py, kbbq/compare_reads.py and kbbq/gatk/applybqsr.py.  Each entry point below
+ * replaces the arithmetic of one of those functions on packed structure-of-arrays batches; the
+ * Python package kbbq-py_b200/kbbq keeps the reference's names and signatures and binds these
+ * symbols with ctypes.  File:line citations are into the reference tree.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / CUDA types in signatures (`stream` is a
+ *    cudaStream_t passed as void*, NULL = default stream);
+ *  - every `*_dev` pointer is a DEVICE pointer; functions named *_host take HOST pointers;
+ *  - device entry points are asynchronous on `stream`, allocate nothing, keep no global state
+ *    and are re-entrant per stream; data errors found on the device (quality > 42, base outside
+ *    ACGTN, rg >= R) are OR-ed into the caller's device word `status_dev`
+ *    (KBBQ_FLAG_*), which the caller reads after synchronising;
+ *  - return value: 0 = ok, negative = KBBQ_E_* (argument / CUDA errors, reported synchronously).
+ *
+ * Packed batch layout: seq, qual, corr are u8[N*L] row-major by read, all reads
+ * of uniform length L; qual holds the phred value (ASCII - 33); rg is u16[N] (read-group int in
+ * first-seen order, kbbq/recalibrate.py:59-64; NULL = all 0), second is u8[N]
+ * (fastq_infer_secondinpair, kbbq/compare_reads.py:304-306; NULL = all 0).
+ * Tables: pos_* int64[R][43][2L], din_* int64[R][43][16] exactly as the reference returns them
+ * (kbbq/recalibrate.py:121); the cycle axis holds read-1 cycle i at i and read-2 cycle i at 2L-1-i.
+ */
+#ifndef KBBQ_B200_H
+#define KBBQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KBBQ_NQ 43        /* maxscore + 1 (kbbq/recalibrate.py:22) */
+#define KBBQ_NDINUC 16    /* kbbq/compare_reads.py:199-214 */
+
+/* return codes */
+#define KBBQ_OK 0
+#define KBBQ_E_ARG (-1)       /* bad argument (NULL, negative size, misaligned pointer, L too small) */
+#define KBBQ_E_CUDA (-2)      /* a CUDA runtime call failed; see kbbq_last_cuda_error() */
+#define KBBQ_E_WORKSPACE (-3) /* workspace too small */
+#define KBBQ_E_DATA (-4)      /* host-API only: device status word was non-zero (see flags) */
+
+/* bits of the device status word */
+#define KBBQ_FLAG_QUAL_RANGE 1 /* a quality > 42: IndexError in the reference */
+#define KBBQ_FLAG_BAD_BASE 2   /* a base outside ACGTN: TypeError in Dinucleotide.vecget */
+#define KBBQ_FLAG_RG_RANGE 4   /* rg[i] >= R */
+
+int kbbq_abi_version(void);
+const char *kbbq_strerror(int code);
+const char *kbbq_last_cuda_error(void);
+
+/* Number of int64 elements of one cycle table / one dinuc table. */
+int64_t kbbq_pos_table_elems(int L, int R);
+int64_t kbbq_din_table_elems(int R);
+
+/* Scratch needed by kbbq_build / kbbq_apply for a batch of N reads (bytes, device memory). */
+int kbbq_workspace_bytes(int64_t N, int L, int R, size_t *bytes);
+
+/*
+ * Table build.  Replaces the per-read body of fastq_to_covariate_arrays: find_corrected_sites
+ * (kbbq/recalibrate.py:13-20), cycle and dinuc covariates (kbbq/compare_reads.py:275-302), the
+ * mask block (:96-101) and the pos_* / dinuc_* np.add.at calls (:116-119).  ACCUMULATES into the
+ * four int64 tables (zero them first for a fresh build; batches and ranks simply add).
+ * `path`: 0 = auto, 1 = shared-memory-privatised kernel, 2 = generic global-atomic kernel.
+ */
+int kbbq_build(const uint8_t *seq_dev, const uint8_t *qual_dev, const uint8_t *corr_dev,
+               const uint16_t *rg_dev, const uint8_t *second_dev, int64_t N, int L, int R,
+               int minscore, int64_t *pos_errs_dev, int64_t *pos_total_dev, int64_t *din_errs_dev,
+               int64_t *din_total_dev, void *workspace_dev, size_t workspace_bytes,
+               int *status_dev, int path, void *stream);
+
+/*
+ * Marginals + meanq.  rg_* / q_* are the sums of pos_* over cycle (and q), which is what the
+ * reference's separate np.add.at calls produce (kbbq/recalibrate.py:112-115); meanq is
+ * p_to_q(expected_errs / rg_total) (:111,:120; kbbq/compare_reads.py:262-271).
+ * Outputs: q_* int64[R][43], rg_* int64[R], meanq int64[R].
+ */
+int kbbq_marginals(const int64_t *pos_errs_dev, const int64_t *pos_total_dev, int L, int R,
+                   int64_t *q_errs_dev, int64_t *q_total_dev, int64_t *rg_errs_dev,
+                   int64_t *rg_total_dev, int64_t *meanq_dev, void *stream);
+
+/* gatk_delta_q on n independent cells (kbbq/compare_reads.py:235-260). */
+int kbbq_delta_q(const int64_t *prior_q_dev, const int64_t *numerrs_dev,
+                 const int64_t *numtotal_dev, int64_t n, int64_t *delta_dev, void *stream);
+
+/*
+ * get_delta_qs (kbbq/gatk/applybqsr.py:80-103) for arbitrary axis lengths: q_* is [R][nq],
+ * pos_* [R][nq][ncyc], din_* [R][nq][ndin].  Outputs rgdq[R], qdq[R][nq], posdq[R][nq][ncyc],
+ * dindq[R][nq][ndin+1] (last dinuc column is the zero pad, :98-101).
+ */
+int kbbq_get_delta_qs(const int64_t *meanq_dev, const int64_t *rg_errs_dev,
+                      const int64_t *rg_total_dev, const int64_t *q_errs_dev,
+                      const int64_t *q_total_dev, const int64_t *pos_errs_dev,
+                      const int64_t *pos_total_dev, const int64_t *din_errs_dev,
+                      const int64_t *din_total_dev, int R, int nq, int ncyc, int ndin,
+                      int64_t *rgdq_dev, int64_t *qdq_dev, int64_t *posdq_dev, int64_t *dindq_dev,
+                      void *stream);
+
+/*
+ * Apply.  Replaces compare_reads.recalibrate_fastq (kbbq/compare_reads.py:320-328) over a batch:
+ * out = q < minscore ? q : meanq[rg] + rgdq[rg] + qdq[rg,q] + dindq[rg,q,dinuc] + posdq[rg,q,cycle]
+ * with dinuc -1 gathering the last dinuc column and read-2 cycles indexing from the end.  The
+ * delta tables have the reference's shapes: qdq [R][nq], posdq [R][nq][2L], dindq [R][nq][ndin1]
+ * (nq <= 43; a quality >= nq raises KBBQ_FLAG_QUAL_RANGE).  out_qual is u8[N*L] (no clamp: the
+ * low 8 bits of the sum, as the reference keeps whatever the sum is).
+ */
+int kbbq_apply(const uint8_t *seq_dev, const uint8_t *qual_dev, const uint16_t *rg_dev,
+               const uint8_t *second_dev, int64_t N, int L, int R, int minscore,
+               const int64_t *meanq_dev, const int64_t *rgdq_dev, const int64_t *qdq_dev,
+               const int64_t *posdq_dev, const int64_t *dindq_dev, int nq, int ndin1,
+               uint8_t *out_qual_dev, void *workspace_dev, size_t workspace_bytes, int *status_dev,
+               int path, void *stream);
+
+/*
+ * Whole path on HOST buffers: H2D, build, marginals, deltas, apply, D2H -- what
+ * recalibrate.recalibrate_fastq (kbbq/recalibrate.py:123-156) does between parsing and printing.
+ * Reads are streamed in chunks over two CUDA streams; tables_host (optional, may be NULL) receives
+ * [pos_errs | pos_total | din_errs | din_total]; deltas_host (optional) receives
+ * [meanq R | rgdq R | qdq R*43 | posdq R*43*2L | dindq R*43*17].  Synchronous.
+ */
+int kbbq_recalibrate_host(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr,
+                          const uint16_t *rg, const uint8_t *second, int64_t N, int L, int R,
+                          int minscore, uint8_t *out_qual, int64_t *tables_host,
+                          int64_t *deltas_host, int *status_out, int device);
+
+/* Host-buffer variants of the two halves (drop-in backing of fastq_to_covariate_arrays and of
+ * the apply loop when the caller keeps the tables). Synchronous. */
+int kbbq_build_host(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr,
+                    const uint16_t *rg, const uint8_t *second, int64_t N, int L, int R,
+                    int minscore, int64_t *pos_errs, int64_t *pos_total, int64_t *din_errs,
+                    int64_t *din_total, int *status_out, int device);
+int kbbq_apply_host(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg,
+                    const uint8_t *second, int64_t N, int L, int R, int minscore,
+                    const int64_t *meanq, const int64_t *rgdq, const int64_t *qdq,
+                    const int64_t *posdq, const int64_t *dindq, int nq, int ndin1,
+                    uint8_t *out_qual, int *status_out, int device);
+int kbbq_get_delta_qs_host(const int64_t *meanq, const int64_t *rg_errs, const int64_t *rg_total,
+                           const int64_t *q_errs, const int64_t *q_total, const int64_t *pos_errs,
+                           const int64_t *pos_total, const int64_t *din_errs,
+                           const int64_t *din_total, int R, int nq, int ncyc, int ndin,
+                           int64_t *rgdq, int64_t *qdq, int64_t *posdq, int64_t *dindq, int device);
+int kbbq_delta_q_host(const int64_t *prior_q, const int64_t *numerrs, const int64_t *numtotal,
+                      int64_t n, int64_t *delta, int device);
+int kbbq_marginals_host(const int64_t *pos_errs, const int64_t *pos_total, int L, int R,
+                        int64_t *q_errs, int64_t *q_total, int64_t *rg_errs, int64_t *rg_total,
+                        int64_t *meanq, int device);
+
+/*
+ * Synthetic Illumina-shaped reads, counter-based so that any read range can be
+ * regenerated anywhere: fills seq/qual/corr u8[n*L], rg u16[n], second u8[n] for reads
+ * [first_read, first_read + n) of the stream identified by `seed`.  Bench / test input only.
+ */
+int kbbq_synth_reads(uint64_t seed, int64_t first_read, int64_t n, int L, int R,
+                     uint8_t *seq_dev, uint8_t *qual_dev, uint8_t *corr_dev, uint16_t *rg_dev,
+                     uint8_t *second_dev, void *stream);
+
+/* Number of kernel launches this library has issued since load (bench.py's gpu_launches). */
+int64_t kbbq_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KBBQ_B200_H */

@@ -1,0 +1,165 @@
+// apply.cuh -- K2: recalibration apply kernel.
+//
+// Replaces compare_reads.recalibrate_fastq (kbbq/compare_reads.py:320-328) over a packed batch:
+//   out = q < minscore ? q : meanq[rg] + rgdq[rg] + qdq[rg,q] + dindq[rg,q,dinuc] + posdq[rg,q,cycle]
+// Every term is an integer, so the five-term sum is folded (model.cuh: fold_kernel) into two small
+// tables per read group -- fold_cyc[q][cycle] (meanq + rgdq + qdq + posdq) and fold_din[q][dinuc]
+// -- and the kernel does two shared-memory gathers per base instead of five global ones.
+//
+// Roofline: HBM, 3 B/base (seq + qual in, new qual out).  Same super-row thread mapping as the
+// build kernel (common.cuh): the cycle table is gathered at consecutive banks by consecutive lanes
+// and the dinuc table is replicated per lane, so both gathers are bank-conflict free.
+#pragma once
+#include "build.cuh"
+#include "common.cuh"
+
+namespace kbbq {
+
+struct ApplyArgs {
+    const uint8_t *seq, *qual;
+    uint8_t *out;
+    long long total_bytes;
+    Geom g;
+    int R, nq;
+    const entry_t *entries;
+    const unsigned int *seg;
+    const short *fold_cyc;  // [R][43][2L]
+    const short *fold_din;  // [R][43][32]
+    int *status;
+};
+
+template <int DREP>
+__global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(ApplyArgs a) {
+    extern __shared__ unsigned int smem[];
+    const Geom &g = a.g;
+    const int nqv = g.nqv, row = g.row;
+    int *t_cyc = reinterpret_cast<int *>(smem);  // [nqv][row]
+    int *t_din = t_cyc + nqv * row;              // [nqv][17][DREP]
+
+    const ThreadMap m = make_thread_map(g);
+    const int lane = threadIdx.x & 31;
+    const uint32_t minq4 = (uint32_t)g.minscore * ONE4;
+    const int qbase_pos = g.minscore * row;
+    const int din_lane = (lane & (DREP - 1)) - g.minscore * 17 * DREP;
+    const uint32_t nqlim4 = (uint32_t)(127 - (a.nq - 1)) * ONE4;  // q + this has bit 7 set iff q >= nq
+
+    const unsigned long long E = a.seg[a.R];
+    const unsigned long long lo = E * blockIdx.x / gridDim.x, hi = E * (blockIdx.x + 1) / gridDim.x;
+    uint32_t qbad = 0;
+
+    for (int rg = 0; rg < a.R; ++rg) {
+        unsigned long long s_lo = a.seg[rg], s_hi = a.seg[rg + 1];
+        if (s_hi <= lo) continue;
+        if (s_lo >= hi) break;
+        if (s_lo < lo) s_lo = lo;
+        if (s_hi > hi) s_hi = hi;
+
+        // stage this read group's folded tables
+        __syncthreads();
+        const int L2 = 2 * g.L;
+        const short *fc = a.fold_cyc + ((size_t)rg * NQ + g.minscore) * L2;
+        for (int i = threadIdx.x; i < nqv * L2; i += blockDim.x) {
+            const int q = i / L2, c2 = i - q * L2;
+            t_cyc[q * row + plane_pos(c2, g.sj)] = fc[i];
+        }
+        const short *fd = a.fold_din + ((size_t)rg * NQ + g.minscore) * 32;
+        for (int i = threadIdx.x; i < nqv * 17 * DREP; i += blockDim.x) {
+            const int cell = i / DREP, q = cell / 17, sl = cell - q * 17;
+            t_din[i] = fd[q * 32 + sl];
+        }
+        __syncthreads();
+
+        for (unsigned long long it = s_lo + m.grp; it < s_hi; it += g.ng) {
+            const entry_t e = __ldg(a.entries + it);
+            const uint32_t sr = (uint32_t)e;
+            const uint32_t rowbits = (uint32_t)(e >> 32);
+            const uint32_t mA = (rowbits >> m.rho0) & 1u, mB = (rowbits >> (m.rho0 + 1)) & 1u;
+            const uint32_t sA = (rowbits >> (4 + m.rho0)) & 1u, sB = (rowbits >> (5 + m.rho0)) & 1u;
+            const uint32_t am = (mA ? m.lo_mask : 0u) | (mB ? m.hi_mask : 0u);
+            const long long off = (long long)sr * g.srb + 4 * m.j;
+
+            uint32_t sw = 0, qw = 0;
+            if (am) {
+                sw = ld_word_guarded(a.seq, off, a.total_bytes);
+                qw = ld_word_guarded(a.qual, off, a.total_bytes);
+            }
+            const uint32_t code3 = (sw >> 1) & 0x07070707u;
+            uint32_t pv3 = __shfl_up_sync(0xFFFFFFFFu, code3 >> 24, 1);
+            if (lane == 0) pv3 = ((am & 0xFFu) && !m.first0) ? ((uint32_t)__ldg(a.seq + off - 1) >> 1) & 7u : 7u;
+            const uint32_t pc3 = __byte_perm(pv3, code3, 0x6540);
+
+            const uint32_t bad = ((qw + nqlim4) | qw) & H4 & am;  // q >= nq: IndexError in the reference
+            qbad |= bad;
+            const uint32_t vm = ((qw | H4) - minq4) & H4 & am & ~bad;
+            const uint32_t anyn = ((code3 | pc3) << 5) & H4;
+            const uint32_t dm = vm & ~anyn & m.notfirst;
+            // dinuc slot: natural-order code when valid, 16 (the pad slot) otherwise
+            const uint32_t dm8 = (dm >> 7) * 0xFFu;
+            const uint32_t din5 = ((((pc3 << 2) & 0x0C0C0C0Cu) | (code3 & 0x03030303u)) & dm8) | (0x10101010u & ~dm8);
+            const uint32_t shA = sA ? 16 : 0, shB = sB ? 16 : 0;
+
+            uint32_t res = qw;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (vm & (0x80u << (8 * b))) {
+                    const uint32_t qb = (qw >> (8 * b)) & 0xFFu;
+                    const bool inA = (m.lo_mask >> (8 * b)) & 1u;
+                    const uint32_t pos = (m.off[b] >> (inA ? shA : shB)) & 0xFFFFu;
+                    const uint32_t db = (din5 >> (8 * b)) & 0x1Fu;
+                    const int v = t_cyc[qb * row + pos - qbase_pos] + t_din[(qb * 17 + db) * DREP + din_lane];
+                    res = (res & ~(0xFFu << (8 * b))) | (((uint32_t)v & 0xFFu) << (8 * b));
+                }
+            }
+            if (am == 0xFFFFFFFFu && off + 4 <= a.total_bytes) {
+                *reinterpret_cast<unsigned int *>(a.out + off) = res;
+            } else if (am) {
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    if ((am >> (8 * b)) & 1u)
+                        if (off + b < a.total_bytes) a.out[off + b] = (uint8_t)(res >> (8 * b));
+            }
+        }
+    }
+    if (qbad) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
+}
+
+// Generic path (any L): one thread per base, folded tables gathered from global memory (L1/L2).
+struct ApplyGenericArgs {
+    const uint8_t *seq, *qual;
+    const uint16_t *rg;
+    const uint8_t *second;
+    uint8_t *out;
+    long long N;
+    int L, R, minscore, nq;
+    const short *fold_cyc, *fold_din;
+    int *status;
+};
+
+__global__ void apply_generic_kernel(ApplyGenericArgs a) {
+    const long long total = a.N * a.L;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / a.L;
+        const int c = (int)(i - r * a.L);
+        const unsigned int q = a.qual[i];
+        if ((int)q < a.minscore) { a.out[i] = (uint8_t)q; continue; }
+        if ((int)q >= a.nq) { atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE); a.out[i] = (uint8_t)q; continue; }
+        const unsigned int g = a.rg ? a.rg[r] : 0;
+        if (g >= (unsigned int)a.R) { atomicOr(a.status, KBBQ_FLAG_RG_RANGE); a.out[i] = (uint8_t)q; continue; }
+        const int c2 = (a.second && a.second[r]) ? 2 * a.L - 1 - c : c;
+        int slot = 16;
+        if (c > 0) {
+            const uint8_t s = a.seq[i], ps = a.seq[i - 1];
+            if (s != 'N' && ps != 'N') slot = (((ps >> 1) & 3) << 2) | ((s >> 1) & 3);
+        }
+        const size_t gq = (size_t)g * NQ + q;
+        const int v = a.fold_cyc[gq * (2 * a.L) + c2] + a.fold_din[gq * 32 + slot];
+        a.out[i] = (uint8_t)v;
+    }
+}
+
+inline size_t apply_smem_bytes(const Geom &g, int drep) {
+    return sizeof(int) * ((size_t)g.nqv * g.row + (size_t)g.nqv * 17 * drep);
+}
+
+}  // namespace kbbq

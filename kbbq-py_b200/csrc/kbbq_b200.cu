@@ -1,0 +1,618 @@
+// kbbq_b200.cu -- the C ABI of libkbbq_b200.so (see include/kbbq_b200.h).
+// One translation unit: kernels live in the .cuh files, this file validates arguments, picks the
+// kernel configuration and enqueues.  Compiled for sm_100a only.
+#include <algorithm>
+#include <mutex>
+#include <string.h>
+#include <vector>
+
+#include "apply.cuh"
+#include "build.cuh"
+#include "common.cuh"
+#include "model.cuh"
+#include "prepare.cuh"
+#include "synth.cuh"
+
+namespace kbbq {
+
+long long g_launches = 0;
+char g_last_cuda_error[256] = "";
+
+static std::once_flag g_const_once[64];
+
+static int upload_constants(int device) {
+    // per-device __constant__ images
+    int rc = KBBQ_OK;
+    auto up = [&]() -> int {
+        KBBQ_CUDA(cudaMemcpyToSymbol(c_lnp, KBBQ_LN_P, sizeof(double) * NQ));
+        KBBQ_CUDA(cudaMemcpyToSymbol(c_ln1mp, KBBQ_LN_1MP, sizeof(double) * NQ));
+        KBBQ_CUDA(cudaMemcpyToSymbol(c_prior, KBBQ_PRIOR, sizeof(double) * NQ));
+        KBBQ_CUDA(cudaMemcpyToSymbol(c_p, KBBQ_P, sizeof(double) * NQ));
+        KBBQ_CUDA(cudaMemcpyToSymbol(c_bound_hi, KBBQ_BOUND_HI, sizeof(double) * NQ));
+        KBBQ_CUDA(cudaMemcpyToSymbol(c_bound_lo, KBBQ_BOUND_LO, sizeof(double) * NQ));
+        return KBBQ_OK;
+    };
+    if (device < 0 || device >= 64) return up();
+    std::call_once(g_const_once[device], [&]() { rc = up(); });
+    return rc;
+}
+
+static int current_device_info(int *device, int *sms, int *max_smem) {
+    KBBQ_CUDA(cudaGetDevice(device));
+    static int s_sms[64], s_smem[64];
+    if (*device < 64 && s_sms[*device]) {
+        *sms = s_sms[*device];
+        *max_smem = s_smem[*device];
+        return KBBQ_OK;
+    }
+    KBBQ_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, *device));
+    KBBQ_CUDA(cudaDeviceGetAttribute(max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, *device));
+    if (*sms <= 0) *sms = KBBQ_SM_COUNT_FALLBACK;
+    if (*device < 64) { s_sms[*device] = *sms; s_smem[*device] = *max_smem; }
+    return KBBQ_OK;
+}
+
+static bool misaligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) != 0; }
+
+template <int DREP>
+static int launch_build_smem(const BuildArgs &a, int grid, size_t smem, cudaStream_t st) {
+    auto kern = build_smem_kernel<DREP, true>;
+    KBBQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, a.g.threads, smem, st>>>(a);
+    KBBQ_LAUNCHED();
+    return KBBQ_OK;
+}
+
+template <int DREP>
+static int launch_apply_smem(const ApplyArgs &a, int grid, size_t smem, cudaStream_t st) {
+    auto kern = apply_smem_kernel<DREP>;
+    KBBQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, a.g.threads, smem, st>>>(a);
+    KBBQ_LAUNCHED();
+    return KBBQ_OK;
+}
+
+}  // namespace kbbq
+
+using namespace kbbq;
+
+extern "C" {
+
+int kbbq_abi_version(void) { return 1; }
+
+const char *kbbq_strerror(int code) {
+    switch (code) {
+    case KBBQ_OK: return "ok";
+    case KBBQ_E_ARG: return "bad argument";
+    case KBBQ_E_CUDA: return "CUDA runtime error";
+    case KBBQ_E_WORKSPACE: return "workspace too small";
+    case KBBQ_E_DATA: return "input data error (see status flags)";
+    default: return "unknown error";
+    }
+}
+
+const char *kbbq_last_cuda_error(void) { return g_last_cuda_error; }
+
+int64_t kbbq_pos_table_elems(int L, int R) { return (int64_t)R * NQ * 2 * L; }
+int64_t kbbq_din_table_elems(int R) { return (int64_t)R * NQ * 16; }
+int64_t kbbq_launch_count(void) { return g_launches; }
+
+int kbbq_workspace_bytes(int64_t N, int L, int R, size_t *bytes) {
+    if (N < 0 || L < 1 || R < 1 || R > 65535 || !bytes) return KBBQ_E_ARG;
+    *bytes = carve_workspace(nullptr, N, L, R).bytes;
+    return KBBQ_OK;
+}
+
+int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,
+               const uint8_t *second, int64_t N, int L, int R, int minscore, int64_t *pos_errs,
+               int64_t *pos_total, int64_t *din_errs, int64_t *din_total, void *workspace,
+               size_t workspace_bytes, int *status, int path, void *stream) {
+    if (N < 0 || L < 1 || R < 1 || R > 65535 || minscore < 0 || minscore >= NQ) return KBBQ_E_ARG;
+    if (!pos_errs || !pos_total || !din_errs || !din_total || !status) return KBBQ_E_ARG;
+    if (N == 0) return KBBQ_OK;
+    if (!seq || !qual || !corr) return KBBQ_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int device, sms, max_smem;
+    int rc = current_device_info(&device, &sms, &max_smem);
+    if (rc) return rc;
+
+    Geom g;
+    bool smem_ok = path != 2 && make_geom(L, minscore, &g) && g.row < 65536 &&
+                   (uint64_t)((N + g.rps - 1) / g.rps) < 0xFFFFFFFFull &&
+                   !misaligned(seq, 4) && !misaligned(qual, 4) && !misaligned(corr, 4);
+    int drep = 32;
+    if (smem_ok) {
+        while (drep >= 1 && build_smem_bytes(g, drep) > (size_t)max_smem) drep >>= 1;
+        if (drep < 1) smem_ok = false;
+    }
+    if (!smem_ok) {
+        if (path == 1) return KBBQ_E_ARG;
+        BuildGenericArgs a = {seq, qual, corr, rg, second, N, L, R, minscore,
+                              (unsigned long long *)pos_errs, (unsigned long long *)pos_total,
+                              (unsigned long long *)din_errs, (unsigned long long *)din_total, status};
+        build_generic_kernel<<<sms * 8, 256, 0, st>>>(a);
+        KBBQ_LAUNCHED();
+        return KBBQ_OK;
+    }
+    Workspace w = carve_workspace(workspace, N, L, R);
+    if (!workspace || workspace_bytes < w.bytes) return KBBQ_E_WORKSPACE;
+    rc = run_prepare(rg, second, N, L, R, w, status, st);
+    if (rc) return rc;
+
+    BuildArgs a;
+    a.seq = seq; a.qual = qual; a.corr = corr; a.total_bytes = N * L; a.g = g; a.R = R;
+    a.entries = w.entries; a.seg = w.seg;
+    a.pos_errs = (unsigned long long *)pos_errs; a.pos_total = (unsigned long long *)pos_total;
+    a.din_errs = (unsigned long long *)din_errs; a.din_total = (unsigned long long *)din_total;
+    a.status = status;
+    const size_t smem = build_smem_bytes(g, drep);
+    switch (drep) {
+    case 32: return launch_build_smem<32>(a, sms, smem, st);
+    case 16: return launch_build_smem<16>(a, sms, smem, st);
+    case 8: return launch_build_smem<8>(a, sms, smem, st);
+    case 4: return launch_build_smem<4>(a, sms, smem, st);
+    case 2: return launch_build_smem<2>(a, sms, smem, st);
+    default: return launch_build_smem<1>(a, sms, smem, st);
+    }
+}
+
+int kbbq_marginals(const int64_t *pos_errs, const int64_t *pos_total, int L, int R, int64_t *q_errs,
+                   int64_t *q_total, int64_t *rg_errs, int64_t *rg_total, int64_t *meanq, void *stream) {
+    if (L < 1 || R < 1 || !pos_errs || !pos_total || !q_errs || !q_total || !rg_errs || !rg_total || !meanq)
+        return KBBQ_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int device;
+    KBBQ_CUDA(cudaGetDevice(&device));
+    int rc = upload_constants(device);
+    if (rc) return rc;
+    marginals_q_kernel<<<dim3(NQ, R), 128, 0, st>>>((const long long *)pos_errs, (const long long *)pos_total,
+                                                   2 * L, (long long *)q_errs, (long long *)q_total);
+    KBBQ_LAUNCHED();
+    marginals_rg_kernel<<<(R + 63) / 64, 64, 0, st>>>((const long long *)q_errs, (const long long *)q_total, R,
+                                                      (long long *)rg_errs, (long long *)rg_total, (long long *)meanq);
+    KBBQ_LAUNCHED();
+    return KBBQ_OK;
+}
+
+int kbbq_delta_q(const int64_t *prior_q, const int64_t *numerrs, const int64_t *numtotal, int64_t n,
+                 int64_t *delta, void *stream) {
+    if (n < 0 || (n > 0 && (!prior_q || !numerrs || !numtotal || !delta))) return KBBQ_E_ARG;
+    if (n == 0) return KBBQ_OK;
+    int device;
+    KBBQ_CUDA(cudaGetDevice(&device));
+    int rc = upload_constants(device);
+    if (rc) return rc;
+    delta_q_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (const long long *)prior_q, (const long long *)numerrs, (const long long *)numtotal, n, (long long *)delta);
+    KBBQ_LAUNCHED();
+    return KBBQ_OK;
+}
+
+int kbbq_get_delta_qs(const int64_t *meanq, const int64_t *rg_errs, const int64_t *rg_total,
+                      const int64_t *q_errs, const int64_t *q_total, const int64_t *pos_errs,
+                      const int64_t *pos_total, const int64_t *din_errs, const int64_t *din_total, int R,
+                      int nq, int ncyc, int ndin, int64_t *rgdq, int64_t *qdq, int64_t *posdq,
+                      int64_t *dindq, void *stream) {
+    if (R < 1 || nq < 1 || ncyc < 0 || ndin < 0) return KBBQ_E_ARG;
+    if (!meanq || !rg_errs || !rg_total || !q_errs || !q_total || !rgdq || !qdq) return KBBQ_E_ARG;
+    if ((ncyc && (!pos_errs || !pos_total || !posdq)) || !dindq || (ndin && (!din_errs || !din_total)))
+        return KBBQ_E_ARG;
+    int device;
+    KBBQ_CUDA(cudaGetDevice(&device));
+    int rc = upload_constants(device);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    DeltaArgs a = {(const long long *)meanq, (const long long *)rg_errs, (const long long *)rg_total,
+                   (const long long *)q_errs, (const long long *)q_total, (const long long *)pos_errs,
+                   (const long long *)pos_total, (const long long *)din_errs, (const long long *)din_total,
+                   R, nq, ncyc, ndin, (long long *)rgdq, (long long *)qdq, (long long *)posdq, (long long *)dindq};
+    delta_levels12_kernel<<<R, 64, 0, st>>>(a);
+    KBBQ_LAUNCHED();
+    const long long cells = (long long)R * nq * (ncyc + ndin + 1);
+    delta_level3_kernel<<<(unsigned)((cells + 127) / 128), 128, 0, st>>>(a);
+    KBBQ_LAUNCHED();
+    return KBBQ_OK;
+}
+
+int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, const uint8_t *second, int64_t N,
+               int L, int R, int minscore, const int64_t *meanq, const int64_t *rgdq, const int64_t *qdq,
+               const int64_t *posdq, const int64_t *dindq, int nq, int ndin1, uint8_t *out_qual,
+               void *workspace, size_t workspace_bytes, int *status, int path, void *stream) {
+    if (N < 0 || L < 1 || R < 1 || R > 65535 || minscore < 0 || minscore >= NQ) return KBBQ_E_ARG;
+    if (nq < 1 || nq > NQ || ndin1 < 16 || ndin1 > 64) return KBBQ_E_ARG;
+    if (!meanq || !rgdq || !qdq || !posdq || !dindq || !status) return KBBQ_E_ARG;
+    if (N == 0) return KBBQ_OK;
+    if (!seq || !qual || !out_qual) return KBBQ_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int device, sms, max_smem;
+    int rc = current_device_info(&device, &sms, &max_smem);
+    if (rc) return rc;
+    Workspace w = carve_workspace(workspace, N, L, R);
+    if (!workspace || workspace_bytes < w.bytes) return KBBQ_E_WORKSPACE;
+
+    const long long fold_cells = (long long)R * NQ * (2 * L + 32);
+    fold_kernel<<<(unsigned)((fold_cells + 255) / 256), 256, 0, st>>>(
+        (const long long *)meanq, (const long long *)rgdq, (const long long *)qdq, (const long long *)posdq,
+        (const long long *)dindq, R, nq, 2 * L, ndin1, w.fold_cyc, w.fold_din);
+    KBBQ_LAUNCHED();
+
+    Geom g;
+    bool smem_ok = path != 2 && make_geom(L, minscore, &g) && g.row < 65536 &&
+                   (uint64_t)((N + g.rps - 1) / g.rps) < 0xFFFFFFFFull &&
+                   !misaligned(seq, 4) && !misaligned(qual, 4) && !misaligned(out_qual, 4);
+    int drep = 32;
+    if (smem_ok) {
+        while (drep >= 1 && apply_smem_bytes(g, drep) > (size_t)max_smem) drep >>= 1;
+        if (drep < 1) smem_ok = false;
+    }
+    if (!smem_ok) {
+        if (path == 1) return KBBQ_E_ARG;
+        ApplyGenericArgs a = {seq, qual, rg, second, out_qual, N, L, R, minscore, nq, w.fold_cyc, w.fold_din, status};
+        apply_generic_kernel<<<sms * 8, 256, 0, st>>>(a);
+        KBBQ_LAUNCHED();
+        return KBBQ_OK;
+    }
+    rc = run_prepare(rg, second, N, L, R, w, status, st);
+    if (rc) return rc;
+    ApplyArgs a;
+    a.seq = seq; a.qual = qual; a.out = out_qual; a.total_bytes = N * L; a.g = g; a.R = R; a.nq = nq;
+    a.entries = w.entries; a.seg = w.seg; a.fold_cyc = w.fold_cyc; a.fold_din = w.fold_din; a.status = status;
+    const size_t smem = apply_smem_bytes(g, drep);
+    switch (drep) {
+    case 32: return launch_apply_smem<32>(a, sms, smem, st);
+    case 16: return launch_apply_smem<16>(a, sms, smem, st);
+    case 8: return launch_apply_smem<8>(a, sms, smem, st);
+    case 4: return launch_apply_smem<4>(a, sms, smem, st);
+    case 2: return launch_apply_smem<2>(a, sms, smem, st);
+    default: return launch_apply_smem<1>(a, sms, smem, st);
+    }
+}
+
+int kbbq_synth_reads(uint64_t seed, int64_t first_read, int64_t n, int L, int R, uint8_t *seq, uint8_t *qual,
+                     uint8_t *corr, uint16_t *rg, uint8_t *second, void *stream) {
+    if (n < 0 || L < 1 || R < 1 || R > 65535 || first_read < 0) return KBBQ_E_ARG;
+    if (n == 0) return KBBQ_OK;
+    if (!seq || !qual || !corr) return KBBQ_E_ARG;
+    int device, sms, max_smem;
+    int rc = current_device_info(&device, &sms, &max_smem);
+    if (rc) return rc;
+    synth_kernel<<<sms * 16, 256, 0, (cudaStream_t)stream>>>(seed, first_read, n, L, R, seq, qual, corr, rg, second);
+    KBBQ_LAUNCHED();
+    return KBBQ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Host-buffer entry points
+// ------------------------------------------------------------------------------------------------
+
+}  // extern "C"
+
+namespace {
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) { KBBQ_CUDA(cudaMalloc(&p, n ? n : 1)); return KBBQ_OK; }
+    template <class T> T *as() { return (T *)p; }
+};
+
+struct Streams {
+    cudaStream_t copy = nullptr, comp = nullptr;
+    std::vector<cudaEvent_t> ev;
+    ~Streams() {
+        for (auto e : ev) cudaEventDestroy(e);
+        if (copy) cudaStreamDestroy(copy);
+        if (comp) cudaStreamDestroy(comp);
+    }
+    int init() {
+        KBBQ_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+        KBBQ_CUDA(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
+        return KBBQ_OK;
+    }
+    int event(cudaEvent_t *e) {
+        KBBQ_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        ev.push_back(*e);
+        return KBBQ_OK;
+    }
+};
+
+#define KBBQ_TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+// Model step on device tables: marginals + deltas; layout of `model`:
+// [q_errs R*43 | q_total R*43 | rg_errs R | rg_total R | meanq R | rgdq R | qdq R*43 | posdq R*43*2L | dindq R*43*17]
+struct ModelPtrs {
+    int64_t *q_errs, *q_total, *rg_errs, *rg_total, *meanq, *rgdq, *qdq, *posdq, *dindq;
+    size_t elems;
+};
+ModelPtrs carve_model(int64_t *base, int L, int R) {
+    ModelPtrs m;
+    size_t o = 0;
+    m.q_errs = base + o; o += (size_t)R * NQ;
+    m.q_total = base + o; o += (size_t)R * NQ;
+    m.rg_errs = base + o; o += R;
+    m.rg_total = base + o; o += R;
+    m.meanq = base + o; o += R;
+    m.rgdq = base + o; o += R;
+    m.qdq = base + o; o += (size_t)R * NQ;
+    m.posdq = base + o; o += (size_t)R * NQ * 2 * L;
+    m.dindq = base + o; o += (size_t)R * NQ * 17;
+    m.elems = o;
+    return m;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kbbq_recalibrate_host(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,
+                          const uint8_t *second, int64_t N, int L, int R, int minscore, uint8_t *out_qual,
+                          int64_t *tables_host, int64_t *deltas_host, int *status_out, int device) {
+    if (N < 0 || L < 1 || R < 1 || R > 65535) return KBBQ_E_ARG;
+    if (N > 0 && (!seq || !qual || !corr || !out_qual)) return KBBQ_E_ARG;
+    KBBQ_CUDA(cudaSetDevice(device));
+    Streams S;
+    KBBQ_TRY(S.init());
+
+    const size_t npos = (size_t)R * NQ * 2 * L, ndin = (size_t)R * NQ * 16;
+    const size_t ntab = 2 * npos + 2 * ndin;
+    DevBuf d_tab, d_model, d_status;
+    KBBQ_TRY(d_tab.alloc(ntab * 8));
+    ModelPtrs mp = carve_model(nullptr, L, R);
+    KBBQ_TRY(d_model.alloc(mp.elems * 8));
+    mp = carve_model(d_model.as<int64_t>(), L, R);
+    KBBQ_TRY(d_status.alloc(sizeof(int)));
+    KBBQ_CUDA(cudaMemsetAsync(d_tab.p, 0, ntab * 8, S.comp));
+    KBBQ_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(int), S.comp));
+    int64_t *pe = d_tab.as<int64_t>(), *pt = pe + npos, *de = pt + npos, *dt = de + ndin;
+
+    // chunking: whole batch resident when it fits, otherwise two passes through rotating buffers
+    size_t free_b = 0, total_b = 0;
+    KBBQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const size_t per_read_resident = (size_t)4 * L + 3;
+    const bool resident = (double)N * per_read_resident < 0.8 * (double)free_b;
+    int64_t chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / L);   // ~256 MiB per array per chunk
+    chunk = (chunk + 15) / 16 * 16;                                    // keep chunk starts 16-byte aligned
+    if (chunk > N) chunk = std::max<int64_t>(N, 1);
+    const int64_t nchunks = N ? (N + chunk - 1) / chunk : 0;
+    const int nbuf = resident ? 1 : 2;
+    const int64_t buf_reads = resident ? N : chunk;
+
+    DevBuf d_seq[2], d_qual[2], d_corr[2], d_out[2], d_rg[2], d_sec[2], d_ws;
+    for (int b = 0; b < nbuf; ++b) {
+        KBBQ_TRY(d_seq[b].alloc((size_t)buf_reads * L));
+        KBBQ_TRY(d_qual[b].alloc((size_t)buf_reads * L));
+        KBBQ_TRY(d_corr[b].alloc((size_t)(resident ? chunk : buf_reads) * L));
+        KBBQ_TRY(d_out[b].alloc((size_t)(resident ? chunk : buf_reads) * L));
+        if (rg) KBBQ_TRY(d_rg[b].alloc((size_t)buf_reads * 2));
+        if (second) KBBQ_TRY(d_sec[b].alloc((size_t)buf_reads));
+    }
+    if (resident) {  // corrected reads and outputs still rotate through two chunk buffers
+        KBBQ_TRY(d_corr[1].alloc((size_t)chunk * L));
+        KBBQ_TRY(d_out[1].alloc((size_t)chunk * L));
+    }
+    size_t ws_bytes = 0;
+    KBBQ_TRY(kbbq_workspace_bytes(chunk, L, R, &ws_bytes));
+    KBBQ_TRY(d_ws.alloc(ws_bytes));
+
+    std::vector<cudaEvent_t> copied(nchunks), consumed(nchunks);
+    for (int64_t k = 0; k < nchunks; ++k) { KBBQ_TRY(S.event(&copied[k])); KBBQ_TRY(S.event(&consumed[k])); }
+
+    auto rd = [&](int64_t k) { return std::min(chunk, N - k * chunk); };
+    // ---- pass 1: H2D + build ----
+    for (int64_t k = 0; k < nchunks; ++k) {
+        const int b = resident ? 0 : (int)(k & 1), cb = (int)(k & 1);
+        const int64_t r0 = k * chunk, n = rd(k);
+        const size_t doff = resident ? (size_t)r0 * L : 0, roff = resident ? (size_t)r0 : 0;
+        if (k >= 2) KBBQ_CUDA(cudaStreamWaitEvent(S.copy, consumed[k - 2], 0));
+        KBBQ_CUDA(cudaMemcpyAsync(d_seq[b].as<uint8_t>() + doff, seq + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, S.copy));
+        KBBQ_CUDA(cudaMemcpyAsync(d_qual[b].as<uint8_t>() + doff, qual + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, S.copy));
+        KBBQ_CUDA(cudaMemcpyAsync(d_corr[cb].as<uint8_t>(), corr + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, S.copy));
+        if (rg) KBBQ_CUDA(cudaMemcpyAsync(d_rg[b].as<uint16_t>() + roff, rg + r0, (size_t)n * 2, cudaMemcpyHostToDevice, S.copy));
+        if (second) KBBQ_CUDA(cudaMemcpyAsync(d_sec[b].as<uint8_t>() + roff, second + r0, (size_t)n, cudaMemcpyHostToDevice, S.copy));
+        KBBQ_CUDA(cudaEventRecord(copied[k], S.copy));
+        KBBQ_CUDA(cudaStreamWaitEvent(S.comp, copied[k], 0));
+        KBBQ_TRY(kbbq_build(d_seq[b].as<uint8_t>() + doff, d_qual[b].as<uint8_t>() + doff, d_corr[cb].as<uint8_t>(),
+                            rg ? d_rg[b].as<uint16_t>() + roff : nullptr, second ? d_sec[b].as<uint8_t>() + roff : nullptr,
+                            n, L, R, minscore, pe, pt, de, dt, d_ws.p, ws_bytes, d_status.as<int>(), 0, S.comp));
+        KBBQ_CUDA(cudaEventRecord(consumed[k], S.comp));
+    }
+    // ---- model ----
+    KBBQ_TRY(kbbq_marginals(pe, pt, L, R, mp.q_errs, mp.q_total, mp.rg_errs, mp.rg_total, mp.meanq, S.comp));
+    KBBQ_TRY(kbbq_get_delta_qs(mp.meanq, mp.rg_errs, mp.rg_total, mp.q_errs, mp.q_total, pe, pt, de, dt, R, NQ,
+                               2 * L, 16, mp.rgdq, mp.qdq, mp.posdq, mp.dindq, S.comp));
+    if (tables_host) KBBQ_CUDA(cudaMemcpyAsync(tables_host, d_tab.p, ntab * 8, cudaMemcpyDeviceToHost, S.comp));
+    if (deltas_host)
+        KBBQ_CUDA(cudaMemcpyAsync(deltas_host, mp.meanq, ((size_t)2 * R + (size_t)R * NQ * (1 + 2 * L + 17)) * 8,
+                                  cudaMemcpyDeviceToHost, S.comp));
+    // ---- pass 2: (H2D) + apply + D2H ----
+    std::vector<cudaEvent_t> applied(nchunks), drained(nchunks), copied2(nchunks);
+    for (int64_t k = 0; k < nchunks; ++k) {
+        KBBQ_TRY(S.event(&applied[k])); KBBQ_TRY(S.event(&drained[k])); KBBQ_TRY(S.event(&copied2[k]));
+    }
+    cudaEvent_t model_done;
+    KBBQ_TRY(S.event(&model_done));
+    KBBQ_CUDA(cudaEventRecord(model_done, S.comp));
+    for (int64_t k = 0; k < nchunks; ++k) {
+        const int b = resident ? 0 : (int)(k & 1), ob = (int)(k & 1);
+        const int64_t r0 = k * chunk, n = rd(k);
+        const size_t doff = resident ? (size_t)r0 * L : 0, roff = resident ? (size_t)r0 : 0;
+        if (!resident) {
+            // the build pass finished with these buffers long ago; only the previous apply pass matters
+            if (k >= 2) KBBQ_CUDA(cudaStreamWaitEvent(S.copy, applied[k - 2], 0));
+            else KBBQ_CUDA(cudaStreamWaitEvent(S.copy, model_done, 0));
+            KBBQ_CUDA(cudaMemcpyAsync(d_seq[b].as<uint8_t>(), seq + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, S.copy));
+            KBBQ_CUDA(cudaMemcpyAsync(d_qual[b].as<uint8_t>(), qual + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, S.copy));
+            if (rg) KBBQ_CUDA(cudaMemcpyAsync(d_rg[b].as<uint16_t>(), rg + r0, (size_t)n * 2, cudaMemcpyHostToDevice, S.copy));
+            if (second) KBBQ_CUDA(cudaMemcpyAsync(d_sec[b].as<uint8_t>(), second + r0, (size_t)n, cudaMemcpyHostToDevice, S.copy));
+            KBBQ_CUDA(cudaEventRecord(copied2[k], S.copy));
+            KBBQ_CUDA(cudaStreamWaitEvent(S.comp, copied2[k], 0));
+        }
+        if (k >= 2) KBBQ_CUDA(cudaStreamWaitEvent(S.comp, drained[k - 2], 0));
+        KBBQ_TRY(kbbq_apply(d_seq[b].as<uint8_t>() + doff, d_qual[b].as<uint8_t>() + doff,
+                            rg ? d_rg[b].as<uint16_t>() + roff : nullptr, second ? d_sec[b].as<uint8_t>() + roff : nullptr,
+                            n, L, R, minscore, mp.meanq, mp.rgdq, mp.qdq, mp.posdq, mp.dindq, NQ, 17,
+                            d_out[ob].as<uint8_t>(), d_ws.p, ws_bytes, d_status.as<int>(), 0, S.comp));
+        KBBQ_CUDA(cudaEventRecord(applied[k], S.comp));
+        // D2H on the copy stream so that it overlaps the next chunk's apply (and H2D when streaming)
+        KBBQ_CUDA(cudaStreamWaitEvent(S.copy, applied[k], 0));
+        KBBQ_CUDA(cudaMemcpyAsync(out_qual + (size_t)r0 * L, d_out[ob].as<uint8_t>(), (size_t)n * L, cudaMemcpyDeviceToHost, S.copy));
+        KBBQ_CUDA(cudaEventRecord(drained[k], S.copy));
+    }
+    int st_host = 0;
+    KBBQ_CUDA(cudaStreamSynchronize(S.copy));
+    KBBQ_CUDA(cudaMemcpyAsync(&st_host, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, S.comp));
+    KBBQ_CUDA(cudaStreamSynchronize(S.comp));
+    if (status_out) *status_out = st_host;
+    return st_host ? KBBQ_E_DATA : KBBQ_OK;
+}
+
+int kbbq_build_host(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,
+                    const uint8_t *second, int64_t N, int L, int R, int minscore, int64_t *pos_errs,
+                    int64_t *pos_total, int64_t *din_errs, int64_t *din_total, int *status_out, int device) {
+    if (N < 0 || L < 1 || R < 1 || R > 65535) return KBBQ_E_ARG;
+    if (!pos_errs || !pos_total || !din_errs || !din_total) return KBBQ_E_ARG;
+    KBBQ_CUDA(cudaSetDevice(device));
+    const size_t npos = (size_t)R * NQ * 2 * L, ndin = (size_t)R * NQ * 16, nb = (size_t)N * L;
+    DevBuf d_seq, d_qual, d_corr, d_rg, d_sec, d_tab, d_ws, d_status;
+    KBBQ_TRY(d_seq.alloc(nb)); KBBQ_TRY(d_qual.alloc(nb)); KBBQ_TRY(d_corr.alloc(nb));
+    KBBQ_TRY(d_tab.alloc((2 * npos + 2 * ndin) * 8));
+    KBBQ_TRY(d_status.alloc(sizeof(int)));
+    size_t ws_bytes = 0;
+    KBBQ_TRY(kbbq_workspace_bytes(N, L, R, &ws_bytes));
+    KBBQ_TRY(d_ws.alloc(ws_bytes));
+    KBBQ_CUDA(cudaMemcpy(d_seq.p, seq, nb, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemcpy(d_qual.p, qual, nb, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemcpy(d_corr.p, corr, nb, cudaMemcpyHostToDevice));
+    if (rg) { KBBQ_TRY(d_rg.alloc((size_t)N * 2)); KBBQ_CUDA(cudaMemcpy(d_rg.p, rg, (size_t)N * 2, cudaMemcpyHostToDevice)); }
+    if (second) { KBBQ_TRY(d_sec.alloc((size_t)N)); KBBQ_CUDA(cudaMemcpy(d_sec.p, second, (size_t)N, cudaMemcpyHostToDevice)); }
+    KBBQ_CUDA(cudaMemset(d_tab.p, 0, (2 * npos + 2 * ndin) * 8));
+    KBBQ_CUDA(cudaMemset(d_status.p, 0, sizeof(int)));
+    int64_t *pe = d_tab.as<int64_t>(), *pt = pe + npos, *de = pt + npos, *dt = de + ndin;
+    KBBQ_TRY(kbbq_build(d_seq.as<uint8_t>(), d_qual.as<uint8_t>(), d_corr.as<uint8_t>(), rg ? d_rg.as<uint16_t>() : nullptr,
+                        second ? d_sec.as<uint8_t>() : nullptr, N, L, R, minscore, pe, pt, de, dt, d_ws.p, ws_bytes,
+                        d_status.as<int>(), 0, nullptr));
+    KBBQ_CUDA(cudaMemcpy(pos_errs, pe, npos * 8, cudaMemcpyDeviceToHost));
+    KBBQ_CUDA(cudaMemcpy(pos_total, pt, npos * 8, cudaMemcpyDeviceToHost));
+    KBBQ_CUDA(cudaMemcpy(din_errs, de, ndin * 8, cudaMemcpyDeviceToHost));
+    KBBQ_CUDA(cudaMemcpy(din_total, dt, ndin * 8, cudaMemcpyDeviceToHost));
+    int st_host = 0;
+    KBBQ_CUDA(cudaMemcpy(&st_host, d_status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (status_out) *status_out = st_host;
+    return st_host ? KBBQ_E_DATA : KBBQ_OK;
+}
+
+int kbbq_apply_host(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, const uint8_t *second, int64_t N,
+                    int L, int R, int minscore, const int64_t *meanq, const int64_t *rgdq, const int64_t *qdq,
+                    const int64_t *posdq, const int64_t *dindq, int nq, int ndin1, uint8_t *out_qual,
+                    int *status_out, int device) {
+    if (N < 0 || L < 1 || R < 1 || R > 65535 || nq < 1 || nq > NQ || ndin1 < 16 || ndin1 > 64) return KBBQ_E_ARG;
+    KBBQ_CUDA(cudaSetDevice(device));
+    const size_t nb = (size_t)N * L;
+    const size_t n_q = (size_t)R * nq, n_pos = n_q * 2 * L, n_din = n_q * ndin1;
+    DevBuf d_seq, d_qual, d_out, d_rg, d_sec, d_dq, d_ws, d_status;
+    KBBQ_TRY(d_seq.alloc(nb)); KBBQ_TRY(d_qual.alloc(nb)); KBBQ_TRY(d_out.alloc(nb));
+    KBBQ_TRY(d_dq.alloc((2 * (size_t)R + n_q + n_pos + n_din) * 8));
+    KBBQ_TRY(d_status.alloc(sizeof(int)));
+    size_t ws_bytes = 0;
+    KBBQ_TRY(kbbq_workspace_bytes(N, L, R, &ws_bytes));
+    KBBQ_TRY(d_ws.alloc(ws_bytes));
+    int64_t *d_meanq = d_dq.as<int64_t>(), *d_rgdq = d_meanq + R, *d_qdq = d_rgdq + R, *d_posdq = d_qdq + n_q,
+            *d_dindq = d_posdq + n_pos;
+    KBBQ_CUDA(cudaMemcpy(d_seq.p, seq, nb, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemcpy(d_qual.p, qual, nb, cudaMemcpyHostToDevice));
+    if (rg) { KBBQ_TRY(d_rg.alloc((size_t)N * 2)); KBBQ_CUDA(cudaMemcpy(d_rg.p, rg, (size_t)N * 2, cudaMemcpyHostToDevice)); }
+    if (second) { KBBQ_TRY(d_sec.alloc((size_t)N)); KBBQ_CUDA(cudaMemcpy(d_sec.p, second, (size_t)N, cudaMemcpyHostToDevice)); }
+    KBBQ_CUDA(cudaMemcpy(d_meanq, meanq, (size_t)R * 8, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemcpy(d_rgdq, rgdq, (size_t)R * 8, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemcpy(d_qdq, qdq, n_q * 8, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemcpy(d_posdq, posdq, n_pos * 8, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemcpy(d_dindq, dindq, n_din * 8, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemset(d_status.p, 0, sizeof(int)));
+    KBBQ_TRY(kbbq_apply(d_seq.as<uint8_t>(), d_qual.as<uint8_t>(), rg ? d_rg.as<uint16_t>() : nullptr,
+                        second ? d_sec.as<uint8_t>() : nullptr, N, L, R, minscore, d_meanq, d_rgdq, d_qdq, d_posdq,
+                        d_dindq, nq, ndin1, d_out.as<uint8_t>(), d_ws.p, ws_bytes, d_status.as<int>(), 0, nullptr));
+    KBBQ_CUDA(cudaMemcpy(out_qual, d_out.p, nb, cudaMemcpyDeviceToHost));
+    int st_host = 0;
+    KBBQ_CUDA(cudaMemcpy(&st_host, d_status.p, sizeof(int), cudaMemcpyDeviceToHost));
+    if (status_out) *status_out = st_host;
+    return st_host ? KBBQ_E_DATA : KBBQ_OK;
+}
+
+int kbbq_get_delta_qs_host(const int64_t *meanq, const int64_t *rg_errs, const int64_t *rg_total,
+                           const int64_t *q_errs, const int64_t *q_total, const int64_t *pos_errs,
+                           const int64_t *pos_total, const int64_t *din_errs, const int64_t *din_total, int R,
+                           int nq, int ncyc, int ndin, int64_t *rgdq, int64_t *qdq, int64_t *posdq,
+                           int64_t *dindq, int device) {
+    if (R < 1 || nq < 1 || ncyc < 0 || ndin < 0) return KBBQ_E_ARG;
+    KBBQ_CUDA(cudaSetDevice(device));
+    const size_t n_q = (size_t)R * nq, n_pos = n_q * ncyc, n_din = n_q * ndin, n_din1 = n_q * (ndin + 1);
+    const size_t in_elems = 3 * (size_t)R + 2 * n_q + 2 * n_pos + 2 * n_din;
+    const size_t out_elems = (size_t)R + n_q + n_pos + n_din1;
+    DevBuf d;
+    KBBQ_TRY(d.alloc((in_elems + out_elems) * 8));
+    int64_t *p = d.as<int64_t>();
+    int64_t *d_meanq = p; p += R;
+    int64_t *d_rge = p; p += R;
+    int64_t *d_rgt = p; p += R;
+    int64_t *d_qe = p; p += n_q;
+    int64_t *d_qt = p; p += n_q;
+    int64_t *d_pe = p; p += n_pos;
+    int64_t *d_pt = p; p += n_pos;
+    int64_t *d_de = p; p += n_din;
+    int64_t *d_dt = p; p += n_din;
+    int64_t *o_rg = p; p += R;
+    int64_t *o_q = p; p += n_q;
+    int64_t *o_pos = p; p += n_pos;
+    int64_t *o_din = p;
+    const struct { int64_t *dst; const int64_t *src; size_t n; } ups[] = {
+        {d_meanq, meanq, (size_t)R}, {d_rge, rg_errs, (size_t)R}, {d_rgt, rg_total, (size_t)R}, {d_qe, q_errs, n_q},
+        {d_qt, q_total, n_q}, {d_pe, pos_errs, n_pos}, {d_pt, pos_total, n_pos}, {d_de, din_errs, n_din},
+        {d_dt, din_total, n_din}};
+    for (auto &u : ups)
+        if (u.n) KBBQ_CUDA(cudaMemcpy(u.dst, u.src, u.n * 8, cudaMemcpyHostToDevice));
+    KBBQ_TRY(kbbq_get_delta_qs(d_meanq, d_rge, d_rgt, d_qe, d_qt, d_pe, d_pt, d_de, d_dt, R, nq, ncyc, ndin, o_rg, o_q,
+                               o_pos, o_din, nullptr));
+    KBBQ_CUDA(cudaMemcpy(rgdq, o_rg, (size_t)R * 8, cudaMemcpyDeviceToHost));
+    KBBQ_CUDA(cudaMemcpy(qdq, o_q, n_q * 8, cudaMemcpyDeviceToHost));
+    if (n_pos) KBBQ_CUDA(cudaMemcpy(posdq, o_pos, n_pos * 8, cudaMemcpyDeviceToHost));
+    KBBQ_CUDA(cudaMemcpy(dindq, o_din, n_din1 * 8, cudaMemcpyDeviceToHost));
+    return KBBQ_OK;
+}
+
+int kbbq_delta_q_host(const int64_t *prior_q, const int64_t *numerrs, const int64_t *numtotal, int64_t n,
+                      int64_t *delta, int device) {
+    if (n < 0) return KBBQ_E_ARG;
+    if (n == 0) return KBBQ_OK;
+    KBBQ_CUDA(cudaSetDevice(device));
+    DevBuf d;
+    KBBQ_TRY(d.alloc((size_t)n * 4 * 8));
+    int64_t *p = d.as<int64_t>();
+    KBBQ_CUDA(cudaMemcpy(p, prior_q, (size_t)n * 8, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemcpy(p + n, numerrs, (size_t)n * 8, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemcpy(p + 2 * n, numtotal, (size_t)n * 8, cudaMemcpyHostToDevice));
+    KBBQ_TRY(kbbq_delta_q(p, p + n, p + 2 * n, n, p + 3 * n, nullptr));
+    KBBQ_CUDA(cudaMemcpy(delta, p + 3 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return KBBQ_OK;
+}
+
+int kbbq_marginals_host(const int64_t *pos_errs, const int64_t *pos_total, int L, int R, int64_t *q_errs,
+                        int64_t *q_total, int64_t *rg_errs, int64_t *rg_total, int64_t *meanq, int device) {
+    if (L < 1 || R < 1) return KBBQ_E_ARG;
+    KBBQ_CUDA(cudaSetDevice(device));
+    const size_t npos = (size_t)R * NQ * 2 * L, n_q = (size_t)R * NQ;
+    DevBuf d;
+    KBBQ_TRY(d.alloc((2 * npos + 2 * n_q + 3 * (size_t)R) * 8));
+    int64_t *pe = d.as<int64_t>(), *pt = pe + npos, *qe = pt + npos, *qt = qe + n_q, *ge = qt + n_q, *gt = ge + R,
+            *mq = gt + R;
+    KBBQ_CUDA(cudaMemcpy(pe, pos_errs, npos * 8, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemcpy(pt, pos_total, npos * 8, cudaMemcpyHostToDevice));
+    KBBQ_TRY(kbbq_marginals(pe, pt, L, R, qe, qt, ge, gt, mq, nullptr));
+    KBBQ_CUDA(cudaMemcpy(q_errs, qe, n_q * 8, cudaMemcpyDeviceToHost));
+    KBBQ_CUDA(cudaMemcpy(q_total, qt, n_q * 8, cudaMemcpyDeviceToHost));
+    KBBQ_CUDA(cudaMemcpy(rg_errs, ge, (size_t)R * 8, cudaMemcpyDeviceToHost));
+    KBBQ_CUDA(cudaMemcpy(rg_total, gt, (size_t)R * 8, cudaMemcpyDeviceToHost));
+    KBBQ_CUDA(cudaMemcpy(meanq, mq, (size_t)R * 8, cudaMemcpyDeviceToHost));
+    return KBBQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,204 @@
+"""ctypes binding of libkbbq_b200.so (include/kbbq_b200.h).
+
+This is the only door between the Python API mirror and the CUDA kernels.  There is no CPU
+fallback: if the shared library is missing, or a compute entry point is called without a CUDA
+device, the call raises -- it never silently computes on the host.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libkbbq_b200.so")
+
+NQ = 43
+FLAG_QUAL_RANGE, FLAG_BAD_BASE, FLAG_RG_RANGE = 1, 2, 4
+E_DATA = -4
+
+_lib = None
+
+# name -> (restype, argtypes); must list every symbol include/kbbq_b200.h declares
+_vp, _i, _i64, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+SIGNATURES = {
+    "kbbq_abi_version": (_i, []),
+    "kbbq_strerror": (C.c_char_p, [_i]),
+    "kbbq_last_cuda_error": (C.c_char_p, []),
+    "kbbq_pos_table_elems": (_i64, [_i, _i]),
+    "kbbq_din_table_elems": (_i64, [_i]),
+    "kbbq_workspace_bytes": (_i, [_i64, _i, _i, C.POINTER(_sz)]),
+    "kbbq_build": (_i, [_vp] * 5 + [_i64, _i, _i, _i] + [_vp] * 4 + [_vp, _sz, _vp, _i, _vp]),
+    "kbbq_marginals": (_i, [_vp, _vp, _i, _i] + [_vp] * 5 + [_vp]),
+    "kbbq_delta_q": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "kbbq_get_delta_qs": (_i, [_vp] * 9 + [_i, _i, _i, _i] + [_vp] * 4 + [_vp]),
+    "kbbq_apply": (_i, [_vp] * 4 + [_i64, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, _vp, _sz, _vp, _i, _vp]),
+    "kbbq_recalibrate_host": (_i, [_vp] * 5 + [_i64, _i, _i, _i] + [_vp] * 3 + [C.POINTER(_i), _i]),
+    "kbbq_build_host": (_i, [_vp] * 5 + [_i64, _i, _i, _i] + [_vp] * 4 + [C.POINTER(_i), _i]),
+    "kbbq_apply_host": (_i, [_vp] * 4 + [_i64, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, C.POINTER(_i), _i]),
+    "kbbq_get_delta_qs_host": (_i, [_vp] * 9 + [_i, _i, _i, _i] + [_vp] * 4 + [_i]),
+    "kbbq_delta_q_host": (_i, [_vp, _vp, _vp, _i64, _vp, _i]),
+    "kbbq_marginals_host": (_i, [_vp, _vp, _i, _i] + [_vp] * 5 + [_i]),
+    "kbbq_synth_reads": (_i, [C.c_uint64, _i64, _i64, _i, _i] + [_vp] * 5 + [_vp]),
+    "kbbq_launch_count": (_i64, []),
+}
+
+
+class KbbqNativeError(RuntimeError):
+    """The CUDA library is missing, or a CUDA / argument error came back from it."""
+
+
+def lib():
+    """Load libkbbq_b200.so (once). Raises if it has not been built -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise KbbqNativeError(
+                "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or make -C kbbq-py_b200/csrc). kbbq_b200 has no CPU fallback." % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, status=0):
+    if rc == 0:
+        return
+    if rc == E_DATA:
+        raise_for_status(status)
+    L = lib()
+    msg = L.kbbq_strerror(rc).decode()
+    if rc == -2:
+        msg += ": " + L.kbbq_last_cuda_error().decode()
+    raise KbbqNativeError("libkbbq_b200: %s (%d)" % (msg, rc))
+
+
+def raise_for_status(status):
+    """Map the device status word onto the exceptions the reference raises for the same input."""
+    if status & FLAG_QUAL_RANGE:
+        # kbbq/recalibrate.py:115-119: a quality > 42 indexes past the 43-row tables
+        raise IndexError("quality score out of range for the covariate tables (max 42)")
+    if status & FLAG_BAD_BASE:
+        # kbbq/compare_reads.py:224: Dinucleotide.vecget returns None for a non-ACGT dinucleotide
+        raise TypeError("sequence contains a base outside A, C, G, T, N")
+    if status & FLAG_RG_RANGE:
+        raise IndexError("read group index out of range")
+
+
+def ptr(a):
+    """Host pointer of a C-contiguous numpy array (None -> NULL)."""
+    if a is None:
+        return None
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def u8(a):
+    return np.ascontiguousarray(a, dtype=np.uint8)
+
+
+def i64(a):
+    return np.ascontiguousarray(a, dtype=np.int64)
+
+
+DEVICE = int(os.environ.get("KBBQ_DEVICE", os.environ.get("LOCAL_RANK", "0")))
+
+
+# ---- host-buffer wrappers (numpy in, numpy out) ---------------------------------------------
+
+def build_host(seq, qual, corr, rg, second, L, R, minscore=6, device=None):
+    seq, qual, corr = u8(seq).ravel(), u8(qual).ravel(), u8(corr).ravel()
+    N = seq.size // L
+    assert seq.size == qual.size == corr.size == N * L
+    rg = None if rg is None else np.ascontiguousarray(rg, dtype=np.uint16)
+    second = None if second is None else u8(second)
+    pe, pt = np.zeros((R, NQ, 2 * L), np.int64), np.zeros((R, NQ, 2 * L), np.int64)
+    de, dt = np.zeros((R, NQ, 16), np.int64), np.zeros((R, NQ, 16), np.int64)
+    st = C.c_int(0)
+    rc = lib().kbbq_build_host(ptr(seq), ptr(qual), ptr(corr), ptr(rg), ptr(second), N, L, R, minscore,
+                               ptr(pe), ptr(pt), ptr(de), ptr(dt), C.byref(st),
+                               DEVICE if device is None else device)
+    check(rc, st.value)
+    return pe, pt, de, dt
+
+
+def marginals_host(pos_errs, pos_total, device=None):
+    pos_errs, pos_total = i64(pos_errs), i64(pos_total)
+    R, nq, L2 = pos_total.shape
+    assert nq == NQ
+    q_e, q_t = np.zeros((R, NQ), np.int64), np.zeros((R, NQ), np.int64)
+    g_e, g_t, mq = np.zeros(R, np.int64), np.zeros(R, np.int64), np.zeros(R, np.int64)
+    check(lib().kbbq_marginals_host(ptr(pos_errs), ptr(pos_total), L2 // 2, R, ptr(q_e), ptr(q_t),
+                                    ptr(g_e), ptr(g_t), ptr(mq), DEVICE if device is None else device))
+    return mq, g_e, g_t, q_e, q_t
+
+
+def delta_q_host(prior_q, numerrs, numtotal, device=None):
+    prior_q, numerrs, numtotal = i64(prior_q), i64(numerrs), i64(numtotal)
+    out = np.zeros(prior_q.shape, np.int64)
+    check(lib().kbbq_delta_q_host(ptr(prior_q), ptr(numerrs), ptr(numtotal), prior_q.size, ptr(out),
+                                  DEVICE if device is None else device))
+    return out
+
+
+def get_delta_qs_host(meanq, rg_errs, rg_total, q_errs, q_total, pos_errs, pos_total, din_errs, din_total,
+                      device=None):
+    arrs = [i64(a) for a in (meanq, rg_errs, rg_total, q_errs, q_total, pos_errs, pos_total, din_errs, din_total)]
+    R, nq = arrs[4].shape
+    ncyc, ndin = arrs[6].shape[2], arrs[8].shape[2]
+    rgdq, qdq = np.zeros(R, np.int64), np.zeros((R, nq), np.int64)
+    posdq, dindq = np.zeros((R, nq, ncyc), np.int64), np.zeros((R, nq, ndin + 1), np.int64)
+    check(lib().kbbq_get_delta_qs_host(*[ptr(a) for a in arrs], R, nq, ncyc, ndin, ptr(rgdq), ptr(qdq),
+                                       ptr(posdq), ptr(dindq), DEVICE if device is None else device))
+    return rgdq, qdq, posdq, dindq
+
+
+def apply_host(seq, qual, rg, second, L, R, meanq, rgdq, qdq, posdq, dindq, minscore=6, device=None):
+    seq, qual = u8(seq).ravel(), u8(qual).ravel()
+    N = seq.size // L
+    rg = None if rg is None else np.ascontiguousarray(rg, dtype=np.uint16)
+    second = None if second is None else u8(second)
+    meanq, rgdq, qdq, posdq, dindq = [i64(a) for a in (meanq, rgdq, qdq, posdq, dindq)]
+    nq, ndin1 = qdq.shape[1], dindq.shape[2]
+    assert posdq.shape == (R, nq, 2 * L) and dindq.shape[:2] == (R, nq)
+    out = np.zeros((N, L), np.uint8)
+    st = C.c_int(0)
+    rc = lib().kbbq_apply_host(ptr(seq), ptr(qual), ptr(rg), ptr(second), N, L, R, minscore, ptr(meanq),
+                               ptr(rgdq), ptr(qdq), ptr(posdq), ptr(dindq), nq, ndin1, ptr(out),
+                               C.byref(st), DEVICE if device is None else device)
+    check(rc, st.value)
+    return out
+
+
+def recalibrate_host(seq, qual, corr, rg, second, L, R, minscore=6, want_tables=False, device=None, out=None):
+    """Whole path on host buffers; returns out_qual [N, L] u8 (and tables / deltas if asked)."""
+    seq, qual, corr = u8(seq).ravel(), u8(qual).ravel(), u8(corr).ravel()
+    N = seq.size // L
+    rg = None if rg is None else np.ascontiguousarray(rg, dtype=np.uint16)
+    second = None if second is None else u8(second)
+    if out is None:
+        out = np.zeros((N, L), np.uint8)
+    tables = deltas = None
+    if want_tables:
+        tables = np.zeros(2 * R * NQ * 2 * L + 2 * R * NQ * 16, np.int64)
+        deltas = np.zeros(2 * R + R * NQ * (1 + 2 * L + 17), np.int64)
+    st = C.c_int(0)
+    rc = lib().kbbq_recalibrate_host(ptr(seq), ptr(qual), ptr(corr), ptr(rg), ptr(second), N, L, R, minscore,
+                                     ptr(out), ptr(tables), ptr(deltas), C.byref(st),
+                                     DEVICE if device is None else device)
+    check(rc, st.value)
+    if not want_tables:
+        return out
+    npos, ndin = R * NQ * 2 * L, R * NQ * 16
+    tabs = (tables[:npos].reshape(R, NQ, 2 * L), tables[npos:2 * npos].reshape(R, NQ, 2 * L),
+            tables[2 * npos:2 * npos + ndin].reshape(R, NQ, 16), tables[2 * npos + ndin:].reshape(R, NQ, 16))
+    o = 0
+    meanq = deltas[o:o + R]; o += R
+    rgdq = deltas[o:o + R]; o += R
+    qdq = deltas[o:o + R * NQ].reshape(R, NQ); o += R * NQ
+    posdq = deltas[o:o + npos].reshape(R, NQ, 2 * L); o += npos
+    dindq = deltas[o:].reshape(R, NQ, 17)
+    return out, tabs, (meanq, rgdq, qdq, posdq, dindq)

@@ -1,0 +1,138 @@
+"""Device-resident driver of the hot path: torch tensors in HBM, kernels through the C ABI.
+
+torch is plumbing only (allocation, streams, torch.distributed); every kernel launched here is
+one of libkbbq_b200.so's.  This is what a batch driver (and bench.py) uses when the packed reads
+already live on the GPU; the host-buffer path is kbbq._native.recalibrate_host.
+
+Multi-GPU: reads shard by rank, each rank builds partial int64 tables, ONE
+all-reduce (sum) over the packed table buffer makes them global, every rank recomputes the deltas
+deterministically from the reduced integers (so no broadcast is needed) and applies them to its
+own shard.  Integer sums make the result independent of the number of ranks.
+"""
+import ctypes as C
+
+import torch
+
+from . import _native
+from . import parallel
+
+NQ = _native.NQ
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class DeviceRecalibrator:
+    """Owns the tables, model buffers and workspace for batches of up to `max_reads` reads."""
+
+    def __init__(self, L, R=1, max_reads=0, minscore=6, device=None, process_group=None):
+        if not torch.cuda.is_available():
+            raise _native.KbbqNativeError("no CUDA device: kbbq_b200 has no CPU fallback")
+        self.lib = _native.lib()
+        self.L, self.R, self.minscore = int(L), int(R), int(minscore)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.pg = process_group
+        npos, ndin = R * NQ * 2 * L, R * NQ * 16
+        with torch.cuda.device(self.device):
+            # one packed buffer [pos_errs | pos_total | din_errs | din_total]: one collective sums it
+            self.tables = torch.zeros(2 * npos + 2 * ndin, dtype=torch.int64, device=self.device)
+            self.pos_errs = self.tables[:npos].view(R, NQ, 2 * L)
+            self.pos_total = self.tables[npos:2 * npos].view(R, NQ, 2 * L)
+            self.din_errs = self.tables[2 * npos:2 * npos + ndin].view(R, NQ, 16)
+            self.din_total = self.tables[2 * npos + ndin:].view(R, NQ, 16)
+            self.q_errs = torch.zeros(R, NQ, dtype=torch.int64, device=self.device)
+            self.q_total = torch.zeros(R, NQ, dtype=torch.int64, device=self.device)
+            self.rg_errs = torch.zeros(R, dtype=torch.int64, device=self.device)
+            self.rg_total = torch.zeros(R, dtype=torch.int64, device=self.device)
+            self.meanq = torch.zeros(R, dtype=torch.int64, device=self.device)
+            self.rgdq = torch.zeros(R, dtype=torch.int64, device=self.device)
+            self.qdq = torch.zeros(R, NQ, dtype=torch.int64, device=self.device)
+            self.posdq = torch.zeros(R, NQ, 2 * L, dtype=torch.int64, device=self.device)
+            self.dindq = torch.zeros(R, NQ, 17, dtype=torch.int64, device=self.device)
+            self.status = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.workspace = None
+        self.ws_reads = -1
+        self._ensure_workspace(max_reads)
+
+    def _ensure_workspace(self, n_reads):
+        if n_reads <= self.ws_reads:
+            return
+        nbytes = C.c_size_t(0)
+        _native.check(self.lib.kbbq_workspace_bytes(n_reads, self.L, self.R, C.byref(nbytes)))
+        self.workspace = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=self.device)
+        self.ws_bytes = nbytes.value
+        self.ws_reads = n_reads
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self):
+        self.tables.zero_()
+        self.status.zero_()
+
+    def build(self, seq, qual, corr, rg=None, second=None, path=0):
+        """Accumulate one batch into the tables (kbbq_build). Tensors: u8 [N, L] (rg int16/uint16 [N])."""
+        N = seq.numel() // self.L
+        self._ensure_workspace(N)
+        rc = self.lib.kbbq_build(_p(seq), _p(qual), _p(corr), _p(rg), _p(second), N, self.L, self.R, self.minscore,
+                                 _p(self.pos_errs), _p(self.pos_total), _p(self.din_errs), _p(self.din_total),
+                                 _p(self.workspace), self.ws_bytes, _p(self.status), path, self._stream())
+        _native.check(rc)
+
+    def allreduce(self):
+        """Sum the partial tables over all ranks: the one collective of the path."""
+        parallel.allreduce_tables(self.tables, self.pg)
+
+    def model(self):
+        """marginals + meanq + hierarchical delta tables (kbbq_marginals, kbbq_get_delta_qs)."""
+        L, R = self.L, self.R
+        _native.check(self.lib.kbbq_marginals(_p(self.pos_errs), _p(self.pos_total), L, R, _p(self.q_errs),
+                                              _p(self.q_total), _p(self.rg_errs), _p(self.rg_total),
+                                              _p(self.meanq), self._stream()))
+        _native.check(self.lib.kbbq_get_delta_qs(_p(self.meanq), _p(self.rg_errs), _p(self.rg_total),
+                                                 _p(self.q_errs), _p(self.q_total), _p(self.pos_errs),
+                                                 _p(self.pos_total), _p(self.din_errs), _p(self.din_total),
+                                                 R, NQ, 2 * L, 16, _p(self.rgdq), _p(self.qdq), _p(self.posdq),
+                                                 _p(self.dindq), self._stream()))
+
+    def apply(self, seq, qual, out, rg=None, second=None, path=0):
+        """Write recalibrated qualities of one batch into `out` (kbbq_apply)."""
+        N = seq.numel() // self.L
+        self._ensure_workspace(N)
+        rc = self.lib.kbbq_apply(_p(seq), _p(qual), _p(rg), _p(second), N, self.L, self.R, self.minscore,
+                                 _p(self.meanq), _p(self.rgdq), _p(self.qdq), _p(self.posdq), _p(self.dindq),
+                                 NQ, 17, _p(out), _p(self.workspace), self.ws_bytes, _p(self.status), path,
+                                 self._stream())
+        _native.check(rc)
+
+    def check_status(self):
+        """Synchronise and raise the reference's exception for any data error seen on the device."""
+        st = int(self.status.item())
+        if st:
+            _native.raise_for_status(st)
+
+    def covariate_arrays(self):
+        """The reference's 9-tuple (kbbq/recalibrate.py:121) as host numpy arrays."""
+        self.model()
+        return tuple(t.cpu().numpy().copy() for t in (self.meanq, self.rg_errs, self.rg_total, self.q_errs,
+                                                      self.q_total, self.pos_errs, self.pos_total,
+                                                      self.din_errs, self.din_total))
+
+    def delta_qs(self):
+        return tuple(t.cpu().numpy().copy() for t in (self.rgdq, self.qdq, self.posdq, self.dindq))
+
+
+def synth_reads(seed, first_read, n, L, R, device=None, want_corr=True):
+    """Counter-based synthetic reads generated on the GPU (kbbq_synth_reads): bench / test input."""
+    lib = _native.lib()
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    seq = torch.empty(n, L, dtype=torch.uint8, device=dev)
+    qual = torch.empty(n, L, dtype=torch.uint8, device=dev)
+    corr = torch.empty(n, L, dtype=torch.uint8, device=dev)
+    rg = torch.empty(n, dtype=torch.int16, device=dev)
+    second = torch.empty(n, dtype=torch.uint8, device=dev)
+    rc = lib.kbbq_synth_reads(seed, first_read, n, L, R, _p(seq), _p(qual), _p(corr), _p(rg), _p(second),
+                              C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _native.check(rc)
+    return seq, qual, corr, rg, second

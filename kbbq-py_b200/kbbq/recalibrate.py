@@ -1,0 +1,85 @@
+"""Mirror of the reference's kbbq/recalibrate.py -- the driver of the FASTQ recalibration path.
+
+Same functions, signatures, return order and exceptions; the per-read Python loops of the
+reference (kbbq/recalibrate.py:56-119 and :141-156) become one packed batch handed to the CUDA
+kernels through the C ABI (include/kbbq_b200.h).
+"""
+import sys
+
+import numpy as np
+
+from . import _native
+from . import compare_reads as utils
+from .batch import ReadBatch
+from .gatk import applybqsr
+
+
+def find_corrected_sites(uncorr_read, corr_read):
+    """reference: kbbq/recalibrate.py:13-20 -- raw character comparison of one read pair."""
+    assert corr_read.name.startswith(uncorr_read.name)
+    uncorr_seq = np.array(list(uncorr_read.sequence), dtype=np.str_)
+    corr_seq = np.array(list(corr_read.sequence), dtype=np.str_)
+    return (uncorr_seq != corr_seq)
+
+
+def _tables_from_batch(batch, minscore=6):
+    if batch.N == 0:
+        # the reference returns zero-length arrays when there are no reads (kbbq/recalibrate.py:45-54)
+        z = np.zeros(0, dtype=np.int64)
+        return (utils.p_to_q(z.astype(float)), z.copy(), z.copy(), np.zeros((0, 43), np.int64),
+                np.zeros((0, 43), np.int64), np.zeros((0, 43, 0), np.int64), np.zeros((0, 43, 0), np.int64),
+                np.zeros((0, 43, 16), np.int64), np.zeros((0, 43, 16), np.int64))
+    pe, pt, de, dt = _native.build_host(batch.seq, batch.qual, batch.corr, batch.rg, batch.second,
+                                        batch.L, batch.R, minscore)
+    meanq, rg_e, rg_t, q_e, q_t = _native.marginals_host(pe, pt)
+    return meanq, rg_e, rg_t, q_e, q_t, pe, pt, de, dt
+
+
+def fastq_to_covariate_arrays(fastq, infer_rg=False, minscore=6, maxscore=42):
+    """reference: kbbq/recalibrate.py:22-121.
+
+    -> (meanq, rg_errs, rg_total, q_errs, q_total, pos_errs, pos_total, dinuc_errs, dinuc_total),
+    fresh int64 arrays of shapes [R], [R], [R], [R,43], [R,43], [R,43,2L], [R,43,2L], [R,43,16] x2.
+    """
+    if maxscore != 42:
+        raise NotImplementedError("only maxscore = 42 is supported")
+    batch = ReadBatch.from_fastq(fastq, infer_rg)
+    return _tables_from_batch(batch, minscore)
+
+
+def recalibrate_fastq(fastq, infer_rg=False):
+    """Recalibrate fastq[0] given its corrected twin fastq[1]; FASTQ to stdout
+    (reference: kbbq/recalibrate.py:123-156: name without comment, sequence, '+', chr(q + 33))."""
+    batch = ReadBatch.from_fastq(fastq, infer_rg)
+    if batch.N == 0:
+        return
+    out = _native.recalibrate_host(batch.seq, batch.qual, batch.corr, batch.rg, batch.second,
+                                   batch.L, batch.R, 6)
+    qual_txt = (out + np.uint8(33)).astype(np.uint8)
+    w = sys.stdout
+    seq = batch.seq
+    chunks = []
+    for i, name in enumerate(batch.names):
+        chunks.append('@%s\n%s\n+\n%s\n' % (name, seq[i].tobytes().decode(), qual_txt[i].tobytes().decode('latin-1')))
+        if len(chunks) >= 4096:
+            w.write(''.join(chunks))
+            chunks = []
+    w.write(''.join(chunks))
+
+
+def recalibrate_bam(bam, use_oq=False, set_oq=False):
+    """Not implemented in the reference either (kbbq/recalibrate.py:158-164)."""
+    raise NotImplementedError('Recalibrating a bam is not yet implemented. \
+        Try converting your BAM to a FASTQ file with the samtools fastq command.')
+
+
+def recalibrate(bam, fastq, infer_rg=False, use_oq=False, set_oq=False, gatkreport=None):
+    """reference: kbbq/recalibrate.py:166-174."""
+    if gatkreport is not None:
+        raise NotImplementedError('GATKreport reading / creation is not yet supported.')
+    elif bam is not None:
+        recalibrate_bam(bam, use_oq, set_oq)
+    elif fastq is not None:
+        recalibrate_fastq(fastq, infer_rg=infer_rg)
+    else:
+        raise ValueError("A BAM or FASTQ file should be provided for recalibration.")

@@ -1,0 +1,1 @@
+"""Empty stand-in (test infrastructure only)."""
