@@ -3,6 +3,7 @@
 // kernel configuration and enqueues.  Compiled for sm_100a only.
 #include <algorithm>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -369,8 +370,11 @@ int kbbq_recalibrate_host(const uint8_t *seq, const uint8_t *qual, const uint8_t
     size_t free_b = 0, total_b = 0;
     KBBQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
     const size_t per_read_resident = (size_t)4 * L + 3;
-    const bool resident = (double)N * per_read_resident < 0.8 * (double)free_b;
+    bool resident = (double)N * per_read_resident < 0.8 * (double)free_b;
     int64_t chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / L);   // ~256 MiB per array per chunk
+    // test hooks: force small chunks / the two-pass streaming mode on small inputs
+    if (const char *e = getenv("KBBQ_HOST_CHUNK_READS")) chunk = std::max<int64_t>(16, atoll(e));
+    if (const char *e = getenv("KBBQ_HOST_FORCE_STREAMING")) resident = resident && atoi(e) == 0;
     chunk = (chunk + 15) / 16 * 16;                                    // keep chunk starts 16-byte aligned
     if (chunk > N) chunk = std::max<int64_t>(N, 1);
     const int64_t nchunks = N ? (N + chunk - 1) / chunk : 0;

@@ -16,8 +16,16 @@ def _mix64(x):
     return x
 
 
-def synth_reads(seed, first_read, n, L, R):
-    """-> seq, qual, corr u8[n, L], rg u16[n], second u8[n] for reads [first_read, first_read + n)."""
+def synth_reads(seed, first_read, n, L, R, block=65536):
+    """-> seq, qual, corr u8[n, L], rg u16[n], second u8[n] for reads [first_read, first_read + n).
+    Generated in blocks of `block` reads to bound the int64 temporaries."""
+    if n > block:
+        parts = [_synth_block(seed, first_read + lo, min(block, n - lo), L, R) for lo in range(0, n, block)]
+        return tuple(np.concatenate([p[k] for p in parts]) for k in range(5))
+    return _synth_block(seed, first_read, n, L, R)
+
+
+def _synth_block(seed, first_read, n, L, R):
     with np.errstate(over="ignore"):
         key = np.uint64(seed) * _GOLD
         r = np.arange(first_read, first_read + n, dtype=np.uint64)

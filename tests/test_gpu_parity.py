@@ -1,0 +1,241 @@
+"""Parity of the CUDA path against the oracle and the reference's golden vectors (B200 only).
+
+Bar: bit-exact for the int64 count tables, the integer delta tables and every output quality byte.
+All calls go through the C ABI (device-pointer entry points via kbbq.device, host-buffer entry
+points via kbbq._native / the Python API mirror).
+"""
+import io
+import contextlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import DELTA_KEYS, TABLE_KEYS, load_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch
+
+
+def _dev(torch, *arrays):
+    out = []
+    for a in arrays:
+        if a is None:
+            out.append(None)
+        elif a.dtype == np.uint16:
+            out.append(torch.from_numpy(a.astype(np.int16)).cuda())
+        else:
+            out.append(torch.from_numpy(np.ascontiguousarray(a)).cuda())
+    return out
+
+
+def _run_device(torch, seq, qual, corr, rg, second, L, R, path, splits=1):
+    from kbbq.device import DeviceRecalibrator
+    N = seq.shape[0]
+    rec = DeviceRecalibrator(L, R, max_reads=N)
+    bounds = [N * i // splits // 16 * 16 for i in range(splits)] + [N]
+    parts = []
+    for lo, hi in zip(bounds, bounds[1:]):
+        parts.append(_dev(torch, seq[lo:hi], qual[lo:hi], corr[lo:hi], rg[lo:hi] if rg is not None else None,
+                          second[lo:hi] if second is not None else None))
+        s, q, c, g, sec = parts[-1]
+        if hi > lo:
+            rec.build(s, q, c, g, sec, path=path)
+    tables = rec.covariate_arrays()
+    deltas = rec.delta_qs()
+    outs = []
+    for (s, q, c, g, sec) in parts:
+        o = torch.full_like(q, 255)
+        if q.numel():
+            rec.apply(s, q, o, g, sec, path=path)
+        outs.append(o.cpu().numpy())
+    rec.check_status()
+    return tables, deltas, np.concatenate(outs).reshape(N, L)
+
+
+@pytest.mark.parametrize("path", [1, 2])
+def test_golden_cases_device_api(torch_cuda, golden_case, path):
+    g = golden_case
+    L, R = int(g["L"]), int(g["R"])
+    tables, deltas, out = _run_device(torch_cuda, g["seq"], g["qual"], g["corr"], g["rg"], g["second"], L, R, path)
+    for got, key in zip(tables, TABLE_KEYS):
+        assert np.array_equal(got, g[key]), key
+    for got, key in zip(deltas, DELTA_KEYS):
+        assert np.array_equal(got, g[key]), key
+    assert np.array_equal(out.astype(np.int16), g["outq"])
+
+
+def test_golden_cases_python_api(golden_case, tmp_path, capfd):
+    """The reference's own entry points, same signatures, fed the same FASTQ files."""
+    from kbbq import recalibrate
+    from kbbq.gatk import applybqsr
+    g = golden_case
+    names = str(g["names"]).split("\n")
+    fu, fc = tmp_path / "u.fq", tmp_path / "c.fq"
+    with open(fu, "w") as hu, open(fc, "w") as hc:
+        for i, name in enumerate(names):
+            q = (g["qual"][i] + 33).astype(np.uint8).tobytes().decode()
+            hu.write("@%s\n%s\n+\n%s\n" % (name, g["seq"][i].tobytes().decode(), q))
+            hc.write("@%s corrected\n%s\n+\n%s\n" % (name, g["corr"][i].tobytes().decode(), q))
+    infer = bool(g["infer_rg"])
+    tables = recalibrate.fastq_to_covariate_arrays((str(fu), str(fc)), infer_rg=infer)
+    for got, key in zip(tables, TABLE_KEYS):
+        assert np.array_equal(got, g[key]), key
+        assert got.dtype == np.int64
+    dqs = applybqsr.get_delta_qs(*tables)
+    for got, key in zip(dqs, DELTA_KEYS):
+        assert np.array_equal(got, g[key]), key
+    capfd.readouterr()
+    recalibrate.recalibrate_fastq((str(fu), str(fc)), infer_rg=infer)
+    text = capfd.readouterr().out
+    lines = text.split("\n")
+    outq = np.array([[ord(ch) - 33 for ch in lines[4 * i + 3]] for i in range(len(names))], dtype=np.int16)
+    assert np.array_equal(outq, g["outq"])
+    assert all(lines[4 * i] == "@" + names[i] and lines[4 * i + 2] == "+" for i in range(len(names)))
+    if "fastq_out" in g.files:
+        assert text == str(g["fastq_out"])
+
+
+def test_delta_grid_matches_reference():
+    from kbbq import compare_reads
+    g = load_case("delta_grid")
+    dq = compare_reads.gatk_delta_q(g["prior"], g["errs"], g["total"])
+    assert np.array_equal(dq, g["dq"])
+
+
+def test_device_synth_equals_numpy_twin(torch_cuda):
+    from kbbq import synth
+    from kbbq.device import synth_reads
+    for (seed, first, n, L, R) in ((1002, 0, 3000, 150, 1), (1004, 12345, 2001, 250, 32), (7, 10 ** 9, 515, 151, 8)):
+        dev = [t.cpu().numpy() for t in synth_reads(seed, first, n, L, R)]
+        host = synth.synth_reads(seed, first, n, L, R)
+        for name, a, b in zip(("seq", "qual", "corr", "rg", "second"), dev, host):
+            assert np.array_equal(a.view(b.dtype) if a.dtype != b.dtype else a, b), name
+
+
+SYNTH_CASES = [
+    # (name, seed, N, L, R)  -- the BASELINE.json configs at oracle-sized N
+    ("c2_l150_r1", 1002, 200_000, 150, 1),
+    ("c3_l150_r8", 1003, 120_000, 150, 8),
+    ("c4_l250_r32", 1004, 60_000, 250, 32),
+    ("c1_l151_r1", 1001, 24_000, 151, 1),
+    ("l100_r3_ragged_n", 5, 33_333, 100, 3),
+    ("l37_r5", 6, 10_007, 37, 5),
+    ("l8_r2", 8, 4_099, 8, 2),
+]
+
+
+@pytest.mark.parametrize("case", SYNTH_CASES, ids=[c[0] for c in SYNTH_CASES])
+def test_synthetic_configs_vs_oracle(torch_cuda, oracle_mod, case):
+    from kbbq import synth
+    _, seed, N, L, R = case
+    seq, qual, corr, rg, second = synth.synth_reads(seed, 0, N, L, R)
+    if "ragged" in case[0]:  # unpaired: every read its own group / orientation
+        rng = np.random.default_rng(seed)
+        rg = rng.integers(0, R, N).astype(np.uint16)
+        second = rng.integers(0, 2, N).astype(np.uint8)
+    want_t = oracle_mod.covariate_arrays(seq, qual, corr, rg, second, L, R)
+    want_d = oracle_mod.get_delta_qs(*want_t)
+    want_o = oracle_mod.apply(seq, qual, rg, second, L, R, want_t[0], *want_d)
+    for path, splits in ((1, 1), (1, 3), (2, 1)):
+        tables, deltas, out = _run_device(torch_cuda, seq, qual, corr, rg, second, L, R, path, splits)
+        for got, want, key in zip(tables, want_t, TABLE_KEYS):
+            assert np.array_equal(got, want), (key, path, splits)
+        for got, want, key in zip(deltas, want_d, DELTA_KEYS):
+            assert np.array_equal(got, want), (key, path, splits)
+        assert np.array_equal(out.astype(np.int16), want_o), (path, splits)
+
+
+@pytest.mark.parametrize("streaming", ["0", "1"])
+def test_host_buffer_entry_point_chunked(oracle_mod, monkeypatch, streaming):
+    """kbbq_recalibrate_host with several chunks, resident and two-pass streaming modes."""
+    from kbbq import _native, synth
+    N, L, R = 50_000, 150, 4
+    seq, qual, corr, rg, second = synth.synth_reads(11, 0, N, L, R)
+    monkeypatch.setenv("KBBQ_HOST_CHUNK_READS", "7000")
+    monkeypatch.setenv("KBBQ_HOST_FORCE_STREAMING", streaming)
+    out, tabs, dqs = _native.recalibrate_host(seq, qual, corr, rg, second, L, R, want_tables=True)
+    want_t = oracle_mod.covariate_arrays(seq, qual, corr, rg, second, L, R)
+    want_d = oracle_mod.get_delta_qs(*want_t)
+    want_o = oracle_mod.apply(seq, qual, rg, second, L, R, want_t[0], *want_d)
+    for got, want in zip(tabs, want_t[5:]):
+        assert np.array_equal(got, want)
+    assert np.array_equal(dqs[0], want_t[0])
+    for got, want in zip(dqs[1:], want_d):
+        assert np.array_equal(got, want)
+    assert np.array_equal(out.astype(np.int16), want_o)
+
+
+def test_input_errors_raise_like_the_reference(torch_cuda):
+    from kbbq import _native
+    L = 40
+    seq = np.frombuffer(b"ACGT" * 10 * 8, np.uint8).reshape(8, L).copy()
+    qual = np.full((8, L), 30, np.uint8)
+    bad_q = qual.copy()
+    bad_q[3, 17] = 43
+    with pytest.raises(IndexError):
+        _native.build_host(seq, bad_q, seq, None, None, L, 1)
+    bad_s = seq.copy()
+    bad_s[5, 20] = ord("X")
+    with pytest.raises(TypeError):
+        _native.build_host(bad_s, qual, seq, None, None, L, 1)
+    lower = seq.copy()
+    lower[0, 0] = ord("a")
+    with pytest.raises(TypeError):
+        _native.build_host(lower, qual, seq, None, None, L, 1)
+    with pytest.raises(IndexError):
+        _native.build_host(seq, qual, seq, np.full(8, 2, np.uint16), None, L, 2)
+    # empty batch is fine
+    pe, pt, de, dt = _native.build_host(seq[:0], qual[:0], seq[:0], None, None, L, 1)
+    assert pt.sum() == 0
+
+
+def test_full_size_properties_config2(torch_cuda):
+    """BASELINE config 2 at full size (10 M x 150 bp, 1 read group): size-independent properties."""
+    torch = torch_cuda
+    from kbbq.device import DeviceRecalibrator, synth_reads
+    N, L, R = 10_000_000, 150, 1
+    seq, qual, corr, rg, second = synth_reads(1002, 0, N, L, R)
+    rec = DeviceRecalibrator(L, R, max_reads=N)
+    rec.build(seq, qual, corr, None, second)
+    whole = rec.tables.clone()
+    valid = qual >= 6
+    err = (seq != corr) & valid
+    # checksum of checksums: every tallied base lands in exactly one cell
+    assert int(rec.pos_total.sum()) == int(valid.sum())
+    assert int(rec.pos_errs.sum()) == int(err.sum())
+    # per-cycle marginal == per-column count, forward half for read 1 and reversed half for read 2
+    col = valid.view(N // 2, 2, L).sum(0)
+    per_cycle = rec.pos_total.sum((0, 1))
+    assert torch.equal(per_cycle[:L], col[0]) and torch.equal(per_cycle[L:].flip(0), col[1])
+    # per-quality marginal == histogram of the quality bytes
+    hist = torch.bincount(qual.view(-1).to(torch.int64), minlength=43)
+    hist[:6] = 0
+    assert torch.equal(rec.pos_total.sum((0, 2)), hist)
+    assert int(rec.din_total.sum()) <= int(valid.sum()) - int(valid[:, 0].sum())
+    assert bool((rec.din_errs <= rec.din_total).all()) and bool((rec.pos_errs <= rec.pos_total).all())
+    # linearity: two half batches add up to the whole; the generic kernel agrees with the smem kernel
+    rec.reset()
+    h = N // 2
+    rec.build(seq[:h], qual[:h], corr[:h], None, second[:h])
+    rec.build(seq[h:], qual[h:], corr[h:], None, second[h:])
+    assert torch.equal(rec.tables, whole)
+    rec.reset()
+    rec.build(seq, qual, corr, None, second, path=2)
+    assert torch.equal(rec.tables, whole)
+    # apply: untouched below minscore, bounded otherwise, smem == generic
+    rec.model()
+    out = torch.empty_like(qual)
+    rec.apply(seq, qual, out, None, second)
+    assert torch.equal(out[~valid], qual[~valid])
+    assert int(out[valid].max()) <= 60
+    out2 = torch.empty_like(qual)
+    rec.apply(seq, qual, out2, None, second, path=2)
+    assert torch.equal(out, out2)
+    rec.check_status()

@@ -1,0 +1,147 @@
+"""Host-side logic that needs no GPU: the C-ABI library loads and exports every declared symbol,
+FASTQ batching, name inference, the synthetic-read twin, shard ranges."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, load_case
+
+
+def test_library_exports_every_declared_symbol():
+    from kbbq import _native
+    header = open(os.path.join(ROOT, "include", "kbbq_b200.h")).read()
+    declared = set(re.findall(r"\b(kbbq_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    lib = _native.lib()  # raises if the .so is missing: there is no fallback
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.kbbq_abi_version() == 1
+    assert lib.kbbq_strerror(-1) == b"bad argument"
+    assert lib.kbbq_pos_table_elems(150, 2) == 2 * 43 * 300
+    assert lib.kbbq_din_table_elems(3) == 3 * 43 * 16
+
+
+def test_workspace_query_and_argument_checks():
+    import ctypes as C
+    from kbbq import _native
+    lib = _native.lib()
+    nbytes = C.c_size_t(0)
+    assert lib.kbbq_workspace_bytes(1000, 150, 1, C.byref(nbytes)) == 0 and nbytes.value > 0
+    assert lib.kbbq_workspace_bytes(-1, 150, 1, C.byref(nbytes)) == -1
+    assert lib.kbbq_workspace_bytes(10, 150, 0, C.byref(nbytes)) == -1
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from kbbq import _native
+    monkeypatch.setattr(_native, "_lib", None)
+    monkeypatch.setattr(_native, "LIB_PATH", str(tmp_path / "nope.so"))
+    with pytest.raises(_native.KbbqNativeError):
+        _native.lib()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "kbbq-py_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.lower(), (dirpath, f)
+
+
+def test_fastx_and_batch(tmp_path):
+    from kbbq import fastx
+    from kbbq.batch import ReadBatch, infer_rg, infer_second
+    g = load_case("tiny_r2")
+    fu, fc = tmp_path / "u.fq", tmp_path / "c.fq"
+    fu.write_text(str(g["fastq_in"]))
+    fc.write_text(str(g["fastq_corr"]))
+    b = ReadBatch.from_fastq((str(fu), str(fc)), True)
+    assert np.array_equal(b.seq, g["seq"]) and np.array_equal(b.qual, g["qual"]) and np.array_equal(b.corr, g["corr"])
+    assert np.array_equal(b.rg, g["rg"]) and np.array_equal(b.second, g["second"]) and b.R == int(g["R"])
+    assert b.names == str(g["names"]).split("\n")
+    recs = list(fastx.FastxFile(str(fc)))
+    assert recs[0].comment == "corrected by lighter" and recs[0].name == b.names[0]
+    assert str(fastx.FastxRecord("foo", "ATG", "((#")) == "@foo\nATG\n+\n((#"
+    # no --infer-rg: a single group
+    b1 = ReadBatch.from_fastq((str(fu), str(fc)), False)
+    assert b1.R == 1 and not b1.rg.any()
+    # reference behaviours: kbbq/compare_reads.py:304-318
+    assert infer_second(["a/1", "a/2", "b/2_RG:Z:x", "c"]).tolist() == [0, 1, 1, 0]
+    rg, keys = infer_rg(["a/1_RG:Z:foo", "a/2_RG:Z:bar", "b/1_RG:Z:foo"], True)
+    assert rg.tolist() == [0, 1, 0] and keys == ["foo", "bar"]
+    with pytest.raises(AssertionError):
+        infer_rg(["a/1_XX:Z:foo"], True)
+    with pytest.raises(IndexError):
+        infer_rg(["a/1"], True)
+
+
+def test_batch_name_mismatch_and_ragged(tmp_path):
+    from kbbq.batch import ReadBatch
+    fu, fc = tmp_path / "u.fq", tmp_path / "c.fq"
+    fu.write_text("@r1\nACGT\n+\nIIII\n")
+    fc.write_text("@x1\nACGT\n+\nIIII\n")
+    with pytest.raises(AssertionError):  # find_corrected_sites, kbbq/recalibrate.py:17
+        ReadBatch.from_fastq((str(fu), str(fc)))
+    fu.write_text("@r1\nACGT\n+\nIIII\n@r2\nACG\n+\nIII\n")
+    with pytest.raises(ValueError):
+        ReadBatch.from_fastq((str(fu), str(fu)))
+    fu.write_text("")
+    fc.write_text("")
+    assert ReadBatch.from_fastq((str(fu), str(fc))).N == 0
+
+
+def test_host_helpers_match_reference_kats():
+    from kbbq import compare_reads as cr
+    # tests/test_compare_reads.py:124-139,153-189 of the reference
+    assert cr.RescaledNormal.prior(0) == np.log(.9)
+    assert np.all(cr.RescaledNormal.prior_dist < 0)
+    s = load_case("scalars")
+    assert np.array_equal(np.asarray(cr.RescaledNormal.prior_dist, dtype=np.float64), s["prior_dist"])
+    assert cr.Dinucleotide.dinucs == ['AA', 'AT', 'AG', 'AC', 'TA', 'TT', 'TG', 'TC', 'GA', 'GT', 'GG', 'GC',
+                                      'CA', 'CT', 'CG', 'CC']
+    assert np.array_equal(cr.Dinucleotide.vecget(np.array(cr.Dinucleotide.dinucs)), np.arange(16))
+    assert np.array_equal(cr.p_to_q(np.array([.2, .3, .4, .1, .01, .001])), [6, 5, 3, 10, 20, 30])
+    assert np.array_equal(cr.p_to_q(cr.q_to_p(np.arange(43))), s["p_to_q_roundtrip"])
+    assert np.allclose(cr.q_to_p(np.array([6, 10, 20, 30])).astype(float), [.251188643, .1, .01, .001])
+    assert np.array_equal(cr.generic_cycle_covariate(17), np.arange(17))
+    assert np.array_equal(cr.generic_cycle_covariate(17, True), -(np.arange(17) + 1))
+    seq = np.array(list('ATGCATGC'))
+    q = np.array([10] * 8)
+    correct = np.concatenate([[-1], cr.Dinucleotide.vecget(np.array(['AT', 'TG', 'GC', 'CA', 'AT', 'TG', 'GC']))])
+    assert np.array_equal(cr.generic_dinuc_covariate(seq, q), correct)
+    seq[1] = 'N'
+    correct[1] = correct[2] = -1
+    assert np.array_equal(cr.generic_dinuc_covariate(seq, q), correct)
+    q[6] = 2
+    correct[6] = -1
+    assert np.array_equal(cr.generic_dinuc_covariate(seq, q), correct)
+    with pytest.raises(TypeError):
+        cr.generic_dinuc_covariate(np.array(list('AXGC')), np.array([10] * 4))
+
+
+def test_synth_twin_is_deterministic_and_shaped():
+    from kbbq import synth
+    a = synth.synth_reads(1002, 0, 512, 150, 4)
+    b = synth.synth_reads(1002, 256, 256, 150, 4)
+    for x, y in zip(a, b):
+        assert np.array_equal(x[256:], y)  # any read range can be regenerated independently
+    seq, qual, corr, rg, second = a
+    assert set(np.unique(seq)) <= set(b"ACGTN") and qual.min() >= 2 and qual.max() <= 41
+    assert np.all(qual[seq == ord("N")] == 2)
+    assert second.tolist() == [0, 1] * 256 and np.array_equal(rg[0::2], rg[1::2]) and rg.max() < 4
+    assert 0.005 < (seq != corr).mean() < 0.015
+    assert not np.array_equal(seq, synth.synth_reads(1003, 0, 512, 150, 4)[0])
+
+
+def test_shard_ranges_cover_and_align():
+    from kbbq.parallel import shard_range
+    for n in (0, 1, 15, 16, 17, 1000, 10_000_001):
+        for world in (1, 2, 3, 8):
+            spans = [shard_range(n, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a, b), (c, d) in zip(spans, spans[1:]):
+                assert b == c and a <= b
+            assert all(lo % 16 == 0 for lo, _ in spans if lo < n)
