@@ -33,28 +33,36 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(ApplyArgs a)
     extern __shared__ unsigned int smem[];
     const Geom &g = a.g;
     const int nqv = g.nqv, row = g.row;
-    int *t_cyc = reinterpret_cast<int *>(smem);  // [nqv][row]
-    int *t_din = t_cyc + nqv * row;              // [nqv][17][DREP]
+    int *t_cyc = reinterpret_cast<int *>(smem);  // [nqv + 1][row]        (+ zero trash row)
+    int *t_din = t_cyc + (nqv + 1) * row;        // [nqv + 1][17][DREP]   (+ zero trash row)
 
     const ThreadMap m = make_thread_map(g);
     const int lane = threadIdx.x & 31;
     const uint32_t minq4 = (uint32_t)g.minscore * ONE4;
-    const int qbase_pos = g.minscore * row;
-    const int din_lane = (lane & (DREP - 1)) - g.minscore * 17 * DREP;
+    const uint32_t trash4 = (uint32_t)NQ * ONE4;
+    const uint32_t cyc_base = smem_addr(t_cyc) - (uint32_t)g.minscore * row * 4;
+    const uint32_t din_base = pin(smem_addr(t_din) + (lane & (DREP - 1)) * 4 - (uint32_t)g.minscore * DIN_SLOTS * DREP * 4);
+    const uint32_t row_bytes = row * 4, dq_bytes = DIN_SLOTS * DREP * 4;
+    const uint32_t rowbit = m.row >= 0 ? (1u << m.row) : 0u, secbit = rowbit << 8;
+    uint32_t afwd[4], arev[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { afwd[b] = pin(cyc_base + m.fwd[b]); arev[b] = pin(cyc_base + m.rev[b]); }
+    const uint32_t gbytes = g.gbytes, ng = g.ng;
+    const uint32_t last_grp = (uint32_t)((a.total_bytes / g.L + g.G - 1) / g.G) - 1u;
     const uint32_t nqlim4 = (uint32_t)(127 - (a.nq - 1)) * ONE4;  // q + this has bit 7 set iff q >= nq
 
     const unsigned long long E = a.seg[a.R];
-    const unsigned long long lo = E * blockIdx.x / gridDim.x, hi = E * (blockIdx.x + 1) / gridDim.x;
+    const uint32_t lo = (uint32_t)(E * blockIdx.x / gridDim.x), hi = (uint32_t)(E * (blockIdx.x + 1) / gridDim.x);
     uint32_t qbad = 0;
 
     for (int rg = 0; rg < a.R; ++rg) {
-        unsigned long long s_lo = a.seg[rg], s_hi = a.seg[rg + 1];
+        uint32_t s_lo = a.seg[rg], s_hi = a.seg[rg + 1];
         if (s_hi <= lo) continue;
         if (s_lo >= hi) break;
         if (s_lo < lo) s_lo = lo;
         if (s_hi > hi) s_hi = hi;
 
-        // stage this read group's folded tables
+        // stage this read group's folded tables (trash row = 0)
         __syncthreads();
         const int L2 = 2 * g.L;
         const short *fc = a.fold_cyc + ((size_t)rg * NQ + g.minscore) * L2;
@@ -62,30 +70,26 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(ApplyArgs a)
             const int q = i / L2, c2 = i - q * L2;
             t_cyc[q * row + plane_pos(c2, g.sj)] = fc[i];
         }
+        for (int i = threadIdx.x; i < row; i += blockDim.x) t_cyc[nqv * row + i] = 0;
         const short *fd = a.fold_din + ((size_t)rg * NQ + g.minscore) * 32;
-        for (int i = threadIdx.x; i < nqv * 17 * DREP; i += blockDim.x) {
-            const int cell = i / DREP, q = cell / 17, sl = cell - q * 17;
-            t_din[i] = fd[q * 32 + sl];
+        for (int i = threadIdx.x; i < (nqv + 1) * DIN_SLOTS * DREP; i += blockDim.x) {
+            const int cell = i / DREP, q = cell / DIN_SLOTS, sl = cell - q * DIN_SLOTS;
+            t_din[i] = q < nqv ? fd[q * 32 + sl] : 0;
         }
         __syncthreads();
 
-        for (unsigned long long it = s_lo + m.grp; it < s_hi; it += g.ng) {
-            const entry_t e = __ldg(a.entries + it);
-            const uint32_t sr = (uint32_t)e;
-            const uint32_t rowbits = (uint32_t)(e >> 32);
-            const uint32_t mA = (rowbits >> m.rho0) & 1u, mB = (rowbits >> (m.rho0 + 1)) & 1u;
-            const uint32_t sA = (rowbits >> (4 + m.rho0)) & 1u, sB = (rowbits >> (5 + m.rho0)) & 1u;
-            const uint32_t am = (mA ? m.lo_mask : 0u) | (mB ? m.hi_mask : 0u);
-            const long long off = (long long)sr * g.srb + 4 * m.j;
+        uint32_t it = s_lo + m.grp;
+        Fetch nx = fetch_words<false>(a.seq, a.qual, nullptr, a.entries, it, s_hi, m, gbytes, rowbit, last_grp, a.total_bytes);
+        for (; it < s_hi; it += ng) {
+            const Fetch cur = nx;
+            nx = fetch_words<false>(a.seq, a.qual, nullptr, a.entries, it + ng, s_hi, m, gbytes, rowbit, last_grp, a.total_bytes);
+            const uint32_t sw = cur.sw, qw = cur.qw;
+            const uint32_t am = cur.bits ? m.rowmask : 0u;
 
-            uint32_t sw = 0, qw = 0;
-            if (am) {
-                sw = ld_word_guarded(a.seq, off, a.total_bytes);
-                qw = ld_word_guarded(a.qual, off, a.total_bytes);
-            }
             const uint32_t code3 = (sw >> 1) & 0x07070707u;
             uint32_t pv3 = __shfl_up_sync(0xFFFFFFFFu, code3 >> 24, 1);
-            if (lane == 0) pv3 = ((am & 0xFFu) && !m.first0) ? ((uint32_t)__ldg(a.seq + off - 1) >> 1) & 7u : 7u;
+            if (lane == 0) pv3 = (am && m.need_prev) ? ((uint32_t)__ldg(a.seq + cur.off - 1) >> 1) & 7u : 7u;
+            if (!am) continue;
             const uint32_t pc3 = __byte_perm(pv3, code3, 0x6540);
 
             const uint32_t bad = ((qw + nqlim4) | qw) & H4 & am;  // q >= nq: IndexError in the reference
@@ -93,30 +97,30 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(ApplyArgs a)
             const uint32_t vm = ((qw | H4) - minq4) & H4 & am & ~bad;
             const uint32_t anyn = ((code3 | pc3) << 5) & H4;
             const uint32_t dm = vm & ~anyn & m.notfirst;
-            // dinuc slot: natural-order code when valid, 16 (the pad slot) otherwise
-            const uint32_t dm8 = (dm >> 7) * 0xFFu;
-            const uint32_t din5 = ((((pc3 << 2) & 0x0C0C0C0Cu) | (code3 & 0x03030303u)) & dm8) | (0x10101010u & ~dm8);
-            const uint32_t shA = sA ? 16 : 0, shB = sB ? 16 : 0;
+            const uint32_t vm8 = (vm >> 7) * 0xFFu, dm8 = (dm >> 7) * 0xFFu;
+            const uint32_t q4 = (qw & vm8) | (trash4 & ~vm8);
+            const uint32_t din4 = ((pc3 << 2) & 0x0C0C0C0Cu) | (code3 & 0x03030303u);
+            const uint32_t d4 = (din4 & dm8) | (0x10101010u & ~dm8);  // invalid dinuc -> the pad slot
+            const bool sec = (cur.bits & secbit) != 0;
 
-            uint32_t res = qw;
+            uint32_t v[4];
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                if (vm & (0x80u << (8 * b))) {
-                    const uint32_t qb = (qw >> (8 * b)) & 0xFFu;
-                    const bool inA = (m.lo_mask >> (8 * b)) & 1u;
-                    const uint32_t pos = (m.off[b] >> (inA ? shA : shB)) & 0xFFFFu;
-                    const uint32_t db = (din5 >> (8 * b)) & 0x1Fu;
-                    const int v = t_cyc[qb * row + pos - qbase_pos] + t_din[(qb * 17 + db) * DREP + din_lane];
-                    res = (res & ~(0xFFu << (8 * b))) | (((uint32_t)v & 0xFFu) << (8 * b));
-                }
+                const uint32_t qb = __byte_perm(q4, 0, 0x4440 + b);
+                const uint32_t db = __byte_perm(d4, 0, 0x4440 + b);
+                uint32_t x, y;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(qb * row_bytes + (sec ? arev[b] : afwd[b])));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(y) : "r"(qb * dq_bytes + (db * (DREP * 4) + din_base)));
+                v[b] = x + y;
             }
-            if (am == 0xFFFFFFFFu && off + 4 <= a.total_bytes) {
-                *reinterpret_cast<unsigned int *>(a.out + off) = res;
-            } else if (am) {
+            const uint32_t sum4 = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+            const uint32_t res = (sum4 & vm8) | (qw & ~vm8);  // untouched below minscore
+            if (am == 0xFFFFFFFFu && cur.off + 4 <= a.total_bytes) {
+                *reinterpret_cast<unsigned int *>(a.out + cur.off) = res;
+            } else {
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
-                    if ((am >> (8 * b)) & 1u)
-                        if (off + b < a.total_bytes) a.out[off + b] = (uint8_t)(res >> (8 * b));
+                    if (((am >> (8 * b)) & 1u) && cur.off + b < a.total_bytes) a.out[cur.off + b] = (uint8_t)(res >> (8 * b));
             }
         }
     }
@@ -159,7 +163,7 @@ __global__ void apply_generic_kernel(ApplyGenericArgs a) {
 }
 
 inline size_t apply_smem_bytes(const Geom &g, int drep) {
-    return sizeof(int) * ((size_t)g.nqv * g.row + (size_t)g.nqv * 17 * drep);
+    return sizeof(int) * ((size_t)(g.nqv + 1) * g.row + (size_t)(g.nqv + 1) * DIN_SLOTS * drep);
 }
 
 }  // namespace kbbq

@@ -5,14 +5,19 @@
 // four pos_* / dinuc_* np.add.at calls (:116-119).
 //
 // Roofline: HBM.  Algorithmic traffic 3 B/base (seq + qual + corrected), nothing written but the
-// tables.  The limiter in practice is shared-memory atomic throughput (2 per base), so the design
-// goal is conflict-free ATOMS:
-//   * one thread owns one 32-bit word position of a super-row (common.cuh), i.e. four fixed
-//     cycles, and walks down the reads; lanes of a warp own consecutive words, so at every byte
-//     position they hit consecutive banks of the cycle table whatever the qualities are;
+// tables.  In practice the kernel is bound by instruction issue and shared-memory atomics (two
+// per base), so the design minimises instructions per base and keeps every ATOMS conflict free:
+//   * one thread owns one (row, 32-bit word) position of a group of G reads (common.cuh), i.e.
+//     four fixed cycles of one read, and walks down the groups; lanes of a warp own consecutive
+//     words, so at every byte position they hit consecutive banks of the cycle table whatever the
+//     qualities are;
 //   * the dinucleotide table (37 x 16 cells, every lane could hit the same cell) is replicated
 //     per lane ([cell][lane]), so bank == lane;
-//   * errors (about 1 % of bases) take a divergent slow path into unreplicated tables;
+//   * bases that must not be tallied (q < minscore, bytes of a neighbouring read, invalid dinuc)
+//     are steered to a TRASH row / slot by byte-parallel selects instead of per-byte predicates,
+//     so the eight reductions of a word are unconditional `red.shared.add.u32`;
+//   * the next word of each stream is prefetched before the current one is tallied;
+//   * mismatches (about 1 % of bases) take a divergent slow path into unreplicated tables;
 //   * tables are per-CTA u32 in shared memory, flushed once per read-group segment to the global
 //     int64 tables with 64-bit reductions (zero cells skipped).
 #pragma once
@@ -20,6 +25,8 @@
 #include "prepare.cuh"
 
 namespace kbbq {
+
+constexpr int DIN_SLOTS = 17;  // 16 dinucleotides + 1 trash slot
 
 struct BuildArgs {
     const uint8_t *seq, *qual, *corr;
@@ -40,39 +47,95 @@ __device__ __forceinline__ uint32_t ld_word_guarded(const uint8_t *p, long long 
     return v;
 }
 
-// Per-thread constants of the super-row mapping.
+__device__ __forceinline__ void red_shared_inc(uint32_t saddr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr));
+}
+
+__device__ __forceinline__ uint32_t smem_addr(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// Per-thread constants of the (row, word) mapping.
 struct ThreadMap {
-    int grp, j;
-    bool act;
-    int rho0;            // row (within the super-row) of byte 0
-    uint32_t lo_mask;    // 0xFF for the bytes that lie in row rho0
-    uint32_t hi_mask;    // 0xFF for the bytes that lie in row rho0 + 1
+    int grp;             // thread-group index inside the CTA
+    int row;             // row of the group this thread works on (-1: padding lane)
+    int toff;            // byte offset of this thread's word inside a group
+    uint32_t rowmask;    // 0xFF for the bytes of the word that belong to the row
     uint32_t notfirst;   // H4 bit for bytes whose cycle is not 0
-    uint32_t off[4];     // (forward position) | (reverse position << 16) inside a quality row
-    bool first0;
+    uint32_t fwd[4];     // forward table position (bytes inside a quality row) of each byte's cycle
+    uint32_t rev[4];     // reverse (read-2) position
+    bool need_prev;      // byte 0 has a predecessor in the same row (word index > 0)
 };
 
 __device__ __forceinline__ ThreadMap make_thread_map(const Geom &g) {
     ThreadMap m;
     const int tid = threadIdx.x;
     m.grp = tid / g.lps;
-    m.j = tid - m.grp * g.lps;
-    m.act = m.j < g.wps;
-    const int flat0 = 4 * m.j;
-    m.rho0 = flat0 / g.L;
-    const int c0 = flat0 - m.rho0 * g.L;
-    const int nb0 = min(4, g.L - c0);
-    m.lo_mask = 0; m.hi_mask = 0; m.notfirst = 0;
+    const int t = tid - m.grp * g.lps;
+    m.row = -1;
+    int w = 0;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-        int c = (b < nb0) ? c0 + b : b - nb0;
-        if (b < nb0) m.lo_mask |= 0xFFu << (8 * b); else m.hi_mask |= 0xFFu << (8 * b);
-        if (c != 0) m.notfirst |= 0x80u << (8 * b);
-        m.off[b] = (uint32_t)plane_pos(c, g.sj) | ((uint32_t)plane_pos(2 * g.L - 1 - c, g.sj) << 16);
+    for (int k = 0; k < MAX_G; ++k)
+        if (k < g.G && t >= g.wstart[k] && t < g.wstart[k + 1]) { m.row = k; w = t - g.wstart[k]; }
+    m.rowmask = 0; m.notfirst = 0; m.toff = 0; m.need_prev = false;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { m.fwd[b] = 0; m.rev[b] = 0; }
+    if (m.row >= 0) {
+        const int a = (m.row * g.L) & 3;
+        m.toff = m.row * g.L - a + 4 * w;
+        m.need_prev = w > 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int c = 4 * w + b - a;
+            if (c >= 0 && c < g.L) {
+                m.rowmask |= 0xFFu << (8 * b);
+                if (c != 0) m.notfirst |= 0x80u << (8 * b);
+                m.fwd[b] = 4u * plane_pos(c, g.sj);
+                m.rev[b] = 4u * plane_pos(2 * g.L - 1 - c, g.sj);
+            }
+        }
     }
-    m.first0 = (c0 == 0);
-    if (!m.act) { m.lo_mask = 0; m.hi_mask = 0; }
     return m;
+}
+
+// The words of one group position, fetched ahead of their use.
+struct Fetch {
+    uint32_t sw, qw, cw, bits;
+    long long off;
+};
+
+// `last_grp` is the only group whose words can reach past the end of the arrays.
+template <bool WITH_CORR>
+__device__ __forceinline__ Fetch fetch_words(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr,
+                                             const entry_t *entries, uint32_t it, uint32_t end,
+                                             const ThreadMap &m, uint32_t gbytes, uint32_t rowbit,
+                                             uint32_t last_grp, long long total) {
+    Fetch f;
+    f.sw = 0; f.qw = 0; f.cw = 0; f.bits = 0; f.off = 0;
+    if (it < end) {
+        const entry_t e = __ldg(entries + it);
+        const uint32_t grp = (uint32_t)e, bits = (uint32_t)(e >> 32);
+        f.off = (long long)((unsigned long long)grp * gbytes) + m.toff;
+        if (bits & rowbit) {
+            f.bits = bits;
+            if (grp != last_grp) {
+                f.sw = __ldg(reinterpret_cast<const unsigned int *>(seq + f.off));
+                f.qw = __ldg(reinterpret_cast<const unsigned int *>(qual + f.off));
+                if (WITH_CORR) f.cw = __ldg(reinterpret_cast<const unsigned int *>(corr + f.off));
+            } else {
+                f.sw = ld_word_guarded(seq, f.off, total);
+                f.qw = ld_word_guarded(qual, f.off, total);
+                if (WITH_CORR) f.cw = ld_word_guarded(corr, f.off, total);
+            }
+        }
+    }
+    return f;
+}
+
+// keep a loop-invariant value in its register instead of letting ptxas rematerialise it
+__device__ __forceinline__ uint32_t pin(uint32_t v) {
+    asm volatile("" : "+r"(v));
+    return v;
 }
 
 template <int DREP, bool VALIDATE>
@@ -80,25 +143,34 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a)
     extern __shared__ unsigned int smem[];
     const Geom &g = a.g;
     const int nqv = g.nqv, row = g.row;
-    unsigned int *pos_t = smem;
-    unsigned int *pos_e = pos_t + nqv * row;
-    unsigned int *din_t = pos_e + nqv * row;
-    unsigned int *din_e = din_t + nqv * 16 * DREP;
-    const int smem_words = 2 * nqv * row + nqv * 16 * DREP + nqv * 16;
+    unsigned int *pos_t = smem;                              // [nqv + 1][row]           (+ trash row)
+    unsigned int *din_t = pos_t + (nqv + 1) * row;           // [nqv + 1][17][DREP]      (+ trash row / slot)
+    unsigned int *pos_e = din_t + (nqv + 1) * DIN_SLOTS * DREP;  // [nqv][row]
+    unsigned int *din_e = pos_e + nqv * row;                 // [nqv][16]
+    const int smem_words = (nqv + 1) * row + (nqv + 1) * DIN_SLOTS * DREP + nqv * row + nqv * 16;
 
     const ThreadMap m = make_thread_map(g);
     const int lane = threadIdx.x & 31;
     const uint32_t minq4 = (uint32_t)g.minscore * ONE4;
-    const int qbase_pos = g.minscore * row;                       // subtract from q*row
-    const int din_lane = (lane & (DREP - 1)) - g.minscore * 16 * DREP;
+    const uint32_t trash4 = (uint32_t)NQ * ONE4;  // quality 43 -> row nqv of the shared tables
+    // byte addresses in the shared window, with the "- minscore rows" folded in
+    const uint32_t pos_base = smem_addr(pos_t) - (uint32_t)g.minscore * row * 4;
+    const uint32_t din_base = pin(smem_addr(din_t) + (lane & (DREP - 1)) * 4 - (uint32_t)g.minscore * DIN_SLOTS * DREP * 4);
+    const uint32_t row_bytes = row * 4, dq_bytes = DIN_SLOTS * DREP * 4;
+    const uint32_t rowbit = m.row >= 0 ? (1u << m.row) : 0u, secbit = rowbit << 8;
+    uint32_t afwd[4], arev[4];  // absolute shared addresses of quality row 0 at this thread's cycles
+#pragma unroll
+    for (int b = 0; b < 4; ++b) { afwd[b] = pin(pos_base + m.fwd[b]); arev[b] = pin(pos_base + m.rev[b]); }
+    const uint32_t gbytes = g.gbytes, ng = g.ng;
+    const uint32_t last_grp = (uint32_t)((a.total_bytes / g.L + g.G - 1) / g.G) - 1u;
 
     // this CTA's slice of the concatenated work list
     const unsigned long long E = a.seg[a.R];
-    const unsigned long long lo = E * blockIdx.x / gridDim.x, hi = E * (blockIdx.x + 1) / gridDim.x;
+    const uint32_t lo = (uint32_t)(E * blockIdx.x / gridDim.x), hi = (uint32_t)(E * (blockIdx.x + 1) / gridDim.x);
     uint32_t qbad = 0, bbad = 0;
 
     for (int rg = 0; rg < a.R; ++rg) {
-        unsigned long long s_lo = a.seg[rg], s_hi = a.seg[rg + 1];
+        uint32_t s_lo = a.seg[rg], s_hi = a.seg[rg + 1];
         if (s_hi <= lo) continue;
         if (s_lo >= hi) break;
         if (s_lo < lo) s_lo = lo;
@@ -107,25 +179,19 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a)
         for (int i = threadIdx.x; i < smem_words; i += blockDim.x) smem[i] = 0;
         __syncthreads();
 
-        for (unsigned long long it = s_lo + m.grp; it < s_hi; it += g.ng) {
-            const entry_t e = __ldg(a.entries + it);
-            const uint32_t sr = (uint32_t)e;
-            const uint32_t rowbits = (uint32_t)(e >> 32);
-            const uint32_t mA = (rowbits >> m.rho0) & 1u, mB = (rowbits >> (m.rho0 + 1)) & 1u;
-            const uint32_t sA = (rowbits >> (4 + m.rho0)) & 1u, sB = (rowbits >> (5 + m.rho0)) & 1u;
-            const uint32_t am = (mA ? m.lo_mask : 0u) | (mB ? m.hi_mask : 0u);
-            const long long off = (long long)sr * g.srb + 4 * m.j;
+        uint32_t it = s_lo + m.grp;
+        Fetch nx = fetch_words<true>(a.seq, a.qual, a.corr, a.entries, it, s_hi, m, gbytes, rowbit, last_grp, a.total_bytes);
+        for (; it < s_hi; it += ng) {
+            const Fetch cur = nx;
+            nx = fetch_words<true>(a.seq, a.qual, a.corr, a.entries, it + ng, s_hi, m, gbytes, rowbit, last_grp, a.total_bytes);
+            const uint32_t sw = cur.sw, qw = cur.qw;
+            const uint32_t am = cur.bits ? m.rowmask : 0u;
 
-            uint32_t sw = 0, qw = 0, cw = 0;
-            if (am) {
-                sw = ld_word_guarded(a.seq, off, a.total_bytes);
-                qw = ld_word_guarded(a.qual, off, a.total_bytes);
-                cw = ld_word_guarded(a.corr, off, a.total_bytes);
-            }
             // 3-bit base code (b >> 1) & 7: A=0 C=1 T=2 G=3 N=7, injective on ACGTN
             const uint32_t code3 = (sw >> 1) & 0x07070707u;
             uint32_t pv3 = __shfl_up_sync(0xFFFFFFFFu, code3 >> 24, 1);
-            if (lane == 0) pv3 = ((am & 0xFFu) && !m.first0) ? ((uint32_t)__ldg(a.seq + off - 1) >> 1) & 7u : 7u;
+            if (lane == 0) pv3 = (am && m.need_prev) ? ((uint32_t)__ldg(a.seq + cur.off - 1) >> 1) & 7u : 7u;
+            if (!am) continue;  // padding lane, or the row belongs to another read group
             const uint32_t pc3 = __byte_perm(pv3, code3, 0x6540);  // previous base of every byte
 
             const uint32_t bad = ((qw + 0x55555555u) | qw) & H4 & am;             // q > 42
@@ -133,7 +199,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a)
             const uint32_t vm = ((qw | H4) - minq4) & H4 & am & ~bad;             // minscore <= q <= 42
             const uint32_t anyn = ((code3 | pc3) << 5) & H4;                      // cur or prev is N
             const uint32_t dm = vm & ~anyn & m.notfirst;                          // dinuc valid
+            const uint32_t vm8 = (vm >> 7) * 0xFFu, dm8 = (dm >> 7) * 0xFFu;
+            const uint32_t q4 = (qw & vm8) | (trash4 & ~vm8);                     // untallied bytes -> trash row
             const uint32_t din4 = ((pc3 << 2) & 0x0C0C0C0Cu) | (code3 & 0x03030303u);
+            const uint32_t d4 = (din4 & dm8) | (0x10101010u & ~dm8);              // invalid dinuc -> trash slot
             if (VALIDATE) {
                 // rebuild each byte from its code with an 8-entry byte LUT; any difference = bad base
                 const uint32_t y = code3 | (code3 >> 4);
@@ -141,36 +210,27 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a)
                 const uint32_t recon = __byte_perm(0x47544341u /* A C T G */, 0x4E000000u /* . . . N */, sel);
                 bbad |= (recon ^ sw) & am;
             }
-            // forward / reverse cycle position of every byte (read-2 rows count from the end)
-            const uint32_t shA = sA ? 16 : 0, shB = sB ? 16 : 0;
-
+            // read-2 rows count cycles from the end of the axis
+            const bool sec = (cur.bits & secbit) != 0;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
-                const uint32_t qb = (qw >> (8 * b)) & 0xFFu;
-                const bool inA = (m.lo_mask >> (8 * b)) & 1u;
-                const uint32_t pos = (m.off[b] >> (inA ? shA : shB)) & 0xFFFFu;
-                if (vm & (0x80u << (8 * b)))
-                    atomicAdd(&pos_t[qb * row + pos - qbase_pos], 1u);
-                if (dm & (0x80u << (8 * b))) {
-                    const uint32_t db = (din4 >> (8 * b)) & 0xFu;
-                    atomicAdd(&din_t[(qb * 16 + db) * DREP + din_lane], 1u);
-                }
+                const uint32_t qb = __byte_perm(q4, 0, 0x4440 + b);
+                const uint32_t db = __byte_perm(d4, 0, 0x4440 + b);
+                red_shared_inc(qb * row_bytes + (sec ? arev[b] : afwd[b]));
+                red_shared_inc(qb * dq_bytes + (db * (DREP * 4) + din_base));
             }
             // mismatches: rare, divergent
-            const uint32_t x = sw ^ cw;
+            const uint32_t x = sw ^ cur.cw;
             const uint32_t xm = (((x | H4) - ONE4) | x) & vm;  // byte differs and is tallied
             if (xm) {
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
                     if (xm & (0x80u << (8 * b))) {
                         const uint32_t qb = (qw >> (8 * b)) & 0xFFu;
-                        const bool inA = (m.lo_mask >> (8 * b)) & 1u;
-                        const uint32_t pos = (m.off[b] >> (inA ? shA : shB)) & 0xFFFFu;
-                        atomicAdd(&pos_e[qb * row + pos - qbase_pos], 1u);
-                        if (dm & (0x80u << (8 * b))) {
-                            const uint32_t db = (din4 >> (8 * b)) & 0xFu;
-                            atomicAdd(&din_e[(qb - g.minscore) * 16 + db], 1u);
-                        }
+                        const uint32_t pos = (sec ? m.rev[b] : m.fwd[b]) >> 2;
+                        atomicAdd(&pos_e[(qb - g.minscore) * row + pos], 1u);
+                        if (dm & (0x80u << (8 * b)))
+                            atomicAdd(&din_e[(qb - g.minscore) * 16 + ((din4 >> (8 * b)) & 0xFu)], 1u);
                     }
                 }
             }
@@ -190,11 +250,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a)
         }
         unsigned long long *gde = a.din_errs + (size_t)rg * NQ * 16, *gdt = a.din_total + (size_t)rg * NQ * 16;
         for (int i = threadIdx.x; i < nqv * 16; i += blockDim.x) {
+            const int q = i >> 4, dn = i & 15;
             unsigned int t = 0;
 #pragma unroll 8
-            for (int k = 0; k < DREP; ++k) t += din_t[i * DREP + ((k + threadIdx.x) & (DREP - 1))];
+            for (int k = 0; k < DREP; ++k)
+                t += din_t[(q * DIN_SLOTS + dn) * DREP + ((k + threadIdx.x) & (DREP - 1))];
             const unsigned int er = din_e[i];
-            const int q = i >> 4, dn = i & 15;
             const int dref = nat_to_ref(dn >> 2) * 4 + nat_to_ref(dn & 3);
             const size_t o = (size_t)(q + g.minscore) * 16 + dref;
             if (t) atomicAdd(gdt + o, (unsigned long long)t);
@@ -253,7 +314,8 @@ __global__ void build_generic_kernel(BuildGenericArgs a) {
 }
 
 inline size_t build_smem_bytes(const Geom &g, int drep) {
-    return sizeof(unsigned int) * ((size_t)2 * g.nqv * g.row + (size_t)g.nqv * 16 * drep + (size_t)g.nqv * 16);
+    return sizeof(unsigned int) * ((size_t)(g.nqv + 1) * g.row + (size_t)(g.nqv + 1) * DIN_SLOTS * drep +
+                                   (size_t)g.nqv * g.row + (size_t)g.nqv * 16);
 }
 
 }  // namespace kbbq

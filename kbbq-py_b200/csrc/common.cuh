@@ -39,32 +39,38 @@ extern char g_last_cuda_error[256];
     } while (0)
 
 // ---------------------------------------------------------------------------------------------
-// Geometry of the "super-row" mapping shared by the build and apply kernels.
+// Geometry of the thread mapping shared by the build and apply kernels.
 //
-// Reads are u8 rows of length L packed back to back, so a row starts at byte r*L, which is in
-// general only 1- or 2-byte aligned.  A super-row is the smallest run of RPS consecutive reads
-// whose byte length is a multiple of 4 (RPS = 4 / gcd(L, 4)); it starts 4-byte aligned and is
-// WPS = RPS*L/4 words long.  One thread owns word j of every super-row its group processes, so
-// the (row-in-super-row, cycle) of each of its 4 bytes is fixed for the whole kernel and the
-// shared-memory table offsets are computed once.  A group is LPS = roundup(WPS, 32) lanes, i.e.
-// whole warps, so a warp never mixes two super-rows.
+// Reads are u8 rows of length L packed back to back, so row r starts at byte r*L, which is in
+// general only 1- or 2-byte aligned.  A GROUP is G consecutive reads whose total byte length is a
+// multiple of 4 (G is a multiple of 4 / gcd(L, 4)), so every group starts 4-byte aligned.  Inside a
+// group, row k starts at misalignment a_k = (k*L) & 3 and is covered by W_k = ceil((a_k + L)/4)
+// aligned 32-bit words; ONE THREAD OWNS ONE (row, word) of every group its thread-group processes,
+// so the cycles of its 4 bytes -- and therefore its shared-memory table offsets -- are fixed for
+// the whole kernel, and all its bytes belong to one read (one read group, one `second` flag).
+// Words that straddle two rows are loaded by both neighbours; each uses only its own bytes.
+// A thread-group is LPS = roundup(sum W_k, 32) lanes, i.e. whole warps.  G (<= 8) is chosen to
+// minimise the padding lanes (L = 150: G = 4, 152 of 160 lanes busy).
 //
 // Shared-memory cycle tables are laid out [q - minscore][plane = c2 & 3][c2 >> 2] with a plane
-// stride SJ that makes the row stride a multiple of 32 words: lanes with consecutive j then
-// touch consecutive banks at every byte position, whatever their qualities.
+// stride SJ that makes the row stride a multiple of 32 words: lanes that own consecutive words of
+// a row touch consecutive banks at every byte position, whatever their qualities.
 // ---------------------------------------------------------------------------------------------
+constexpr int MAX_G = 8;
+
 struct Geom {
-    int L;         // read length
-    int rps;       // reads per super-row
-    int srb;       // bytes per super-row
-    int wps;       // words per super-row
-    int lps;       // lanes per super-row (multiple of 32)
-    int ng;        // groups (super-rows in flight) per CTA
-    int threads;   // ng * lps
-    int sj;        // plane stride (words)
-    int row;       // words per quality row = 4 * sj
-    int minscore;  // first tallied quality
-    int nqv;       // tallied quality rows = 43 - minscore
+    int L;            // read length
+    int G;            // reads per group
+    int gbytes;       // bytes per group = G * L (multiple of 4)
+    int lanes;        // busy lanes per thread-group = sum of words per row
+    int lps;          // lanes per thread-group (multiple of 32)
+    int ng;           // thread-groups (groups in flight) per CTA
+    int threads;      // ng * lps
+    int sj;           // plane stride (words)
+    int row;          // words per quality row = 4 * sj
+    int minscore;     // first tallied quality
+    int nqv;          // tallied quality rows = 43 - minscore (row nqv is the trash row)
+    int wstart[MAX_G + 1];  // first lane of every row inside the thread-group
 };
 
 __host__ __device__ inline int gcd_int(int a, int b) {
@@ -74,15 +80,32 @@ __host__ __device__ inline int gcd_int(int a, int b) {
 
 inline bool make_geom(int L, int minscore, Geom *g) {
     if (L < 4 || minscore < 0 || minscore >= NQ) return false;
+    const int rps = 4 / gcd_int(L, 4);
+    int best_g = 0, best_lanes = 0, best_lps = 1;
+    for (int G = rps; G <= MAX_G; G += rps) {
+        int lanes = 0;
+        for (int k = 0; k < G; ++k) lanes += ((k * L) % 4 + L + 3) / 4;
+        const int lps = (lanes + 31) / 32 * 32;
+        if (lps > MAX_THREADS) break;
+        // strictly better lane efficiency wins; ties keep the smaller group
+        if (best_g == 0 || (long long)lanes * best_lps > (long long)best_lanes * lps) {
+            best_g = G; best_lanes = lanes; best_lps = lps;
+        }
+    }
+    if (best_g == 0) return false;
     g->L = L;
-    g->rps = 4 / gcd_int(L, 4);
-    g->srb = g->rps * L;
-    g->wps = g->srb / 4;
-    g->lps = (g->wps + 31) / 32 * 32;
-    if (g->lps > MAX_THREADS) return false;
+    g->G = best_g;
+    g->gbytes = best_g * L;
+    g->lanes = best_lanes;
+    g->lps = best_lps;
     g->ng = MAX_THREADS / g->lps;
     g->threads = g->ng * g->lps;
-    int planes = (2 * L + 3) / 4;
+    int w = 0;
+    for (int k = 0; k <= MAX_G; ++k) {
+        g->wstart[k] = w;
+        if (k < best_g) w += ((k * L) % 4 + L + 3) / 4;
+    }
+    const int planes = (2 * L + 3) / 4;
     g->sj = (planes + 7) / 8 * 8;
     g->row = 4 * g->sj;
     g->minscore = minscore;
@@ -93,10 +116,10 @@ inline bool make_geom(int L, int minscore, Geom *g) {
 // position of cycle-axis index c2 (0 .. 2L-1) inside a shared-memory quality row
 __host__ __device__ inline int plane_pos(int c2, int sj) { return (c2 & 3) * sj + (c2 >> 2); }
 
-// Work-list entry: one super-row seen from one read group.
-//   bits  0..31  super-row index
-//   bits 32..35  rows of the super-row that belong to this read group (and exist)
-//   bits 36..39  `second` flag of each row
+// Work-list entry: one group of G reads seen from one read group.
+//   bits  0..31  group index
+//   bits 32..39  rows of the group that belong to this read group (and exist)
+//   bits 40..47  `second` flag of each row
 typedef unsigned long long entry_t;
 
 // natural 2-bit code (b >> 1) & 3: A=0 C=1 T=2 G=3  ->  reference order A=0 T=1 G=2 C=3

@@ -119,7 +119,7 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
 
     Geom g;
     bool smem_ok = path != 2 && make_geom(L, minscore, &g) && g.row < 65536 &&
-                   (uint64_t)((N + g.rps - 1) / g.rps) < 0xFFFFFFFFull &&
+                   (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull &&
                    !misaligned(seq, 4) && !misaligned(qual, 4) && !misaligned(corr, 4);
     int drep = 32;
     if (smem_ok) {
@@ -137,7 +137,7 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
     }
     Workspace w = carve_workspace(workspace, N, L, R);
     if (!workspace || workspace_bytes < w.bytes) return KBBQ_E_WORKSPACE;
-    rc = run_prepare(rg, second, N, L, R, w, status, st);
+    rc = run_prepare(rg, second, N, g.G, R, w, status, st);
     if (rc) return rc;
 
     BuildArgs a;
@@ -239,7 +239,7 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
 
     Geom g;
     bool smem_ok = path != 2 && make_geom(L, minscore, &g) && g.row < 65536 &&
-                   (uint64_t)((N + g.rps - 1) / g.rps) < 0xFFFFFFFFull &&
+                   (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull &&
                    !misaligned(seq, 4) && !misaligned(qual, 4) && !misaligned(out_qual, 4);
     int drep = 32;
     if (smem_ok) {
@@ -253,7 +253,7 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
         KBBQ_LAUNCHED();
         return KBBQ_OK;
     }
-    rc = run_prepare(rg, second, N, L, R, w, status, st);
+    rc = run_prepare(rg, second, N, g.G, R, w, status, st);
     if (rc) return rc;
     ApplyArgs a;
     a.seq = seq; a.qual = qual; a.out = out_qual; a.total_bytes = N * L; a.g = g; a.R = R; a.nq = nq;

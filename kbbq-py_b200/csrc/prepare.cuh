@@ -1,11 +1,11 @@
 // prepare.cuh -- builds the per-read-group work list the build and apply kernels iterate over.
 //
 // The shared-memory tables of one CTA hold ONE read group (a cycle table for 32 read groups of
-// 250 bp reads would need 2.4 MB).  Reads of all groups are interleaved in the batch, so a tiny
-// pre-pass buckets SUPER-ROW indices (not data) by read group: entries[seg[g] .. seg[g+1]) lists
-// the super-rows that contain at least one read of group g, with the bitmask of those rows and
-// their `second` flags.  The main kernels then walk contiguous slices of that list; the read
-// data itself is never moved.  Cost: 3 B/read in, 8 B/super-row out and back in (< 1 % of the
+// 250 bp reads would need 2.4 MB).  Reads of all read groups are interleaved in the batch, so a tiny
+// pre-pass buckets GROUP indices (not data) by read group: entries[seg[g] .. seg[g+1]) lists the
+// groups of G reads (common.cuh) that contain at least one read of read group g, with the bitmask
+// of those rows and their `second` flags.  The main kernels walk contiguous slices of that list;
+// the read data itself is never moved.  Cost: 3 B/read in, 8 B/group out and back in (< 1 % of the
 // 3 B/base the build reads).
 #pragma once
 #include "common.cuh"
@@ -13,32 +13,35 @@
 namespace kbbq {
 
 constexpr int PREP_THREADS = 256;
-constexpr int PREP_ITEMS = 4;              // super-rows per thread
-constexpr int PREP_SMEM_RG = 8192;         // read groups countable in shared memory
+constexpr int PREP_SMEM_RG = 8192;  // read groups countable in shared memory
 
 struct PrepArgs {
     const uint16_t *rg;     // may be NULL (all zero)
     const uint8_t *second;  // may be NULL (all zero)
     long long N;            // reads
-    long long nsr;          // super-rows = ceil(N / rps)
-    int rps;
+    long long ngroups;      // ceil(N / G)
+    int G;
     int R;
     unsigned int *seg;      // [R + 1] segment offsets (out)
     unsigned int *cursor;   // [R] scratch
-    entry_t *entries;       // [nsr * rps] (out)
+    entry_t *entries;       // [ngroups * G] (out)
     int *status;
 };
 
-// rows of super-row `sr`: rg value (0xFFFFFFFF if the row does not exist) and second bits
-__device__ __forceinline__ void load_rows(const PrepArgs &a, long long sr, unsigned int rgv[4],
+__device__ __forceinline__ entry_t make_entry(long long grp, unsigned int match, unsigned int sec) {
+    return (entry_t)(unsigned int)grp | ((entry_t)match << 32) | ((entry_t)sec << 40);
+}
+
+// rows of group `grp`: rg value (0xFFFFFFFF if the row does not exist) and second bits
+__device__ __forceinline__ void load_rows(const PrepArgs &a, long long grp, unsigned int rgv[MAX_G],
                                           unsigned int &sec, unsigned int &exist) {
     sec = 0;
     exist = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < MAX_G; ++k) {
         rgv[k] = 0xFFFFFFFFu;
-        if (k < a.rps) {
-            long long r = sr * a.rps + k;
+        if (k < a.G) {
+            const long long r = grp * a.G + k;
             if (r < a.N) {
                 rgv[k] = a.rg ? a.rg[r] : 0u;
                 exist |= 1u << k;
@@ -50,28 +53,29 @@ __device__ __forceinline__ void load_rows(const PrepArgs &a, long long sr, unsig
 
 // Single read group: the list is the identity, no counting needed.
 __global__ void prep_identity_kernel(PrepArgs a) {
-    long long sr = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (sr == 0) {
+    const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (grp == 0) {
         a.seg[0] = 0;
-        a.seg[1] = (unsigned int)a.nsr;
+        a.seg[1] = (unsigned int)a.ngroups;
     }
-    if (sr >= a.nsr) return;
-    unsigned int rgv[4], sec, exist;
-    load_rows(a, sr, rgv, sec, exist);
+    if (grp >= a.ngroups) return;
+    unsigned int rgv[MAX_G], sec, exist;
+    load_rows(a, grp, rgv, sec, exist);
     if (a.rg) {
         unsigned int ok = 0;
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
+        for (int k = 0; k < MAX_G; ++k)
             if ((exist >> k) & 1) {
                 if (rgv[k] == 0) ok |= 1u << k;
                 else atomicOr(a.status, KBBQ_FLAG_RG_RANGE);
             }
         exist = ok;
     }
-    a.entries[sr] = (entry_t)(unsigned int)sr | ((entry_t)exist << 32) | ((entry_t)sec << 36);
+    a.entries[grp] = make_entry(grp, exist, sec);
 }
 
 // mode 0: count list entries per read group into a.cursor; mode 1: scatter entries.
+// One group per thread; per-block counts in shared memory, one global atomic per (block, read group).
 template <int MODE>
 __global__ void __launch_bounds__(PREP_THREADS) prep_bucket_kernel(PrepArgs a) {
     extern __shared__ unsigned int s_cnt[];  // [R] when R <= PREP_SMEM_RG
@@ -80,69 +84,54 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_bucket_kernel(PrepArgs a) {
         for (int i = threadIdx.x; i < a.R; i += blockDim.x) s_cnt[i] = 0;
         __syncthreads();
     }
-    const long long base = ((long long)blockIdx.x * blockDim.x) * PREP_ITEMS + threadIdx.x;
-    unsigned int slot[PREP_ITEMS][4];  // MODE 1: position of each (item, distinct rg) inside the block's share
-    unsigned int rgs[PREP_ITEMS][4], masks[PREP_ITEMS][4], secs[PREP_ITEMS];
+    const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    unsigned int rgv[MAX_G], exist = 0, sec = 0;
+    unsigned int slot[MAX_G], mask[MAX_G];
+    if (grp < a.ngroups) load_rows(a, grp, rgv, sec, exist);
 #pragma unroll
-    for (int it = 0; it < PREP_ITEMS; ++it) {
-        long long sr = base + (long long)it * blockDim.x;
-        unsigned int rgv[4], exist = 0;
-        secs[it] = 0;
-        if (sr < a.nsr) load_rows(a, sr, rgv, secs[it], exist);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            masks[it][k] = 0;
-            rgs[it][k] = 0;
-            slot[it][k] = 0;
-            if (!((exist >> k) & 1)) continue;
-            unsigned int v = rgv[k];
-            if (v >= (unsigned int)a.R) {
-                atomicOr(a.status, KBBQ_FLAG_RG_RANGE);
-                continue;
-            }
-            bool first = true;  // is row k the first row of this super-row with value v?
-            unsigned int m = 0;
-#pragma unroll
-            for (int k2 = 0; k2 < 4; ++k2) {
-                if (((exist >> k2) & 1) && rgv[k2] == v) {
-                    if (k2 < k) first = false;
-                    m |= 1u << k2;
-                }
-            }
-            if (!first) continue;
-            masks[it][k] = m;
-            rgs[it][k] = v;
-            if (use_smem) slot[it][k] = atomicAdd(&s_cnt[v], 1u);
-            else if (MODE == 0) atomicAdd(&a.cursor[v], 1u);
-            else slot[it][k] = atomicAdd(&a.cursor[v], 1u);
+    for (int k = 0; k < MAX_G; ++k) {
+        mask[k] = 0;
+        slot[k] = 0;
+        if (!((exist >> k) & 1)) continue;
+        const unsigned int v = rgv[k];
+        if (v >= (unsigned int)a.R) {
+            atomicOr(a.status, KBBQ_FLAG_RG_RANGE);
+            continue;
         }
+        bool first = true;  // is row k the first row of this group with value v?
+        unsigned int m = 0;
+#pragma unroll
+        for (int k2 = 0; k2 < MAX_G; ++k2) {
+            if (((exist >> k2) & 1) && rgv[k2] == v) {
+                if (k2 < k) first = false;
+                m |= 1u << k2;
+            }
+        }
+        if (!first) continue;
+        mask[k] = m;
+        if (use_smem) slot[k] = atomicAdd(&s_cnt[v], 1u);
+        else slot[k] = atomicAdd(&a.cursor[v], 1u);
     }
     if (use_smem) {
         __syncthreads();
-        // one global atomic per (block, read group): reserve the block's share
         for (int i = threadIdx.x; i < a.R; i += blockDim.x) {
-            unsigned int c = s_cnt[i];
-            if (c) s_cnt[i] = atomicAdd(&a.cursor[i], c);
+            const unsigned int c = s_cnt[i];
+            if (c) s_cnt[i] = atomicAdd(&a.cursor[i], c);  // reserve the block's share
         }
         if (MODE == 0) return;
         __syncthreads();
     }
     if (MODE == 1) {
 #pragma unroll
-        for (int it = 0; it < PREP_ITEMS; ++it) {
-            long long sr = base + (long long)it * blockDim.x;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (!masks[it][k]) continue;
-                unsigned int pos = slot[it][k] + (use_smem ? s_cnt[rgs[it][k]] : 0u);
-                a.entries[pos] = (entry_t)(unsigned int)sr | ((entry_t)masks[it][k] << 32) |
-                                 ((entry_t)secs[it] << 36);
-            }
+        for (int k = 0; k < MAX_G; ++k) {
+            if (!mask[k]) continue;
+            const unsigned int pos = slot[k] + (use_smem ? s_cnt[rgv[k]] : 0u);
+            a.entries[pos] = make_entry(grp, mask[k], sec);
         }
     }
 }
 
-// Exclusive scan of the per-group counts (one block): seg[0..R], cursor[g] = seg[g].
+// Exclusive scan of the per-read-group counts (one block): seg[0..R], cursor[g] = seg[g].
 __global__ void prep_scan_kernel(PrepArgs a) {
     __shared__ unsigned int s_part[1024];
     const int T = blockDim.x;
@@ -155,7 +144,7 @@ __global__ void prep_scan_kernel(PrepArgs a) {
     if (threadIdx.x == 0) {
         unsigned int run = 0;
         for (int t = 0; t < T; ++t) {
-            unsigned int v = s_part[t];
+            const unsigned int v = s_part[t];
             s_part[t] = run;
             run += v;
         }
@@ -164,7 +153,7 @@ __global__ void prep_scan_kernel(PrepArgs a) {
     __syncthreads();
     unsigned int run = s_part[threadIdx.x];
     for (int i = lo; i < hi; ++i) {
-        unsigned int v = a.cursor[i];
+        const unsigned int v = a.cursor[i];
         a.seg[i] = run;
         a.cursor[i] = run;
         run += v;
@@ -184,16 +173,14 @@ struct Workspace {
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 inline Workspace carve_workspace(void *base, long long N, int L, int R) {
-    Geom g;
     Workspace w = {};
-    int rps = 4 / gcd_int(L, 4);
-    (void)g;
-    long long nsr = (N + rps - 1) / rps;
     size_t off = 0;
     char *p = (char *)base;
+    // a group never lists more entries than it has rows, so N (+ padding) entries always suffice
+    const size_t max_entries = (size_t)N + MAX_G;
     w.seg = (unsigned int *)(p + off);      off = align_up(off + sizeof(unsigned int) * ((size_t)R + 1), 256);
     w.cursor = (unsigned int *)(p + off);   off = align_up(off + sizeof(unsigned int) * (size_t)R, 256);
-    w.entries = (entry_t *)(p + off);       off = align_up(off + sizeof(entry_t) * (size_t)nsr * rps, 256);
+    w.entries = (entry_t *)(p + off);       off = align_up(off + sizeof(entry_t) * max_entries, 256);
     w.fold_cyc = (short *)(p + off);        off = align_up(off + sizeof(short) * (size_t)R * NQ * 2 * L, 256);
     w.fold_din = (short *)(p + off);        off = align_up(off + sizeof(short) * (size_t)R * NQ * 32, 256);
     w.bytes = off;
@@ -201,25 +188,23 @@ inline Workspace carve_workspace(void *base, long long N, int L, int R) {
 }
 
 // Enqueue the pre-pass.  After it, seg[R] (device) holds the number of entries.
-inline int run_prepare(const uint16_t *rg, const uint8_t *second, long long N, int L, int R,
+inline int run_prepare(const uint16_t *rg, const uint8_t *second, long long N, int G, int R,
                        const Workspace &w, int *status, cudaStream_t st) {
     PrepArgs a;
-    a.rg = rg; a.second = second; a.N = N; a.rps = 4 / gcd_int(L, 4);
-    a.nsr = (N + a.rps - 1) / a.rps; a.R = R;
+    a.rg = rg; a.second = second; a.N = N; a.G = G;
+    a.ngroups = (N + G - 1) / G; a.R = R;
     a.seg = w.seg; a.cursor = w.cursor; a.entries = w.entries; a.status = status;
-    if (a.nsr == 0) {
+    if (a.ngroups == 0) {
         KBBQ_CUDA(cudaMemsetAsync(w.seg, 0, sizeof(unsigned int) * ((size_t)R + 1), st));
         return KBBQ_OK;
     }
+    const unsigned int blocks = (unsigned int)((a.ngroups + PREP_THREADS - 1) / PREP_THREADS);
     if (R == 1) {
-        unsigned int blocks = (unsigned int)((a.nsr + 255) / 256);
-        prep_identity_kernel<<<blocks, 256, 0, st>>>(a);
+        prep_identity_kernel<<<blocks, PREP_THREADS, 0, st>>>(a);
         KBBQ_LAUNCHED();
         return KBBQ_OK;
     }
-    const long long per_block = (long long)PREP_THREADS * PREP_ITEMS;
-    unsigned int blocks = (unsigned int)((a.nsr + per_block - 1) / per_block);
-    size_t smem = R <= PREP_SMEM_RG ? sizeof(unsigned int) * (size_t)R : 0;
+    const size_t smem = R <= PREP_SMEM_RG ? sizeof(unsigned int) * (size_t)R : 0;
     KBBQ_CUDA(cudaMemsetAsync(w.cursor, 0, sizeof(unsigned int) * (size_t)R, st));
     prep_bucket_kernel<0><<<blocks, PREP_THREADS, smem, st>>>(a);
     KBBQ_LAUNCHED();
