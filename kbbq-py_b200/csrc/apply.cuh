@@ -12,14 +12,15 @@
 #pragma once
 #include "build.cuh"
 #include "common.cuh"
+#include "stage.cuh"
 
 namespace kbbq {
 
 struct ApplyArgs {
     const uint8_t *seq, *qual;
     uint8_t *out;
-    long long total_bytes;
     Geom g;
+    StageLayout sl;
     int R, nq;
     const entry_t *entries;
     const unsigned int *seg;
@@ -30,11 +31,35 @@ struct ApplyArgs {
 
 template <int DREP>
 __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(ApplyArgs a) {
-    extern __shared__ unsigned int smem[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     const Geom &g = a.g;
+    const StageLayout &sl = a.sl;
     const int nqv = g.nqv, row = g.row;
-    int *t_cyc = reinterpret_cast<int *>(smem);  // [nqv + 1][row]        (+ zero trash row)
-    int *t_din = t_cyc + (nqv + 1) * row;        // [nqv + 1][17][DREP]   (+ zero trash row)
+    int *t_cyc = reinterpret_cast<int *>(smem_raw);  // [nqv + 1][row]        (+ zero trash row)
+    int *t_din = t_cyc + (nqv + 1) * row;            // [nqv + 1][17][DREP]   (+ zero trash row)
+    const int nconsumers = g.threads;
+
+    const unsigned long long E = a.seg[a.R];
+    const uint32_t lo = (uint32_t)(E * blockIdx.x / gridDim.x), hi = (uint32_t)(E * (blockIdx.x + 1) / gridDim.x);
+
+    const uint32_t bar0 = smem_u32(smem_raw + sl.bar_off);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < sl.stages; ++s) {
+            mbar_init(bar0 + s * 8, 1);
+            mbar_init(bar0 + (sl.stages + s) * 8, nconsumers / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if ((int)threadIdx.x >= nconsumers) {  // ---- producer warp ----
+        ProducerArgs p;
+        p.arr[0] = a.seq; p.arr[1] = a.qual; p.arr[2] = nullptr;
+        p.entries = a.entries; p.seg = a.seg; p.R = a.R; p.lo = lo; p.hi = hi;
+        p.gbytes = g.gbytes; p.ng = g.ng;
+        producer_loop(p, sl, smem_raw);
+        return;
+    }
 
     const ThreadMap m = make_thread_map(g);
     const int lane = threadIdx.x & 31;
@@ -47,12 +72,13 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(ApplyArgs a)
     uint32_t afwd[4], arev[4];
 #pragma unroll
     for (int b = 0; b < 4; ++b) { afwd[b] = pin(cyc_base + m.fwd[b]); arev[b] = pin(cyc_base + m.rev[b]); }
-    const uint32_t gbytes = g.gbytes, ng = g.ng;
-    const uint32_t last_grp = (uint32_t)((a.total_bytes / g.L + g.G - 1) / g.G) - 1u;
+    const uint32_t data0 = smem_u32(smem_raw + sl.data_off) + m.toff;
+    const uint32_t hdr0 = smem_u32(smem_raw + sl.hdr_off) + m.grp * 16;
+    const uint32_t stage_bytes = sl.narr * sl.abytes, abytes = sl.abytes, hdr_stride = g.ng * 16;
+    const uint32_t prev_keep = m.need_prev ? 0u : 7u;
     const uint32_t nqlim4 = (uint32_t)(127 - (a.nq - 1)) * ONE4;  // q + this has bit 7 set iff q >= nq
-
-    const unsigned long long E = a.seg[a.R];
-    const uint32_t lo = (uint32_t)(E * blockIdx.x / gridDim.x), hi = (uint32_t)(E * (blockIdx.x + 1) / gridDim.x);
+    const bool full_word = m.rowmask == 0xFFFFFFFFu;
+    uint32_t stage = 0, phase = 0;
     uint32_t qbad = 0;
 
     for (int rg = 0; rg < a.R; ++rg) {
@@ -63,33 +89,45 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(ApplyArgs a)
         if (s_hi > hi) s_hi = hi;
 
         // stage this read group's folded tables (trash row = 0)
-        __syncthreads();
+        consumer_sync(nconsumers);
         const int L2 = 2 * g.L;
         const short *fc = a.fold_cyc + ((size_t)rg * NQ + g.minscore) * L2;
-        for (int i = threadIdx.x; i < nqv * L2; i += blockDim.x) {
+        for (int i = threadIdx.x; i < nqv * L2; i += nconsumers) {
             const int q = i / L2, c2 = i - q * L2;
             t_cyc[q * row + plane_pos(c2, g.sj)] = fc[i];
         }
-        for (int i = threadIdx.x; i < row; i += blockDim.x) t_cyc[nqv * row + i] = 0;
+        for (int i = threadIdx.x; i < row; i += nconsumers) t_cyc[nqv * row + i] = 0;
         const short *fd = a.fold_din + ((size_t)rg * NQ + g.minscore) * 32;
-        for (int i = threadIdx.x; i < (nqv + 1) * DIN_SLOTS * DREP; i += blockDim.x) {
-            const int cell = i / DREP, q = cell / DIN_SLOTS, sl = cell - q * DIN_SLOTS;
-            t_din[i] = q < nqv ? fd[q * 32 + sl] : 0;
+        for (int i = threadIdx.x; i < (nqv + 1) * DIN_SLOTS * DREP; i += nconsumers) {
+            const int cell = i / DREP, q = cell / DIN_SLOTS, sl_ = cell - q * DIN_SLOTS;
+            t_din[i] = q < nqv ? fd[q * 32 + sl_] : 0;
         }
-        __syncthreads();
+        consumer_sync(nconsumers);
 
-        uint32_t it = s_lo + m.grp;
-        Fetch nx = fetch_words<false>(a.seq, a.qual, nullptr, a.entries, it, s_hi, m, gbytes, rowbit, last_grp, a.total_bytes);
-        for (; it < s_hi; it += ng) {
-            const Fetch cur = nx;
-            nx = fetch_words<false>(a.seq, a.qual, nullptr, a.entries, it + ng, s_hi, m, gbytes, rowbit, last_grp, a.total_bytes);
-            const uint32_t sw = cur.sw, qw = cur.qw;
-            const uint32_t am = cur.bits ? m.rowmask : 0u;
+        for (uint32_t first = s_lo; first < s_hi; first += g.ng) {
+            mbar_wait(bar0 + stage * 8, phase);
+            uint32_t bits, soff, grp, hpad;
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(bits), "=r"(soff), "=r"(grp), "=r"(hpad)
+                         : "r"(hdr0 + stage * hdr_stride));
+            uint32_t sw = 0, qw = 0, pb = 0;
+            const bool mine = (bits & rowbit) != 0;
+            if (mine) {
+                const uint32_t wa = data0 + stage * stage_bytes + soff;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sw) : "r"(wa));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qw) : "r"(wa + abytes));
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pb) : "r"(wa - 1));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + (sl.stages + stage) * 8);
+            if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
+            if (!mine) continue;
+            const uint32_t am = m.rowmask;
+            // global byte offset of this word: group index * group bytes + offset inside the group
+            const long long off = (long long)((unsigned long long)grp * g.gbytes) + m.toff;
 
             const uint32_t code3 = (sw >> 1) & 0x07070707u;
-            uint32_t pv3 = __shfl_up_sync(0xFFFFFFFFu, code3 >> 24, 1);
-            if (lane == 0) pv3 = (am && m.need_prev) ? ((uint32_t)__ldg(a.seq + cur.off - 1) >> 1) & 7u : 7u;
-            if (!am) continue;
+            const uint32_t pv3 = ((pb >> 1) & 7u) | prev_keep;
             const uint32_t pc3 = __byte_perm(pv3, code3, 0x6540);
 
             const uint32_t bad = ((qw + nqlim4) | qw) & H4 & am;  // q >= nq: IndexError in the reference
@@ -101,7 +139,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(ApplyArgs a)
             const uint32_t q4 = (qw & vm8) | (trash4 & ~vm8);
             const uint32_t din4 = ((pc3 << 2) & 0x0C0C0C0Cu) | (code3 & 0x03030303u);
             const uint32_t d4 = (din4 & dm8) | (0x10101010u & ~dm8);  // invalid dinuc -> the pad slot
-            const bool sec = (cur.bits & secbit) != 0;
+            const bool sec = (bits & secbit) != 0;
 
             uint32_t v[4];
 #pragma unroll
@@ -115,12 +153,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(ApplyArgs a)
             }
             const uint32_t sum4 = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
             const uint32_t res = (sum4 & vm8) | (qw & ~vm8);  // untouched below minscore
-            if (am == 0xFFFFFFFFu && cur.off + 4 <= a.total_bytes) {
-                *reinterpret_cast<unsigned int *>(a.out + cur.off) = res;
+            if (full_word) {
+                *reinterpret_cast<unsigned int *>(a.out + off) = res;
             } else {
 #pragma unroll
                 for (int b = 0; b < 4; ++b)
-                    if (((am >> (8 * b)) & 1u) && cur.off + b < a.total_bytes) a.out[cur.off + b] = (uint8_t)(res >> (8 * b));
+                    if ((am >> (8 * b)) & 1u) a.out[off + b] = (uint8_t)(res >> (8 * b));
             }
         }
     }

@@ -16,13 +16,15 @@
 //   * bases that must not be tallied (q < minscore, bytes of a neighbouring read, invalid dinuc)
 //     are steered to a TRASH row / slot by byte-parallel selects instead of per-byte predicates,
 //     so the eight reductions of a word are unconditional `red.shared.add.u32`;
-//   * the next word of each stream is prefetched before the current one is tallied;
+//   * reads reach the SM through a TMA bulk-copy ring filled by a producer warp (stage.cuh): HBM
+//     is read exactly once and the consumers' hot loop holds no global loads;
 //   * mismatches (about 1 % of bases) take a divergent slow path into unreplicated tables;
 //   * tables are per-CTA u32 in shared memory, flushed once per read-group segment to the global
 //     int64 tables with 64-bit reductions (zero cells skipped).
 #pragma once
 #include "common.cuh"
 #include "prepare.cuh"
+#include "stage.cuh"
 
 namespace kbbq {
 
@@ -30,22 +32,14 @@ constexpr int DIN_SLOTS = 17;  // 16 dinucleotides + 1 trash slot
 
 struct BuildArgs {
     const uint8_t *seq, *qual, *corr;
-    long long total_bytes;  // N * L
     Geom g;
+    StageLayout sl;
     int R;
     const entry_t *entries;
     const unsigned int *seg;  // [R + 1]
     unsigned long long *pos_errs, *pos_total, *din_errs, *din_total;
     int *status;
 };
-
-__device__ __forceinline__ uint32_t ld_word_guarded(const uint8_t *p, long long off, long long total) {
-    if (off + 4 <= total) return __ldg(reinterpret_cast<const unsigned int *>(p + off));
-    uint32_t v = 0;
-    for (int b = 0; b < 4; ++b)
-        if (off + b < total) v |= (uint32_t)__ldg(p + off + b) << (8 * b);
-    return v;
-}
 
 __device__ __forceinline__ void red_shared_inc(uint32_t saddr) {
     asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr));
@@ -98,40 +92,6 @@ __device__ __forceinline__ ThreadMap make_thread_map(const Geom &g) {
     return m;
 }
 
-// The words of one group position, fetched ahead of their use.
-struct Fetch {
-    uint32_t sw, qw, cw, bits;
-    long long off;
-};
-
-// `last_grp` is the only group whose words can reach past the end of the arrays.
-template <bool WITH_CORR>
-__device__ __forceinline__ Fetch fetch_words(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr,
-                                             const entry_t *entries, uint32_t it, uint32_t end,
-                                             const ThreadMap &m, uint32_t gbytes, uint32_t rowbit,
-                                             uint32_t last_grp, long long total) {
-    Fetch f;
-    f.sw = 0; f.qw = 0; f.cw = 0; f.bits = 0; f.off = 0;
-    if (it < end) {
-        const entry_t e = __ldg(entries + it);
-        const uint32_t grp = (uint32_t)e, bits = (uint32_t)(e >> 32);
-        f.off = (long long)((unsigned long long)grp * gbytes) + m.toff;
-        if (bits & rowbit) {
-            f.bits = bits;
-            if (grp != last_grp) {
-                f.sw = __ldg(reinterpret_cast<const unsigned int *>(seq + f.off));
-                f.qw = __ldg(reinterpret_cast<const unsigned int *>(qual + f.off));
-                if (WITH_CORR) f.cw = __ldg(reinterpret_cast<const unsigned int *>(corr + f.off));
-            } else {
-                f.sw = ld_word_guarded(seq, f.off, total);
-                f.qw = ld_word_guarded(qual, f.off, total);
-                if (WITH_CORR) f.cw = ld_word_guarded(corr, f.off, total);
-            }
-        }
-    }
-    return f;
-}
-
 // keep a loop-invariant value in its register instead of letting ptxas rematerialise it
 __device__ __forceinline__ uint32_t pin(uint32_t v) {
     asm volatile("" : "+r"(v));
@@ -140,15 +100,42 @@ __device__ __forceinline__ uint32_t pin(uint32_t v) {
 
 template <int DREP, bool VALIDATE>
 __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a) {
-    extern __shared__ unsigned int smem[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    unsigned int *smem = reinterpret_cast<unsigned int *>(smem_raw);
     const Geom &g = a.g;
+    const StageLayout &sl = a.sl;
     const int nqv = g.nqv, row = g.row;
     unsigned int *pos_t = smem;                              // [nqv + 1][row]           (+ trash row)
     unsigned int *din_t = pos_t + (nqv + 1) * row;           // [nqv + 1][17][DREP]      (+ trash row / slot)
     unsigned int *pos_e = din_t + (nqv + 1) * DIN_SLOTS * DREP;  // [nqv][row]
     unsigned int *din_e = pos_e + nqv * row;                 // [nqv][16]
-    const int smem_words = (nqv + 1) * row + (nqv + 1) * DIN_SLOTS * DREP + nqv * row + nqv * 16;
+    const int table_words = (nqv + 1) * row + (nqv + 1) * DIN_SLOTS * DREP + nqv * row + nqv * 16;
+    const int nconsumers = g.threads;                        // + one producer warp
 
+    // this CTA's slice of the concatenated work list
+    const unsigned long long E = a.seg[a.R];
+    const uint32_t lo = (uint32_t)(E * blockIdx.x / gridDim.x), hi = (uint32_t)(E * (blockIdx.x + 1) / gridDim.x);
+
+    const uint32_t bar0 = smem_u32(smem_raw + sl.bar_off);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < sl.stages; ++s) {
+            mbar_init(bar0 + s * 8, 1);                               // full: the producer's arrive + tx bytes
+            mbar_init(bar0 + (sl.stages + s) * 8, nconsumers / 32);   // empty: one arrive per consumer warp
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if ((int)threadIdx.x >= nconsumers) {  // ---- producer warp ----
+        ProducerArgs p;
+        p.arr[0] = a.seq; p.arr[1] = a.qual; p.arr[2] = a.corr;
+        p.entries = a.entries; p.seg = a.seg; p.R = a.R; p.lo = lo; p.hi = hi;
+        p.gbytes = g.gbytes; p.ng = g.ng;
+        producer_loop(p, sl, smem_raw);
+        return;
+    }
+
+    // ---- consumer warps ----
     const ThreadMap m = make_thread_map(g);
     const int lane = threadIdx.x & 31;
     const uint32_t minq4 = (uint32_t)g.minscore * ONE4;
@@ -161,12 +148,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a)
     uint32_t afwd[4], arev[4];  // absolute shared addresses of quality row 0 at this thread's cycles
 #pragma unroll
     for (int b = 0; b < 4; ++b) { afwd[b] = pin(pos_base + m.fwd[b]); arev[b] = pin(pos_base + m.rev[b]); }
-    const uint32_t gbytes = g.gbytes, ng = g.ng;
-    const uint32_t last_grp = (uint32_t)((a.total_bytes / g.L + g.G - 1) / g.G) - 1u;
-
-    // this CTA's slice of the concatenated work list
-    const unsigned long long E = a.seg[a.R];
-    const uint32_t lo = (uint32_t)(E * blockIdx.x / gridDim.x), hi = (uint32_t)(E * (blockIdx.x + 1) / gridDim.x);
+    const uint32_t data0 = smem_u32(smem_raw + sl.data_off) + m.toff;
+    const uint32_t hdr0 = smem_u32(smem_raw + sl.hdr_off) + m.grp * 16;
+    const uint32_t stage_bytes = sl.narr * sl.abytes, abytes = sl.abytes, hdr_stride = g.ng * 16;
+    const uint32_t prev_keep = m.need_prev ? 0u : 7u;  // no predecessor in this row -> treat as N
+    uint32_t stage = 0, phase = 0;
     uint32_t qbad = 0, bbad = 0;
 
     for (int rg = 0; rg < a.R; ++rg) {
@@ -176,22 +162,31 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a)
         if (s_lo < lo) s_lo = lo;
         if (s_hi > hi) s_hi = hi;
 
-        for (int i = threadIdx.x; i < smem_words; i += blockDim.x) smem[i] = 0;
-        __syncthreads();
+        for (int i = threadIdx.x; i < table_words; i += nconsumers) smem[i] = 0;
+        consumer_sync(nconsumers);
 
-        uint32_t it = s_lo + m.grp;
-        Fetch nx = fetch_words<true>(a.seq, a.qual, a.corr, a.entries, it, s_hi, m, gbytes, rowbit, last_grp, a.total_bytes);
-        for (; it < s_hi; it += ng) {
-            const Fetch cur = nx;
-            nx = fetch_words<true>(a.seq, a.qual, a.corr, a.entries, it + ng, s_hi, m, gbytes, rowbit, last_grp, a.total_bytes);
-            const uint32_t sw = cur.sw, qw = cur.qw;
-            const uint32_t am = cur.bits ? m.rowmask : 0u;
+        for (uint32_t first = s_lo; first < s_hi; first += g.ng) {
+            mbar_wait(bar0 + stage * 8, phase);
+            uint32_t bits, soff;
+            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bits), "=r"(soff) : "r"(hdr0 + stage * hdr_stride));
+            uint32_t sw = 0, qw = 0, cw = 0, pb = 0;
+            const bool mine = (bits & rowbit) != 0;
+            if (mine) {
+                const uint32_t wa = data0 + stage * stage_bytes + soff;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sw) : "r"(wa));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qw) : "r"(wa + abytes));
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(wa + 2 * abytes));
+                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pb) : "r"(wa - 1));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar0 + (sl.stages + stage) * 8);  // the stage may be refilled
+            if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
+            if (!mine) continue;  // padding lane, or the row belongs to another read group
+            const uint32_t am = m.rowmask;
 
             // 3-bit base code (b >> 1) & 7: A=0 C=1 T=2 G=3 N=7, injective on ACGTN
             const uint32_t code3 = (sw >> 1) & 0x07070707u;
-            uint32_t pv3 = __shfl_up_sync(0xFFFFFFFFu, code3 >> 24, 1);
-            if (lane == 0) pv3 = (am && m.need_prev) ? ((uint32_t)__ldg(a.seq + cur.off - 1) >> 1) & 7u : 7u;
-            if (!am) continue;  // padding lane, or the row belongs to another read group
+            const uint32_t pv3 = ((pb >> 1) & 7u) | prev_keep;
             const uint32_t pc3 = __byte_perm(pv3, code3, 0x6540);  // previous base of every byte
 
             const uint32_t bad = ((qw + 0x55555555u) | qw) & H4 & am;             // q > 42
@@ -211,7 +206,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a)
                 bbad |= (recon ^ sw) & am;
             }
             // read-2 rows count cycles from the end of the axis
-            const bool sec = (cur.bits & secbit) != 0;
+            const bool sec = (bits & secbit) != 0;
 #pragma unroll
             for (int b = 0; b < 4; ++b) {
                 const uint32_t qb = __byte_perm(q4, 0, 0x4440 + b);
@@ -220,7 +215,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a)
                 red_shared_inc(qb * dq_bytes + (db * (DREP * 4) + din_base));
             }
             // mismatches: rare, divergent
-            const uint32_t x = sw ^ cur.cw;
+            const uint32_t x = sw ^ cw;
             const uint32_t xm = (((x | H4) - ONE4) | x) & vm;  // byte differs and is tallied
             if (xm) {
 #pragma unroll
@@ -235,12 +230,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a)
                 }
             }
         }
-        __syncthreads();
+        consumer_sync(nconsumers);
 
         // flush this read group's partial tables: u32 shared -> int64 global
         const int L2 = 2 * g.L;
         unsigned long long *gpe = a.pos_errs + (size_t)rg * NQ * L2, *gpt = a.pos_total + (size_t)rg * NQ * L2;
-        for (int i = threadIdx.x; i < nqv * L2; i += blockDim.x) {
+        for (int i = threadIdx.x; i < nqv * L2; i += nconsumers) {
             const int q = i / L2, c2 = i - q * L2;
             const int s = q * row + plane_pos(c2, g.sj);
             const unsigned int t = pos_t[s], er = pos_e[s];
@@ -249,7 +244,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a)
             if (er) atomicAdd(gpe + o, (unsigned long long)er);
         }
         unsigned long long *gde = a.din_errs + (size_t)rg * NQ * 16, *gdt = a.din_total + (size_t)rg * NQ * 16;
-        for (int i = threadIdx.x; i < nqv * 16; i += blockDim.x) {
+        for (int i = threadIdx.x; i < nqv * 16; i += nconsumers) {
             const int q = i >> 4, dn = i & 15;
             unsigned int t = 0;
 #pragma unroll 8
@@ -261,7 +256,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a)
             if (t) atomicAdd(gdt + o, (unsigned long long)t);
             if (er) atomicAdd(gde + o, (unsigned long long)er);
         }
-        __syncthreads();
+        consumer_sync(nconsumers);
     }
     if (qbad) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
     if (VALIDATE && bbad) atomicOr(a.status, KBBQ_FLAG_BAD_BASE);

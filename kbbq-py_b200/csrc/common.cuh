@@ -86,7 +86,7 @@ inline bool make_geom(int L, int minscore, Geom *g) {
         int lanes = 0;
         for (int k = 0; k < G; ++k) lanes += ((k * L) % 4 + L + 3) / 4;
         const int lps = (lanes + 31) / 32 * 32;
-        if (lps > MAX_THREADS) break;
+        if (lps > MAX_THREADS - 32) break;  // one warp is the TMA producer
         // strictly better lane efficiency wins; ties keep the smaller group
         if (best_g == 0 || (long long)lanes * best_lps > (long long)best_lanes * lps) {
             best_g = G; best_lanes = lanes; best_lps = lps;
@@ -98,7 +98,7 @@ inline bool make_geom(int L, int minscore, Geom *g) {
     g->gbytes = best_g * L;
     g->lanes = best_lanes;
     g->lps = best_lps;
-    g->ng = MAX_THREADS / g->lps;
+    g->ng = (MAX_THREADS - 32) / g->lps;
     g->threads = g->ng * g->lps;
     int w = 0;
     for (int k = 0; k <= MAX_G; ++k) {

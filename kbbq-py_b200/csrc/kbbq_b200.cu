@@ -55,11 +55,26 @@ static int current_device_info(int *device, int *sms, int *max_smem) {
 
 static bool misaligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) != 0; }
 
+// Largest dinuc replication (bank-conflict freedom) and ring depth that fit the CTA's shared memory:
+// at least 2 stages, then replication, then up to MAX_STAGES.
+static bool pick_smem_config(const Geom &g, int narr, int max_smem, size_t (*table_bytes)(const Geom &, int),
+                             int *drep, int *stages) {
+    for (int d = 32; d >= 1; d >>= 1) {
+        for (int s = MAX_STAGES; s >= 2; --s) {
+            if (make_stage_layout(g, narr, s, table_bytes(g, d)).total <= max_smem) {
+                *drep = d; *stages = s;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
 template <int DREP>
 static int launch_build_smem(const BuildArgs &a, int grid, size_t smem, cudaStream_t st) {
     auto kern = build_smem_kernel<DREP, true>;
     KBBQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, a.g.threads, smem, st>>>(a);
+    kern<<<grid, a.g.threads + 32, smem, st>>>(a);  // + the producer warp
     KBBQ_LAUNCHED();
     return KBBQ_OK;
 }
@@ -68,7 +83,7 @@ template <int DREP>
 static int launch_apply_smem(const ApplyArgs &a, int grid, size_t smem, cudaStream_t st) {
     auto kern = apply_smem_kernel<DREP>;
     KBBQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, a.g.threads, smem, st>>>(a);
+    kern<<<grid, a.g.threads + 32, smem, st>>>(a);  // + the producer warp
     KBBQ_LAUNCHED();
     return KBBQ_OK;
 }
@@ -120,12 +135,9 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
     Geom g;
     bool smem_ok = path != 2 && make_geom(L, minscore, &g) && g.row < 65536 &&
                    (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull &&
-                   !misaligned(seq, 4) && !misaligned(qual, 4) && !misaligned(corr, 4);
-    int drep = 32;
-    if (smem_ok) {
-        while (drep >= 1 && build_smem_bytes(g, drep) > (size_t)max_smem) drep >>= 1;
-        if (drep < 1) smem_ok = false;
-    }
+                   !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(corr, 16);
+    int drep = 32, stages = 0;
+    if (smem_ok) smem_ok = pick_smem_config(g, 3, max_smem, build_smem_bytes, &drep, &stages);
     if (!smem_ok) {
         if (path == 1) return KBBQ_E_ARG;
         BuildGenericArgs a = {seq, qual, corr, rg, second, N, L, R, minscore,
@@ -141,12 +153,13 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
     if (rc) return rc;
 
     BuildArgs a;
-    a.seq = seq; a.qual = qual; a.corr = corr; a.total_bytes = N * L; a.g = g; a.R = R;
+    a.seq = seq; a.qual = qual; a.corr = corr; a.g = g; a.R = R;
+    a.sl = make_stage_layout(g, 3, stages, build_smem_bytes(g, drep));
     a.entries = w.entries; a.seg = w.seg;
     a.pos_errs = (unsigned long long *)pos_errs; a.pos_total = (unsigned long long *)pos_total;
     a.din_errs = (unsigned long long *)din_errs; a.din_total = (unsigned long long *)din_total;
     a.status = status;
-    const size_t smem = build_smem_bytes(g, drep);
+    const size_t smem = a.sl.total;
     switch (drep) {
     case 32: return launch_build_smem<32>(a, sms, smem, st);
     case 16: return launch_build_smem<16>(a, sms, smem, st);
@@ -240,12 +253,9 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
     Geom g;
     bool smem_ok = path != 2 && make_geom(L, minscore, &g) && g.row < 65536 &&
                    (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull &&
-                   !misaligned(seq, 4) && !misaligned(qual, 4) && !misaligned(out_qual, 4);
-    int drep = 32;
-    if (smem_ok) {
-        while (drep >= 1 && apply_smem_bytes(g, drep) > (size_t)max_smem) drep >>= 1;
-        if (drep < 1) smem_ok = false;
-    }
+                   !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(out_qual, 4);
+    int drep = 32, stages = 0;
+    if (smem_ok) smem_ok = pick_smem_config(g, 2, max_smem, apply_smem_bytes, &drep, &stages);
     if (!smem_ok) {
         if (path == 1) return KBBQ_E_ARG;
         ApplyGenericArgs a = {seq, qual, rg, second, out_qual, N, L, R, minscore, nq, w.fold_cyc, w.fold_din, status};
@@ -256,9 +266,10 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
     rc = run_prepare(rg, second, N, g.G, R, w, status, st);
     if (rc) return rc;
     ApplyArgs a;
-    a.seq = seq; a.qual = qual; a.out = out_qual; a.total_bytes = N * L; a.g = g; a.R = R; a.nq = nq;
+    a.seq = seq; a.qual = qual; a.out = out_qual; a.g = g; a.R = R; a.nq = nq;
+    a.sl = make_stage_layout(g, 2, stages, apply_smem_bytes(g, drep));
     a.entries = w.entries; a.seg = w.seg; a.fold_cyc = w.fold_cyc; a.fold_din = w.fold_din; a.status = status;
-    const size_t smem = apply_smem_bytes(g, drep);
+    const size_t smem = a.sl.total;
     switch (drep) {
     case 32: return launch_apply_smem<32>(a, sms, smem, st);
     case 16: return launch_apply_smem<16>(a, sms, smem, st);
