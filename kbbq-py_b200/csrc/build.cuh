@@ -5,22 +5,31 @@
 // four pos_* / dinuc_* np.add.at calls (:116-119).
 //
 // Roofline: HBM.  Algorithmic traffic 3 B/base (seq + qual + corrected), nothing written but the
-// tables.  In practice the kernel is bound by instruction issue and shared-memory atomics (two
-// per base), so the design minimises instructions per base and keeps every ATOMS conflict free:
+// tables.  What actually limits the kernel is the SM: two shared-memory reductions per base (LSU,
+// about 1.6 cycles per warp instruction) and the ALU pipe, on which a LOP3 costs 0.75 - 1 cycle per
+// warp against 0.5 for IADD3 / PRMT / SHF and 0.5 on the separate FMA pipe for IMAD / IDP.4A
+// (tools/microbench.cu, measured on B200).  The design therefore does all per-base address
+// arithmetic on the FMA pipe and keeps the ALU pipe for a handful of byte-parallel ops per word:
 //   * one thread owns one (row, 32-bit word) position of a group of G reads (common.cuh), i.e.
-//     four fixed cycles of one read, and walks down the groups; lanes of a warp own consecutive
-//     words, so at every byte position they hit consecutive banks of the cycle table whatever the
-//     qualities are;
-//   * the dinucleotide table (37 x 16 cells, every lane could hit the same cell) is replicated
-//     per lane ([cell][lane]), so bank == lane;
+//     four fixed cycles of one read; lanes of a warp own consecutive words, so at every byte
+//     position they hit consecutive banks of the cycle table whatever the qualities are;
+//   * table addresses come from dot products: IDP.4A of the byte-parallel row index with a
+//     one-hot byte constant extracts byte b AND scales it by the row stride in one FMA-pipe
+//     instruction -- no per-byte extract, select or multiply on the ALU pipe;
 //   * bases that must not be tallied (q < minscore, bytes of a neighbouring read, invalid dinuc)
-//     are steered to a TRASH row / slot by byte-parallel selects instead of per-byte predicates,
-//     so the eight reductions of a word are unconditional `red.shared.add.u32`;
+//     get row index 0 (a trash row) through byte masks made by sign-replicating PRMTs whose
+//     selectors are per-thread constants (they also encode which bytes of the word the thread owns
+//     and which one is cycle 0);
+//   * every counter packs total and errors: a base adds 1 + 65025 * mismatch with ONE reduction
+//     per table (65025 = 255 * 255, again one IDP.4A), so mismatches cost no branch and no
+//     second table; counters are decoded as (v % 65025, v / 65025) and folded before the total
+//     field could reach 65025;
+//   * the dinucleotide table (every lane could hit the same cell) is replicated per lane
+//     ([row][slot][lane]), so bank == lane;
 //   * reads reach the SM through a TMA bulk-copy ring filled by a producer warp (stage.cuh): HBM
 //     is read exactly once and the consumers' hot loop holds no global loads;
-//   * mismatches (about 1 % of bases) take a divergent slow path into unreplicated tables;
-//   * tables are per-CTA u32 in shared memory, flushed once per read-group segment to the global
-//     int64 tables with 64-bit reductions (zero cells skipped).
+//   * tables are per-CTA u32 in shared memory, flushed per read-group segment to the global int64
+//     tables with 64-bit reductions (zero cells skipped).
 #pragma once
 #include "common.cuh"
 #include "prepare.cuh"
@@ -28,11 +37,68 @@
 
 namespace kbbq {
 
-constexpr int DIN_SLOTS = 17;  // 16 dinucleotides + 1 trash slot
+constexpr uint32_t ERR_UNIT = 65025u;  // 255 * 255: what a mismatching base adds on top of the 1
+constexpr int DIN_SLOTS = 16;
+constexpr int DIN_REP = 32;            // dinuc table replicas = lanes of a warp
+constexpr int MAX_WARPS = MAX_THREADS / 32;
+
+// Shared-memory table geometry, chosen on the host (make_table_cfg).
+// Row index of a base: qrow = q - (minscore - 1) for minscore <= q <= 42, 0 (trash) otherwise.
+struct TableCfg {
+    int nrows;        // 44 - minscore (row 0 = trash)
+    int mp, kp;       // cycle table: byte-parallel qrow * mp, then * kp (both <= 255); row stride rs = mp * kp
+    int rs;           // bytes, multiple of 128
+    int sj;           // plane stride in words: cell of cycle c at word (c & 3) * sj + (c >> 2)
+    int revoff;       // bytes from the read-1 table to the read-2 table = nrows * rs
+    int md, k1, k2;   // dinuc table: qrow * md, then * (k1 + k2); row stride dq = md * (k1 + k2)
+    int dq;           // bytes, multiple of 128, >= 16 * 32 * 4
+    int pos_off, din_off, sums_off;  // byte offsets from the start of dynamic shared memory
+    int table_bytes;  // zeroed at the start of every segment
+    int flush_pos;    // iterations between flushes of the cycle table
+    int fold_din;     // iterations between folds of the dinuc replicas
+    uint32_t addq;    // 0x81 - minscore in every byte: (q + addq) has bit 7 set iff q >= minscore - 1
+    // one-hot byte constants, k << 8b: IDP.4A with one of them = (byte b of the other operand) * k.
+    // Kept in the kernel parameters so that the instruction reads them straight from the constant bank.
+    uint32_t ohp[4];  // kp: cycle-table row
+    uint32_t ohq[4];  // k1 (= k2): dinuc-table row, applied twice
+    uint32_t ohd[4];  // 64: the slot byte holds 2 * slot, a slot is 32 lanes x 4 B
+    uint32_t ohe[4];  // 255: mismatch byte 0xFF -> 65025
+};
+
+inline bool make_table_cfg(const Geom &g, TableCfg *t) {
+    if (g.minscore < 1) return false;  // row index * 6 must fit a byte
+    t->nrows = NQ + 1 - g.minscore;
+    t->sj = (g.L + 3) / 4;
+    const int need = 16 * t->sj;                       // bytes of one row: 4 planes x sj words
+    const int rs = (need + 127) / 128 * 128;
+    if (rs <= 896) { t->mp = 4; t->kp = rs / 4; t->rs = rs; }
+    else if (rs <= 1152) { t->mp = 6; t->kp = 192; t->rs = 1152; }
+    else return false;
+    t->revoff = t->nrows * t->rs;
+    t->md = 6; t->k1 = 192; t->k2 = 192; t->dq = 6 * 384;   // 2304 B >= 2048, multiple of 128
+    t->pos_off = 0;
+    t->din_off = 2 * t->revoff;
+    t->sums_off = t->din_off + t->nrows * t->dq;
+    t->table_bytes = t->sums_off + t->nrows * DIN_SLOTS * 2 * 8;
+    // a cycle cell is hit at most once per (thread-group, row) and iteration; a dinuc replica cell
+    // at most 4 times per thread of that lane id and iteration
+    t->flush_pos = (int)((ERR_UNIT - 1) / (uint32_t)(g.ng * g.G));
+    t->fold_din = (int)((ERR_UNIT - 1) / (uint32_t)(4 * (g.threads / 32)));
+    t->addq = (uint32_t)(0x81 - g.minscore) * ONE4;
+    for (int b = 0; b < 4; ++b) {
+        t->ohp[b] = (uint32_t)t->kp << (8 * b);
+        t->ohq[b] = (uint32_t)t->k1 << (8 * b);
+        t->ohd[b] = (uint32_t)(DIN_REP * 4 / 2) << (8 * b);
+        t->ohe[b] = 255u << (8 * b);
+    }
+    return true;
+}
 
 struct BuildArgs {
     const uint8_t *seq, *qual, *corr;
+    long long total_bytes;  // N * L
     Geom g;
+    TableCfg t;
     StageLayout sl;
     int R;
     const entry_t *entries;
@@ -41,12 +107,22 @@ struct BuildArgs {
     int *status;
 };
 
-__device__ __forceinline__ void red_shared_inc(uint32_t saddr) {
-    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(saddr));
+__device__ __forceinline__ void red_shared_add(uint32_t saddr, uint32_t v) {
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
 }
-
 __device__ __forceinline__ uint32_t smem_addr(const void *p) {
     return (uint32_t)__cvta_generic_to_shared(p);
+}
+// byte permute with the sign-replicate selector bit honoured (PTX prmt.b32, default mode)
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+// keep a loop-invariant value in its register instead of letting ptxas rematerialise it
+__device__ __forceinline__ uint32_t pin(uint32_t v) {
+    asm volatile("" : "+r"(v));
+    return v;
 }
 
 // Per-thread constants of the (row, word) mapping.
@@ -55,13 +131,13 @@ struct ThreadMap {
     int row;             // row of the group this thread works on (-1: padding lane)
     int toff;            // byte offset of this thread's word inside a group
     uint32_t rowmask;    // 0xFF for the bytes of the word that belong to the row
-    uint32_t notfirst;   // H4 bit for bytes whose cycle is not 0
-    uint32_t fwd[4];     // forward table position (bytes inside a quality row) of each byte's cycle
-    uint32_t rev[4];     // reverse (read-2) position
-    bool need_prev;      // byte 0 has a predecessor in the same row (word index > 0)
+    uint32_t selv;       // prmt selector: owned byte b -> sign of byte b of the first source, else byte 0 of the second
+    uint32_t seln;       // same, but cycle 0 (no previous base) also takes the second source
+    uint32_t cell[4];    // byte offset of each byte's cycle inside a row of the cycle table
+    int cyc[4];          // cycle of each byte (-1: not owned)
 };
 
-__device__ __forceinline__ ThreadMap make_thread_map(const Geom &g) {
+__device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, int sj) {
     ThreadMap m;
     const int tid = threadIdx.x;
     m.grp = tid / g.lps;
@@ -71,46 +147,79 @@ __device__ __forceinline__ ThreadMap make_thread_map(const Geom &g) {
 #pragma unroll
     for (int k = 0; k < MAX_G; ++k)
         if (k < g.G && t >= g.wstart[k] && t < g.wstart[k + 1]) { m.row = k; w = t - g.wstart[k]; }
-    m.rowmask = 0; m.notfirst = 0; m.toff = 0; m.need_prev = false;
+    m.rowmask = 0; m.toff = 0; m.selv = 0x4444u; m.seln = 0x4444u;
 #pragma unroll
-    for (int b = 0; b < 4; ++b) { m.fwd[b] = 0; m.rev[b] = 0; }
+    for (int b = 0; b < 4; ++b) { m.cell[b] = 0; m.cyc[b] = -1; }
     if (m.row >= 0) {
         const int a = (m.row * g.L) & 3;
         m.toff = m.row * g.L - a + 4 * w;
-        m.need_prev = w > 0;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
             const int c = 4 * w + b - a;
             if (c >= 0 && c < g.L) {
+                m.cyc[b] = c;
                 m.rowmask |= 0xFFu << (8 * b);
-                if (c != 0) m.notfirst |= 0x80u << (8 * b);
-                m.fwd[b] = 4u * plane_pos(c, g.sj);
-                m.rev[b] = 4u * plane_pos(2 * g.L - 1 - c, g.sj);
+                m.selv = (m.selv & ~(0xFu << (4 * b))) | ((8u | b) << (4 * b));
+                if (c != 0) m.seln = (m.seln & ~(0xFu << (4 * b))) | ((8u | b) << (4 * b));
+                m.cell[b] = 4u * ((c & 3) * sj + (c >> 2));
             }
         }
     }
     return m;
 }
 
-// keep a loop-invariant value in its register instead of letting ptxas rematerialise it
-__device__ __forceinline__ uint32_t pin(uint32_t v) {
-    asm volatile("" : "+r"(v));
-    return v;
+// Fold the per-lane dinuc replicas into the int64 sums (one warp per cell) and clear them.
+__device__ __forceinline__ void fold_din_replicas(const TableCfg &t, unsigned char *smem_raw, int nconsumers) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nconsumers >> 5;
+    unsigned long long *sums = reinterpret_cast<unsigned long long *>(smem_raw + t.sums_off);
+    for (int cell = warp; cell < t.nrows * DIN_SLOTS; cell += nwarps) {
+        const int r = cell / DIN_SLOTS, s = cell - r * DIN_SLOTS;
+        unsigned int *p = reinterpret_cast<unsigned int *>(smem_raw + t.din_off + r * t.dq + s * (DIN_REP * 4)) + lane;
+        const unsigned int v = *p;
+        if (__any_sync(0xFFFFFFFFu, v != 0)) {
+            *p = 0;
+            unsigned int tot = v % ERR_UNIT, er = v / ERR_UNIT;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
+                er += __shfl_xor_sync(0xFFFFFFFFu, er, o);
+            }
+            if (lane == 0) { sums[2 * cell] += tot; sums[2 * cell + 1] += er; }
+        }
+    }
 }
 
-template <int DREP, bool VALIDATE>
-__global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    unsigned int *smem = reinterpret_cast<unsigned int *>(smem_raw);
+// Flush the cycle table of this CTA into the global int64 tables of read group rg and clear it.
+__device__ __forceinline__ void flush_pos_table(const BuildArgs &a, unsigned char *smem_raw, int rg, int nconsumers) {
     const Geom &g = a.g;
+    const TableCfg &t = a.t;
+    const int L = g.L, L2 = 2 * g.L;
+    unsigned long long *gpe = a.pos_errs + (size_t)rg * NQ * L2, *gpt = a.pos_total + (size_t)rg * NQ * L2;
+    const int per_half = (t.nrows - 1) * L;
+    for (int i = threadIdx.x; i < 2 * per_half; i += nconsumers) {
+        const int half = i >= per_half, j = i - half * per_half;
+        const int r = j / L + 1, c = j - (r - 1) * L;
+        unsigned int *p = reinterpret_cast<unsigned int *>(smem_raw + t.pos_off + half * t.revoff + r * t.rs) +
+                          ((c & 3) * t.sj + (c >> 2));
+        const unsigned int v = *p;
+        if (v) {
+            *p = 0;
+            const unsigned int tot = v % ERR_UNIT, er = v / ERR_UNIT;
+            // row r holds quality r + minscore - 1; read-2 cycles count from the end of the axis
+            const size_t o = (size_t)(r + g.minscore - 1) * L2 + (half ? L2 - 1 - c : c);
+            atomicAdd(gpt + o, (unsigned long long)tot);
+            if (er) atomicAdd(gpe + o, (unsigned long long)er);
+        }
+    }
+}
+
+template <bool VALIDATE>
+__global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid_constant__ BuildArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const Geom &g = a.g;
+    const TableCfg &t = a.t;
     const StageLayout &sl = a.sl;
-    const int nqv = g.nqv, row = g.row;
-    unsigned int *pos_t = smem;                              // [nqv + 1][row]           (+ trash row)
-    unsigned int *din_t = pos_t + (nqv + 1) * row;           // [nqv + 1][17][DREP]      (+ trash row / slot)
-    unsigned int *pos_e = din_t + (nqv + 1) * DIN_SLOTS * DREP;  // [nqv][row]
-    unsigned int *din_e = pos_e + nqv * row;                 // [nqv][16]
-    const int table_words = (nqv + 1) * row + (nqv + 1) * DIN_SLOTS * DREP + nqv * row + nqv * 16;
-    const int nconsumers = g.threads;                        // + one producer warp
+    const int nconsumers = g.threads;  // + one producer warp
 
     // this CTA's slice of the concatenated work list
     const unsigned long long E = a.seg[a.R];
@@ -130,28 +239,25 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a)
         ProducerArgs p;
         p.arr[0] = a.seq; p.arr[1] = a.qual; p.arr[2] = a.corr;
         p.entries = a.entries; p.seg = a.seg; p.R = a.R; p.lo = lo; p.hi = hi;
-        p.gbytes = g.gbytes; p.ng = g.ng;
+        p.gbytes = g.gbytes; p.ng = g.ng; p.total_bytes = a.total_bytes;
         producer_loop(p, sl, smem_raw);
         return;
     }
 
     // ---- consumer warps ----
-    const ThreadMap m = make_thread_map(g);
+    const ThreadMap m = make_thread_map(g, t.sj);
     const int lane = threadIdx.x & 31;
-    const uint32_t minq4 = (uint32_t)g.minscore * ONE4;
-    const uint32_t trash4 = (uint32_t)NQ * ONE4;  // quality 43 -> row nqv of the shared tables
-    // byte addresses in the shared window, with the "- minscore rows" folded in
-    const uint32_t pos_base = smem_addr(pos_t) - (uint32_t)g.minscore * row * 4;
-    const uint32_t din_base = pin(smem_addr(din_t) + (lane & (DREP - 1)) * 4 - (uint32_t)g.minscore * DIN_SLOTS * DREP * 4);
-    const uint32_t row_bytes = row * 4, dq_bytes = DIN_SLOTS * DREP * 4;
-    const uint32_t rowbit = m.row >= 0 ? (1u << m.row) : 0u, secbit = rowbit << 8;
-    uint32_t afwd[4], arev[4];  // absolute shared addresses of quality row 0 at this thread's cycles
+    const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
+    const uint32_t din_base = pin(smem_addr(smem_raw + t.din_off) + lane * 4);
+    uint32_t afwd[4];  // shared address of row 0 of the read-1 cycle table at this thread's cycles
 #pragma unroll
-    for (int b = 0; b < 4; ++b) { afwd[b] = pin(pos_base + m.fwd[b]); arev[b] = pin(pos_base + m.rev[b]); }
+    for (int b = 0; b < 4; ++b) afwd[b] = pin(pos_base + m.cell[b]);
+    const uint32_t selv = pin(m.selv), seln = pin(m.seln);
+    const uint32_t rowsel = m.row >= 0 ? (uint32_t)m.row : 0u;  // prmt selector: flag byte of this thread's row
     const uint32_t data0 = smem_u32(smem_raw + sl.data_off) + m.toff;
     const uint32_t hdr0 = smem_u32(smem_raw + sl.hdr_off) + m.grp * 16;
     const uint32_t stage_bytes = sl.narr * sl.abytes, abytes = sl.abytes, hdr_stride = g.ng * 16;
-    const uint32_t prev_keep = m.need_prev ? 0u : 7u;  // no predecessor in this row -> treat as N
+    const uint32_t mp = t.mp, md = t.md, revoff = t.revoff, addq = t.addq;
     uint32_t stage = 0, phase = 0;
     uint32_t qbad = 0, bbad = 0;
 
@@ -162,103 +268,107 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(BuildArgs a)
         if (s_lo < lo) s_lo = lo;
         if (s_hi > hi) s_hi = hi;
 
-        for (int i = threadIdx.x; i < table_words; i += nconsumers) smem[i] = 0;
+        for (int i = threadIdx.x; i < t.table_bytes / 4; i += nconsumers) reinterpret_cast<unsigned int *>(smem_raw)[i] = 0;
         consumer_sync(nconsumers);
+        int since_pos = 0;  // iterations since the cycle table was last flushed
 
-        for (uint32_t first = s_lo; first < s_hi; first += g.ng) {
-            mbar_wait(bar0 + stage * 8, phase);
-            uint32_t bits, soff;
-            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bits), "=r"(soff) : "r"(hdr0 + stage * hdr_stride));
-            uint32_t sw = 0, qw = 0, cw = 0, pb = 0;
-            const bool mine = (bits & rowbit) != 0;
-            if (mine) {
-                const uint32_t wa = data0 + stage * stage_bytes + soff;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sw) : "r"(wa));
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qw) : "r"(wa + abytes));
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(wa + 2 * abytes));
-                asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pb) : "r"(wa - 1));
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar0 + (sl.stages + stage) * 8);  // the stage may be refilled
-            if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
-            if (!mine) continue;  // padding lane, or the row belongs to another read group
-            const uint32_t am = m.rowmask;
+        // The hot loop runs in chunks of fold_din iterations; between chunks the counters whose
+        // total field could otherwise reach ERR_UNIT are folded.
+        for (uint32_t first = s_lo; first < s_hi;) {
+            const uint32_t chunk_end = (uint32_t)min((unsigned long long)s_hi,
+                                                     (unsigned long long)first + (unsigned long long)t.fold_din * g.ng);
+            since_pos += t.fold_din;
+            for (; first < chunk_end; first += g.ng) {
+                const uint32_t nlive = min((uint32_t)g.ng, s_hi - first);  // thread-groups with a record
+                mbar_wait(bar0 + stage * 8, phase);
+                uint32_t soff, hgrp, flo, fhi;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
+                             : "r"(hdr0 + stage * hdr_stride));
+                // flag byte of this thread's row: 0 = not in this segment, 1 = read 1, 3 = read 2
+                const uint32_t flag = (m.row >= 0 && (uint32_t)m.grp < nlive) ? (prmt(flo, fhi, rowsel) & 0xFFu) : 0u;
+                uint32_t sw = 0, qw = 0, cw = 0, pb = 0;
+                if (flag) {
+                    const uint32_t wa = data0 + stage * stage_bytes + soff;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sw) : "r"(wa));
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qw) : "r"(wa + abytes));
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(wa + 2 * abytes));
+                    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pb) : "r"(wa - 1));
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar0 + (sl.stages + stage) * 8);  // the stage may be refilled
+                if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
+                if (!flag) continue;  // padding lane, or the row belongs to another read group
 
-            // 3-bit base code (b >> 1) & 7: A=0 C=1 T=2 G=3 N=7, injective on ACGTN
-            const uint32_t code3 = (sw >> 1) & 0x07070707u;
-            const uint32_t pv3 = ((pb >> 1) & 7u) | prev_keep;
-            const uint32_t pc3 = __byte_perm(pv3, code3, 0x6540);  // previous base of every byte
+                // ---- quality -> row index, byte-parallel ----
+                const uint32_t u = qw + 0x55555555u;        // bit 7 <=> q >= 43 (for q < 128)
+                const uint32_t w5 = qw + addq;              // bit 7 <=> q >= minscore - 1, low bits q - (minscore - 1)
+                qbad |= u | qw;
+                const uint32_t vraw = w5 & ~u & ~qw;        // bit 7 <=> minscore - 1 <= q <= 42
+                const uint32_t vm8 = prmt(vraw, 0u, selv);  // 0xFF for owned bytes in range
+                const uint32_t qrow4 = w5 & vm8 & 0x3F3F3F3Fu;  // 0 = trash row
+                const uint32_t q4p = qrow4 * mp;
 
-            const uint32_t bad = ((qw + 0x55555555u) | qw) & H4 & am;             // q > 42
-            qbad |= bad;
-            const uint32_t vm = ((qw | H4) - minq4) & H4 & am & ~bad;             // minscore <= q <= 42
-            const uint32_t anyn = ((code3 | pc3) << 5) & H4;                      // cur or prev is N
-            const uint32_t dm = vm & ~anyn & m.notfirst;                          // dinuc valid
-            const uint32_t vm8 = (vm >> 7) * 0xFFu, dm8 = (dm >> 7) * 0xFFu;
-            const uint32_t q4 = (qw & vm8) | (trash4 & ~vm8);                     // untallied bytes -> trash row
-            const uint32_t din4 = ((pc3 << 2) & 0x0C0C0C0Cu) | (code3 & 0x03030303u);
-            const uint32_t d4 = (din4 & dm8) | (0x10101010u & ~dm8);              // invalid dinuc -> trash slot
-            if (VALIDATE) {
-                // rebuild each byte from its code with an 8-entry byte LUT; any difference = bad base
-                const uint32_t y = code3 | (code3 >> 4);
-                const uint32_t sel = __byte_perm(y, 0, 0x4420);
-                const uint32_t recon = __byte_perm(0x47544341u /* A C T G */, 0x4E000000u /* . . . N */, sel);
-                bbad |= (recon ^ sw) & am;
-            }
-            // read-2 rows count cycles from the end of the axis
-            const bool sec = (bits & secbit) != 0;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const uint32_t qb = __byte_perm(q4, 0, 0x4440 + b);
-                const uint32_t db = __byte_perm(d4, 0, 0x4440 + b);
-                red_shared_inc(qb * row_bytes + (sec ? arev[b] : afwd[b]));
-                red_shared_inc(qb * dq_bytes + (db * (DREP * 4) + din_base));
-            }
-            // mismatches: rare, divergent
-            const uint32_t x = sw ^ cw;
-            const uint32_t xm = (((x | H4) - ONE4) | x) & vm;  // byte differs and is tallied
-            if (xm) {
+                // ---- dinucleotide slot, byte-parallel: 2 * (4 * code(prev) + code(cur)), code = (b >> 1) & 3 ----
+                const uint32_t pw = prmt(pb, sw, 0x6540u);  // previous base of every byte
+                const uint32_t d4 = (pw & 0x06060606u) * 4u + (sw & 0x06060606u);
+                // 'N' is the only accepted base with bit 3 set; cycle 0 and foreign bytes take 0xFF from the selector
+                const uint32_t nm8 = prmt((sw | pw) * 16u, 0xFFFFFFFFu, seln);
+                const uint32_t q4d = (qrow4 & ~nm8) * md;
+
+                // ---- mismatch: 0xFF where the corrected base differs (bases are 7-bit) ----
+                const uint32_t e8 = prmt((sw ^ cw) + 0x7F7F7F7Fu, 0u, 0xBA98u);
+
+                if (VALIDATE) {
+                    // rebuild each byte from its 3-bit code with an 8-entry byte LUT; any difference = bad base
+                    const uint32_t code3 = (sw >> 1) & 0x07070707u;
+                    const uint32_t y = code3 | (code3 >> 4);
+                    const uint32_t sel = __byte_perm(y, 0, 0x4420);
+                    const uint32_t recon = __byte_perm(0x47544341u /* A C T G */, 0x4E000000u /* . . . N */, sel);
+                    bbad |= (recon ^ sw) & m.rowmask;
+                }
+
+                const uint32_t rev = (flag >> 1) * revoff;  // read-2 rows tally into the second cycle table
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    if (xm & (0x80u << (8 * b))) {
-                        const uint32_t qb = (qw >> (8 * b)) & 0xFFu;
-                        const uint32_t pos = (sec ? m.rev[b] : m.fwd[b]) >> 2;
-                        atomicAdd(&pos_e[(qb - g.minscore) * row + pos], 1u);
-                        if (dm & (0x80u << (8 * b)))
-                            atomicAdd(&din_e[(qb - g.minscore) * 16 + ((din4 >> (8 * b)) & 0xFu)], 1u);
-                    }
+                    const uint32_t inc = __dp4a(e8, t.ohe[b], 1u);
+                    const uint32_t pa = __dp4a(q4p, t.ohp[b], afwd[b] + rev);
+                    uint32_t da = __dp4a(d4, t.ohd[b], din_base);
+                    da = __dp4a(q4d, t.ohq[b], da);
+                    da = __dp4a(q4d, t.ohq[b], da);
+                    red_shared_add(pa, inc);
+                    red_shared_add(da, inc);
                 }
+            }
+            if (first < s_hi) {
+                consumer_sync(nconsumers);
+                if (since_pos + t.fold_din > t.flush_pos) {
+                    flush_pos_table(a, smem_raw, rg, nconsumers);
+                    since_pos = 0;
+                }
+                fold_din_replicas(t, smem_raw, nconsumers);
+                consumer_sync(nconsumers);
             }
         }
         consumer_sync(nconsumers);
 
         // flush this read group's partial tables: u32 shared -> int64 global
-        const int L2 = 2 * g.L;
-        unsigned long long *gpe = a.pos_errs + (size_t)rg * NQ * L2, *gpt = a.pos_total + (size_t)rg * NQ * L2;
-        for (int i = threadIdx.x; i < nqv * L2; i += nconsumers) {
-            const int q = i / L2, c2 = i - q * L2;
-            const int s = q * row + plane_pos(c2, g.sj);
-            const unsigned int t = pos_t[s], er = pos_e[s];
-            const size_t o = (size_t)(q + g.minscore) * L2 + c2;
-            if (t) atomicAdd(gpt + o, (unsigned long long)t);
-            if (er) atomicAdd(gpe + o, (unsigned long long)er);
-        }
+        flush_pos_table(a, smem_raw, rg, nconsumers);
+        fold_din_replicas(t, smem_raw, nconsumers);
+        consumer_sync(nconsumers);
+        const unsigned long long *sums = reinterpret_cast<const unsigned long long *>(smem_raw + t.sums_off);
         unsigned long long *gde = a.din_errs + (size_t)rg * NQ * 16, *gdt = a.din_total + (size_t)rg * NQ * 16;
-        for (int i = threadIdx.x; i < nqv * 16; i += nconsumers) {
-            const int q = i >> 4, dn = i & 15;
-            unsigned int t = 0;
-#pragma unroll 8
-            for (int k = 0; k < DREP; ++k)
-                t += din_t[(q * DIN_SLOTS + dn) * DREP + ((k + threadIdx.x) & (DREP - 1))];
-            const unsigned int er = din_e[i];
+        for (int i = threadIdx.x; i < (t.nrows - 1) * DIN_SLOTS; i += nconsumers) {
+            const int r = i / DIN_SLOTS + 1, dn = i & (DIN_SLOTS - 1);
+            const unsigned long long tot = sums[2 * (r * DIN_SLOTS + dn)], er = sums[2 * (r * DIN_SLOTS + dn) + 1];
             const int dref = nat_to_ref(dn >> 2) * 4 + nat_to_ref(dn & 3);
-            const size_t o = (size_t)(q + g.minscore) * 16 + dref;
-            if (t) atomicAdd(gdt + o, (unsigned long long)t);
-            if (er) atomicAdd(gde + o, (unsigned long long)er);
+            const size_t o = (size_t)(r + g.minscore - 1) * 16 + dref;
+            if (tot) atomicAdd(gdt + o, tot);
+            if (er) atomicAdd(gde + o, er);
         }
         consumer_sync(nconsumers);
     }
-    if (qbad) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
+    if (qbad & m.rowmask & H4) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
     if (VALIDATE && bbad) atomicOr(a.status, KBBQ_FLAG_BAD_BASE);
 }
 
@@ -306,11 +416,6 @@ __global__ void build_generic_kernel(BuildGenericArgs a) {
             }
         }
     }
-}
-
-inline size_t build_smem_bytes(const Geom &g, int drep) {
-    return sizeof(unsigned int) * ((size_t)(g.nqv + 1) * g.row + (size_t)(g.nqv + 1) * DIN_SLOTS * drep +
-                                   (size_t)g.nqv * g.row + (size_t)g.nqv * 16);
 }
 
 }  // namespace kbbq

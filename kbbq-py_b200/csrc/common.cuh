@@ -116,11 +116,14 @@ inline bool make_geom(int L, int minscore, Geom *g) {
 // position of cycle-axis index c2 (0 .. 2L-1) inside a shared-memory quality row
 __host__ __device__ inline int plane_pos(int c2, int sj) { return (c2 & 3) * sj + (c2 >> 2); }
 
-// Work-list entry: one group of G reads seen from one read group.
-//   bits  0..31  group index
-//   bits 32..39  rows of the group that belong to this read group (and exist)
-//   bits 40..47  `second` flag of each row
-typedef unsigned long long entry_t;
+// Work-list record: one group of G reads seen from one read group, ready to be dropped into a
+// stage header by the copy engine (stage.cuh):
+//   x  byte offset of the group inside the stage's data area (the prepare pass knows where every
+//      record lands: which CTA, which iteration, which slot)
+//   y  group index
+//   z  flag bytes of rows 0-3, w of rows 4-7: 0 = row not tallied in this segment (other read
+//      group / past the end), 1 = read 1, 3 = read 2 of a pair
+typedef uint4 entry_t;
 
 // natural 2-bit code (b >> 1) & 3: A=0 C=1 T=2 G=3  ->  reference order A=0 T=1 G=2 C=3
 // (Dinucleotide.nucleotides, kbbq/compare_reads.py:199)

@@ -55,33 +55,27 @@ static int current_device_info(int *device, int *sms, int *max_smem) {
 
 static bool misaligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) != 0; }
 
-// Largest dinuc replication (bank-conflict freedom) and ring depth that fit the CTA's shared memory:
-// at least 2 stages, then replication, then up to MAX_STAGES.
-static bool pick_smem_config(const Geom &g, int narr, int max_smem, size_t (*table_bytes)(const Geom &, int),
-                             int *drep, int *stages) {
-    for (int d = 32; d >= 1; d >>= 1) {
-        for (int s = MAX_STAGES; s >= 2; --s) {
-            if (make_stage_layout(g, narr, s, table_bytes(g, d)).total <= max_smem) {
-                *drep = d; *stages = s;
-                return true;
-            }
+// Deepest staging ring (at least 2 stages) that fits the CTA's shared memory behind the tables.
+static bool pick_stages(const Geom &g, int narr, int max_smem, size_t table_bytes, int *stages) {
+    for (int s = MAX_STAGES; s >= 2; --s) {
+        if (make_stage_layout(g, narr, s, table_bytes).total <= max_smem) {
+            *stages = s;
+            return true;
         }
     }
     return false;
 }
 
-template <int DREP>
 static int launch_build_smem(const BuildArgs &a, int grid, size_t smem, cudaStream_t st) {
-    auto kern = build_smem_kernel<DREP, true>;
+    auto kern = build_smem_kernel<true>;
     KBBQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, a.g.threads + 32, smem, st>>>(a);  // + the producer warp
     KBBQ_LAUNCHED();
     return KBBQ_OK;
 }
 
-template <int DREP>
 static int launch_apply_smem(const ApplyArgs &a, int grid, size_t smem, cudaStream_t st) {
-    auto kern = apply_smem_kernel<DREP>;
+    auto kern = apply_smem_kernel;
     KBBQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, a.g.threads + 32, smem, st>>>(a);  // + the producer warp
     KBBQ_LAUNCHED();
@@ -136,8 +130,9 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
     bool smem_ok = path != 2 && make_geom(L, minscore, &g) && g.row < 65536 &&
                    (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull &&
                    !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(corr, 16);
-    int drep = 32, stages = 0;
-    if (smem_ok) smem_ok = pick_smem_config(g, 3, max_smem, build_smem_bytes, &drep, &stages);
+    TableCfg tc;
+    int stages = 0;
+    smem_ok = smem_ok && make_table_cfg(g, &tc) && pick_stages(g, 3, max_smem, tc.table_bytes, &stages);
     if (!smem_ok) {
         if (path == 1) return KBBQ_E_ARG;
         BuildGenericArgs a = {seq, qual, corr, rg, second, N, L, R, minscore,
@@ -149,25 +144,18 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
     }
     Workspace w = carve_workspace(workspace, N, L, R);
     if (!workspace || workspace_bytes < w.bytes) return KBBQ_E_WORKSPACE;
-    rc = run_prepare(rg, second, N, g.G, R, w, status, st);
+    const StageLayout sl = make_stage_layout(g, 3, stages, tc.table_bytes);
+    rc = run_prepare(rg, second, N, g.G, R, w, status, sms, g.ng, g.gbytes, sl.slot, st);
     if (rc) return rc;
 
     BuildArgs a;
-    a.seq = seq; a.qual = qual; a.corr = corr; a.g = g; a.R = R;
-    a.sl = make_stage_layout(g, 3, stages, build_smem_bytes(g, drep));
+    a.seq = seq; a.qual = qual; a.corr = corr; a.total_bytes = N * L; a.g = g; a.t = tc; a.R = R;
+    a.sl = sl;
     a.entries = w.entries; a.seg = w.seg;
     a.pos_errs = (unsigned long long *)pos_errs; a.pos_total = (unsigned long long *)pos_total;
     a.din_errs = (unsigned long long *)din_errs; a.din_total = (unsigned long long *)din_total;
     a.status = status;
-    const size_t smem = a.sl.total;
-    switch (drep) {
-    case 32: return launch_build_smem<32>(a, sms, smem, st);
-    case 16: return launch_build_smem<16>(a, sms, smem, st);
-    case 8: return launch_build_smem<8>(a, sms, smem, st);
-    case 4: return launch_build_smem<4>(a, sms, smem, st);
-    case 2: return launch_build_smem<2>(a, sms, smem, st);
-    default: return launch_build_smem<1>(a, sms, smem, st);
-    }
+    return launch_build_smem(a, sms, a.sl.total, st);
 }
 
 int kbbq_marginals(const int64_t *pos_errs, const int64_t *pos_total, int L, int R, int64_t *q_errs,
@@ -244,7 +232,7 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
     Workspace w = carve_workspace(workspace, N, L, R);
     if (!workspace || workspace_bytes < w.bytes) return KBBQ_E_WORKSPACE;
 
-    const long long fold_cells = (long long)R * NQ * (2 * L + 32);
+    const long long fold_cells = (long long)R * NQ * (2 * L + 16);
     fold_kernel<<<(unsigned)((fold_cells + 255) / 256), 256, 0, st>>>(
         (const long long *)meanq, (const long long *)rgdq, (const long long *)qdq, (const long long *)posdq,
         (const long long *)dindq, R, nq, 2 * L, ndin1, w.fold_cyc, w.fold_din);
@@ -254,8 +242,9 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
     bool smem_ok = path != 2 && make_geom(L, minscore, &g) && g.row < 65536 &&
                    (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull &&
                    !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(out_qual, 4);
-    int drep = 32, stages = 0;
-    if (smem_ok) smem_ok = pick_smem_config(g, 2, max_smem, apply_smem_bytes, &drep, &stages);
+    TableCfg tc;
+    int stages = 0;
+    smem_ok = smem_ok && make_table_cfg(g, &tc) && pick_stages(g, 2, max_smem, apply_table_bytes(tc), &stages);
     if (!smem_ok) {
         if (path == 1) return KBBQ_E_ARG;
         ApplyGenericArgs a = {seq, qual, rg, second, out_qual, N, L, R, minscore, nq, w.fold_cyc, w.fold_din, status};
@@ -263,21 +252,14 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
         KBBQ_LAUNCHED();
         return KBBQ_OK;
     }
-    rc = run_prepare(rg, second, N, g.G, R, w, status, st);
+    const StageLayout sl = make_stage_layout(g, 2, stages, apply_table_bytes(tc));
+    rc = run_prepare(rg, second, N, g.G, R, w, status, sms, g.ng, g.gbytes, sl.slot, st);
     if (rc) return rc;
     ApplyArgs a;
-    a.seq = seq; a.qual = qual; a.out = out_qual; a.g = g; a.R = R; a.nq = nq;
-    a.sl = make_stage_layout(g, 2, stages, apply_smem_bytes(g, drep));
+    a.seq = seq; a.qual = qual; a.out = out_qual; a.total_bytes = N * L; a.g = g; a.t = tc; a.R = R; a.nq = nq;
+    a.sl = sl;
     a.entries = w.entries; a.seg = w.seg; a.fold_cyc = w.fold_cyc; a.fold_din = w.fold_din; a.status = status;
-    const size_t smem = a.sl.total;
-    switch (drep) {
-    case 32: return launch_apply_smem<32>(a, sms, smem, st);
-    case 16: return launch_apply_smem<16>(a, sms, smem, st);
-    case 8: return launch_apply_smem<8>(a, sms, smem, st);
-    case 4: return launch_apply_smem<4>(a, sms, smem, st);
-    case 2: return launch_apply_smem<2>(a, sms, smem, st);
-    default: return launch_apply_smem<1>(a, sms, smem, st);
-    }
+    return launch_apply_smem(a, sms, a.sl.total, st);
 }
 
 int kbbq_synth_reads(uint64_t seed, int64_t first_read, int64_t n, int L, int R, uint8_t *seq, uint8_t *qual,

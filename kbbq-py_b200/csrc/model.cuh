@@ -170,30 +170,33 @@ __global__ void delta_level3_kernel(DeltaArgs a) {
 }
 
 // ---- fold: reference-shaped int64 delta tables -> the two small tables the apply kernel gathers --
-// fold_cyc[rg][q][c2] = meanq + rgdq + qdq + posdq      (q < nq, else 0)
-// fold_din[rg][q][n]  = dindq[rg][q][ref(n)] for natural-order dinuc n < 16, dindq[..][ndin1-1]
-//                       (the slot index -1 gathers) for n = 16..31
+// With pad = dindq[rg][q][ndin1-1] (the column the dinuc index -1 gathers, kbbq/gatk/applybqsr.py:98-101):
+// fold_cyc[rg][q][c2] = meanq + rgdq + qdq + posdq + pad      (q < nq, else 0)
+// fold_din[rg][q][n]  = dindq[rg][q][ref(n)] - pad            for natural-order dinuc n < 16
+// so an invalid dinucleotide contributes nothing on top of fold_cyc.
 __global__ void fold_kernel(const long long *meanq, const long long *rgdq, const long long *qdq,
                             const long long *posdq, const long long *dindq, int R, int nq, int L2,
                             int ndin1, short *fold_cyc, short *fold_din) {
-    const long long ncyc = (long long)R * NQ * L2, ndin = (long long)R * NQ * 32;
+    const long long ncyc = (long long)R * NQ * L2, ndin = (long long)R * NQ * 16;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < ncyc) {
         const long long gq = i / L2;
         const int c2 = (int)(i - gq * L2);
         const int rg = (int)(gq / NQ), q = (int)(gq - (long long)rg * NQ);
         long long v = 0;
-        if (q < nq) v = meanq[rg] + rgdq[rg] + qdq[rg * nq + q] + posdq[((size_t)rg * nq + q) * L2 + c2];
+        if (q < nq)
+            v = meanq[rg] + rgdq[rg] + qdq[rg * nq + q] + posdq[((size_t)rg * nq + q) * L2 + c2] +
+                dindq[((size_t)rg * nq + q) * ndin1 + ndin1 - 1];
         fold_cyc[i] = (short)v;
     } else if (i < ncyc + ndin) {
         i -= ncyc;
-        const long long gq = i >> 5;
-        const int n = (int)(i & 31);
+        const long long gq = i >> 4;
+        const int n = (int)(i & 15);
         const int rg = (int)(gq / NQ), q = (int)(gq - (long long)rg * NQ);
         long long v = 0;
         if (q < nq) {
-            const int col = n < 16 ? nat_to_ref(n >> 2) * 4 + nat_to_ref(n & 3) : ndin1 - 1;
-            v = dindq[((size_t)rg * nq + q) * ndin1 + col];
+            const size_t row = ((size_t)rg * nq + q) * ndin1;
+            v = dindq[row + nat_to_ref(n >> 2) * 4 + nat_to_ref(n & 3)] - dindq[row + ndin1 - 1];
         }
         fold_din[i] = (short)v;
     }

@@ -3,10 +3,10 @@
 // The shared-memory tables of one CTA hold ONE read group (a cycle table for 32 read groups of
 // 250 bp reads would need 2.4 MB).  Reads of all read groups are interleaved in the batch, so a tiny
 // pre-pass buckets GROUP indices (not data) by read group: entries[seg[g] .. seg[g+1]) lists the
-// groups of G reads (common.cuh) that contain at least one read of read group g, with the bitmask
-// of those rows and their `second` flags.  The main kernels walk contiguous slices of that list;
-// the read data itself is never moved.  Cost: 3 B/read in, 8 B/group out and back in (< 1 % of the
-// 3 B/base the build reads).
+// groups of G reads (common.cuh) that contain at least one read of read group g, with one flag byte
+// per row (is it of this read group, is it read 2) and the place the group will take in the
+// staging ring.  The main kernels walk contiguous slices of that list; the read data itself is
+// never moved.  Cost: 3 B/read in, 16 B/group out and back in (< 1 % of the 3 B/base the build reads).
 #pragma once
 #include "common.cuh"
 
@@ -24,12 +24,33 @@ struct PrepArgs {
     int R;
     unsigned int *seg;      // [R + 1] segment offsets (out)
     unsigned int *cursor;   // [R] scratch
-    entry_t *entries;       // [ngroups * G] (out)
+    entry_t *entries;       // (out)
     int *status;
+    // staging geometry of the kernel that will walk the list (stage.cuh)
+    int grid;               // its number of CTAs
+    int ng;                 // groups per stage
+    unsigned int gbytes;    // bytes per group
+    unsigned int slot;      // bytes reserved per group when a stage is not one contiguous span
 };
 
-__device__ __forceinline__ entry_t make_entry(long long grp, unsigned int match, unsigned int sec) {
-    return (entry_t)(unsigned int)grp | ((entry_t)match << 32) | ((entry_t)sec << 40);
+// flag bytes from the rows of the group that are tallied (`match`) and their `second` bits
+__device__ __forceinline__ entry_t make_entry(unsigned int soff, long long grp, unsigned int match, unsigned int sec) {
+    unsigned int f[2] = {0u, 0u};
+#pragma unroll
+    for (int k = 0; k < MAX_G; ++k) {
+        const unsigned int live = (match >> k) & 1u, s2 = (sec >> k) & 1u;
+        f[k >> 2] |= (live | ((live & s2) << 1)) << (8 * (k & 3));
+    }
+    return make_uint4(soff, (unsigned int)grp, f[0], f[1]);
+}
+
+// First list position of the slice CTA b walks (the kernels use the same expression).
+__device__ __forceinline__ unsigned long long slice_lo(unsigned long long E, unsigned long long b, int grid) {
+    return E * b / (unsigned long long)grid;
+}
+// The CTA whose slice holds list position i: lo(b) <= i < lo(b + 1).
+__device__ __forceinline__ unsigned long long slice_of(unsigned long long E, unsigned long long i, int grid) {
+    return ((i + 1) * (unsigned long long)grid + E - 1) / E - 1;
 }
 
 // rows of group `grp`: rg value (0xFFFFFFFF if the row does not exist) and second bits
@@ -71,7 +92,13 @@ __global__ void prep_identity_kernel(PrepArgs a) {
             }
         exist = ok;
     }
-    a.entries[grp] = make_entry(grp, exist, sec);
+    // the list is the identity, so a stage is one contiguous span: ng consecutive groups from the
+    // start of the CTA's slice, the first one 16-byte aligned down
+    const unsigned long long E = (unsigned long long)a.ngroups;
+    const unsigned long long lo = slice_lo(E, slice_of(E, (unsigned long long)grp, a.grid), a.grid);
+    const unsigned int j = (unsigned int)(((unsigned long long)grp - lo) % (unsigned int)a.ng);
+    const unsigned int mis0 = (unsigned int)((((unsigned long long)grp - j) * a.gbytes) & 15ull);
+    a.entries[grp] = make_entry(mis0 + j * a.gbytes, grp, exist, sec);
 }
 
 // mode 0: count list entries per read group into a.cursor; mode 1: scatter entries.
@@ -122,11 +149,18 @@ __global__ void __launch_bounds__(PREP_THREADS) prep_bucket_kernel(PrepArgs a) {
         __syncthreads();
     }
     if (MODE == 1) {
+        const unsigned long long E = a.seg[a.R];
 #pragma unroll
         for (int k = 0; k < MAX_G; ++k) {
             if (!mask[k]) continue;
             const unsigned int pos = slot[k] + (use_smem ? s_cnt[rgv[k]] : 0u);
-            a.entries[pos] = make_entry(grp, mask[k], sec);
+            // iterations restart at the start of every (CTA slice, segment) intersection; every
+            // group has its own slot in the stage
+            const unsigned long long lo = slice_lo(E, slice_of(E, pos, a.grid), a.grid);
+            const unsigned long long start = max((unsigned long long)a.seg[rgv[k]], lo);
+            const unsigned int j = (unsigned int)((pos - start) % (unsigned int)a.ng);
+            const unsigned int mis = (unsigned int)(((unsigned long long)grp * a.gbytes) & 15ull);
+            a.entries[pos] = make_entry(j * a.slot + mis, grp, mask[k], sec);
         }
     }
 }
@@ -166,7 +200,7 @@ struct Workspace {
     unsigned int *cursor;
     entry_t *entries;
     short *fold_cyc;   // [R][43][2L]   apply only
-    short *fold_din;   // [R][43][32]   apply only (natural dinuc order, 16..31 = pad value)
+    short *fold_din;   // [R][43][16]   apply only (natural dinuc order, relative to the pad column)
     size_t bytes;
 };
 
@@ -176,24 +210,27 @@ inline Workspace carve_workspace(void *base, long long N, int L, int R) {
     Workspace w = {};
     size_t off = 0;
     char *p = (char *)base;
-    // a group never lists more entries than it has rows, so N (+ padding) entries always suffice
+    // a group never lists more entries than it has rows, so N (+ padding) entries always suffice;
+    // with one read group the list is one entry per group of at least 1 read
     const size_t max_entries = (size_t)N + MAX_G;
     w.seg = (unsigned int *)(p + off);      off = align_up(off + sizeof(unsigned int) * ((size_t)R + 1), 256);
     w.cursor = (unsigned int *)(p + off);   off = align_up(off + sizeof(unsigned int) * (size_t)R, 256);
     w.entries = (entry_t *)(p + off);       off = align_up(off + sizeof(entry_t) * max_entries, 256);
     w.fold_cyc = (short *)(p + off);        off = align_up(off + sizeof(short) * (size_t)R * NQ * 2 * L, 256);
-    w.fold_din = (short *)(p + off);        off = align_up(off + sizeof(short) * (size_t)R * NQ * 32, 256);
+    w.fold_din = (short *)(p + off);        off = align_up(off + sizeof(short) * (size_t)R * NQ * 16, 256);
     w.bytes = off;
     return w;
 }
 
 // Enqueue the pre-pass.  After it, seg[R] (device) holds the number of entries.
 inline int run_prepare(const uint16_t *rg, const uint8_t *second, long long N, int G, int R,
-                       const Workspace &w, int *status, cudaStream_t st) {
+                       const Workspace &w, int *status, int grid, int ng, unsigned int gbytes,
+                       unsigned int slot, cudaStream_t st) {
     PrepArgs a;
     a.rg = rg; a.second = second; a.N = N; a.G = G;
     a.ngroups = (N + G - 1) / G; a.R = R;
     a.seg = w.seg; a.cursor = w.cursor; a.entries = w.entries; a.status = status;
+    a.grid = grid; a.ng = ng; a.gbytes = gbytes; a.slot = slot;
     if (a.ngroups == 0) {
         KBBQ_CUDA(cudaMemsetAsync(w.seg, 0, sizeof(unsigned int) * ((size_t)R + 1), st));
         return KBBQ_OK;

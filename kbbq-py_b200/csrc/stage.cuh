@@ -8,17 +8,22 @@
 // address arithmetic in the consumer's hot loop, and the copy engine runs ahead of the tally.
 //
 // One stage holds the `ng` groups (common.cuh) the thread-groups of the CTA process in one
-// iteration.  When the ng work-list entries are consecutive groups (always, with one read group)
-// the producer issues ONE copy per array of the aligned span that covers them; otherwise one copy
-// per group and array into fixed slots.  A header per group slot tells the consumers where the
-// group starts inside the stage (`soff`) and which of its rows belong to the read group (`bits`).
+// iteration, plus their `ng` work-list records (prepare.cuh), which the copy engine drops into
+// the stage header as they are: the record tells a thread-group where its group starts inside the
+// stage and, one flag byte per row, which rows are tallied (0 = not in this segment, 1 = read 1,
+// 3 = read 2 of a pair).  With one read group the list is the identity, so the producer issues ONE
+// copy per array of the aligned span that covers the ng consecutive groups and never reads the
+// list itself -- per stage it is one elected lane issuing four copies.  With several read groups
+// every group has its own slot and the lanes of the producer warp issue one copy per group and array.
+// Copies never reach past the 16-byte unit that holds the last byte of the arrays: callers must
+// make the arrays readable up to there (any cudaMalloc'ed or torch buffer is).
 #pragma once
 #include "common.cuh"
 #include "prepare.cuh"
 
 namespace kbbq {
 
-constexpr int MAX_STAGES = 4;
+constexpr int MAX_STAGES = 8;
 
 struct StageLayout {
     int stages;       // ring depth
@@ -26,7 +31,7 @@ struct StageLayout {
     int abytes;       // bytes of one array inside a stage (multiple of 128)
     int slot;         // bytes reserved per group when the groups of a stage are not contiguous
     int data_off;     // byte offsets from the start of dynamic shared memory
-    int hdr_off;      // stages x ng x uint4 {bits, soff, group index, 0}
+    int hdr_off;      // stages x ng work-list records (entry_t)
     int bar_off;      // full[stages], empty[stages] (8 bytes each)
     int total;        // dynamic shared memory bytes including the tables in front
 };
@@ -85,58 +90,95 @@ struct ProducerArgs {
     uint32_t lo, hi;      // this CTA's slice of the work list
     uint32_t gbytes;
     int ng;
+    long long total_bytes;  // bytes of each array (N * L)
 };
+
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 
 // Producer warp: walks the same (segment, iteration) sequence as the consumers.
 __device__ __forceinline__ void producer_loop(const ProducerArgs &p, const StageLayout &sl, unsigned char *smem_base) {
     const int lane = threadIdx.x & 31;
     const uint32_t data0 = smem_u32(smem_base + sl.data_off);
-    uint4 *hdr = reinterpret_cast<uint4 *>(smem_base + sl.hdr_off);
+    const uint32_t hdr0 = smem_u32(smem_base + sl.hdr_off);
     const uint32_t bar0 = smem_u32(smem_base + sl.bar_off);
     uint32_t stage = 0, phase = 0;
+    const unsigned long long end16 = ((unsigned long long)p.total_bytes + 15ull) & ~15ull;
+
+    if (p.R == 1) {  // identity list: one contiguous span per stage
+        if (lane != 0) return;
+        for (uint32_t first = p.lo; first < p.hi; first += p.ng) {
+            const uint32_t n = min((uint32_t)p.ng, p.hi - first);
+            const uint32_t full = bar0 + stage * 8, empty = bar0 + (sl.stages + stage) * 8;
+            const unsigned long long start = (unsigned long long)first * p.gbytes;
+            const uint32_t mis = (uint32_t)start & 15u;
+            const unsigned long long src = start - mis;
+            uint32_t bytes = (mis + n * p.gbytes + 15u) & ~15u;
+            // the last group of a batch may be partial: stop at the end of the arrays
+            bytes = src >= end16 ? 0u : (uint32_t)min((unsigned long long)bytes, end16 - src);
+            mbar_wait(empty, phase ^ 1);
+            mbar_arrive_expect_tx(full, bytes * sl.narr + n * 16u);
+            const uint32_t dst = data0 + stage * sl.narr * sl.abytes;
+            if (bytes) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k)
+                    if (k < sl.narr) bulk_g2s(dst + k * sl.abytes, p.arr[k] + src, bytes, full);
+            }
+            bulk_g2s(hdr0 + stage * p.ng * 16u, p.entries + first, n * 16u, full);
+            if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
+        }
+        return;
+    }
+
+    // Several read groups: lane j copies group j of the stage into slot j.  The group indices are
+    // fetched a batch (up to 32 records = several stages) ahead, so that no global-load latency
+    // sits between a stage being released and its refill being issued.
+    const uint32_t per_batch = (uint32_t)(32 / p.ng) * p.ng;  // whole iterations only
     for (int rg = 0; rg < p.R; ++rg) {
         uint32_t s_lo = p.seg[rg], s_hi = p.seg[rg + 1];
         if (s_hi <= p.lo) continue;
         if (s_lo >= p.hi) break;
         if (s_lo < p.lo) s_lo = p.lo;
         if (s_hi > p.hi) s_hi = p.hi;
+        auto fetch = [&](uint32_t base) -> uint32_t {
+            const unsigned long long i = (unsigned long long)base + lane;
+            return ((uint32_t)lane < per_batch && i < s_hi) ? __ldg(&p.entries[i].y) : 0u;
+        };
+        uint32_t bbase = s_lo;
+        uint32_t cur = fetch(bbase), nxt = fetch(bbase + per_batch);
         for (uint32_t first = s_lo; first < s_hi; first += p.ng) {
+            if (first - bbase >= per_batch) {
+                bbase += per_batch;
+                cur = nxt;
+                nxt = fetch(bbase + per_batch);
+            }
             const uint32_t n = min((uint32_t)p.ng, s_hi - first);
             const uint32_t full = bar0 + stage * 8, empty = bar0 + (sl.stages + stage) * 8;
+            const uint32_t grp = __shfl_sync(0xFFFFFFFFu, cur, (first - bbase + lane) & 31);
+            const unsigned long long start = (unsigned long long)grp * p.gbytes;
+            const uint32_t mis = (uint32_t)start & 15u;
+            const unsigned long long src = start - mis;
+            uint32_t bytes = 0;
+            if ((uint32_t)lane < n) {
+                bytes = (mis + p.gbytes + 15u) & ~15u;
+                bytes = src >= end16 ? 0u : (uint32_t)min((unsigned long long)bytes, end16 - src);
+            }
             if (lane == 0) mbar_wait(empty, phase ^ 1);
             __syncwarp();
-            uint32_t grp = 0, bits = 0;
-            if ((uint32_t)lane < n) {
-                const entry_t e = __ldg(p.entries + first + lane);
-                grp = (uint32_t)e;
-                bits = (uint32_t)(e >> 32);
-            }
-            const uint32_t grp0 = __shfl_sync(0xFFFFFFFFu, grp, 0);
-            const bool contig = __all_sync(0xFFFFFFFFu, (uint32_t)lane >= n || grp == grp0 + lane);
-            const unsigned long long start = (unsigned long long)(contig ? grp0 : grp) * p.gbytes;
-            const uint32_t mis = (uint32_t)start & 15u;
-            uint32_t soff, bytes;
-            if (contig) {
-                soff = mis + lane * p.gbytes;
-                bytes = (lane == 0) ? (mis + n * p.gbytes + 15u) & ~15u : 0u;
-            } else {
-                soff = lane * sl.slot + mis;
-                bytes = ((uint32_t)lane < n) ? (mis + p.gbytes + 15u) & ~15u : 0u;
-            }
-            if (lane < p.ng) hdr[stage * p.ng + lane] = make_uint4(bits, soff, grp, 0u);
-            uint32_t tx = bytes;
-#pragma unroll
-            for (int o = 16; o; o >>= 1) tx += __shfl_xor_sync(0xFFFFFFFFu, tx, o);
-            __syncwarp();
-            if (lane == 0) mbar_arrive_expect_tx(full, tx * sl.narr);
-            __syncwarp();
             if (bytes) {
-                const uint32_t dst = data0 + stage * sl.narr * sl.abytes + (contig ? 0u : lane * sl.slot);
-                const unsigned long long src = start - mis;
+                mbar_expect_tx(full, bytes * sl.narr);
+                const uint32_t dst = data0 + stage * sl.narr * sl.abytes + lane * sl.slot;
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                     if (k < sl.narr) bulk_g2s(dst + k * sl.abytes, p.arr[k] + src, bytes, full);
             }
+            if (lane == 0) {
+                mbar_expect_tx(full, n * 16u);
+                bulk_g2s(hdr0 + stage * p.ng * 16u, p.entries + first, n * 16u, full);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(full);  // after every expect_tx of the stage
             if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
         }
     }
