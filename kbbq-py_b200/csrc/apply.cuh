@@ -36,9 +36,10 @@ struct ApplyArgs {
     int *status;
 };
 
-// bytes of shared memory the apply tables take (no int64 sums)
-__host__ __device__ inline int apply_table_bytes(const TableCfg &t) { return t.sums_off; }
+// bytes of shared memory the apply tables take
+__host__ __device__ inline int apply_table_bytes(const TableCfg &t) { return t.table_bytes; }
 
+template <int KPS>
 __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid_constant__ ApplyArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Geom &g = a.g;
@@ -63,7 +64,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
         ProducerArgs p;
         p.arr[0] = a.seq; p.arr[1] = a.qual; p.arr[2] = nullptr;
         p.entries = a.entries; p.seg = a.seg; p.R = a.R; p.lo = lo; p.hi = hi;
-        p.gbytes = g.gbytes; p.ng = g.ng; p.total_bytes = a.total_bytes;
+        p.gbytes = g.gbytes; p.ng = sl.ngs; p.total_bytes = a.total_bytes;
         producer_loop(p, sl, smem_raw);
         return;
     }
@@ -77,13 +78,16 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
     for (int b = 0; b < 4; ++b) afwd[b] = pin(pos_base + m.cell[b]);
     const uint32_t selv = pin(m.selv), seln = pin(m.seln);
     const uint32_t rowsel = m.row >= 0 ? (uint32_t)m.row : 0u;
+    const uint32_t lanemask = pin(m.row >= 0 ? 0xFFu : 0u);
+    const uint32_t rowmask = pin(m.rowmask);
+    uint8_t *const outp = a.out + m.toff;
     const uint32_t data0 = smem_u32(smem_raw + sl.data_off) + m.toff;
     const uint32_t hdr0 = smem_u32(smem_raw + sl.hdr_off) + m.grp * 16;
-    const uint32_t stage_bytes = sl.narr * sl.abytes, abytes = sl.abytes, hdr_stride = g.ng * 16;
+    const uint32_t stage_bytes = sl.narr * sl.abytes, abytes = sl.abytes, hdr_stride = sl.ngs * 16, krec = g.ng * 16;
     const uint32_t mp = t.mp, md = t.md, revoff = t.revoff, addq = t.addq;
     const uint32_t addnq = (uint32_t)(128 - a.nq) * ONE4;  // q + this has bit 7 set iff q >= nq (q < 128)
     // how this thread's word is written back: whole, one aligned half, or byte by byte
-    const int wmode = m.rowmask == 0xFFFFFFFFu ? 0 : m.rowmask == 0x0000FFFFu ? 1 : m.rowmask == 0xFFFF0000u ? 2 : 3;
+    const uint32_t wmode = pin(m.rowmask == 0xFFFFFFFFu ? 0u : m.rowmask == 0x0000FFFFu ? 1u : m.rowmask == 0xFFFF0000u ? 2u : 3u);
     uint32_t stage = 0, phase = 0;
     uint32_t qbad = 0;
 
@@ -114,71 +118,72 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
         }
         consumer_sync(nconsumers);
 
-        for (uint32_t first = s_lo; first < s_hi; first += g.ng) {
-            const uint32_t nlive = min((uint32_t)g.ng, s_hi - first);
+        for (uint32_t first = s_lo; first < s_hi; first += sl.ngs) {
             mbar_wait(bar0 + stage * 8, phase);
-            uint32_t soff, hgrp, flo, fhi;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
-                         : "r"(hdr0 + stage * hdr_stride));
-            const uint32_t flag = (m.row >= 0 && (uint32_t)m.grp < nlive) ? (prmt(flo, fhi, rowsel) & 0xFFu) : 0u;
-            uint32_t sw = 0, qw = 0, pb = 0;
-            if (flag) {
-                const uint32_t wa = data0 + stage * stage_bytes + soff;
+            const uint32_t sdata = data0 + stage * stage_bytes, shdr = hdr0 + stage * hdr_stride;
+#pragma unroll
+            for (int k = 0; k < KPS; ++k) {
+                uint32_t soff, hgrp, flo, fhi;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
+                             : "r"(shdr + k * krec));
+                const uint32_t flag = prmt(flo, fhi, rowsel) & lanemask;
+                if (!flag) continue;
+                const uint32_t wa = sdata + soff;
+                uint32_t sw, qw, pb;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sw) : "r"(wa));
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qw) : "r"(wa + abytes));
                 asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pb) : "r"(wa - 1));
+
+                const uint32_t u = qw + addnq;              // bit 7 <=> q >= nq: IndexError in the reference
+                const uint32_t w5 = qw + addq;
+                qbad |= u | qw;
+                const uint32_t vraw = w5 & ~u & ~qw;
+                const uint32_t vm8 = prmt(vraw, 0u, selv);  // 0xFF for owned bytes with minscore - 1 <= q < nq
+                const uint32_t qrow4 = w5 & vm8 & 0x3F3F3F3Fu;
+                const uint32_t q4p = qrow4 * mp;
+                const uint32_t pw = prmt(pb, sw, 0x6540u);
+                const uint32_t d4 = (pw & 0x06060606u) * 4u + (sw & 0x06060606u);
+                const uint32_t nm8 = prmt((sw | pw) * 16u, 0xFFFFFFFFu, seln);
+                const uint32_t q4d = (qrow4 & ~nm8) * md;
+                const uint32_t rev = (flag >> 1) * revoff;
+
+                uint32_t v[4];
+#pragma unroll
+                for (int b = 0; b < 4; ++b) {
+                    const uint32_t pa = __dp4a(q4p, t.ohp[b], afwd[b] + rev);
+                    uint32_t da = __dp4a(d4, t.ohd[b], din_base);
+                    da = __dp4a(q4d, t.ohq[b], da);
+                    da = __dp4a(q4d, t.ohq[b], da);
+                    uint32_t x, y;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(pa));
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(y) : "r"(da));
+                    v[b] = x + y;
+                }
+                // low byte of every sum; qualities below minscore (row 0 selected nothing) pass through.
+                // q == minscore - 1 also has vm8 set with row 0: its "sum" must be q itself
+                const uint32_t sum4 = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+                const uint32_t keep8 = prmt(qrow4 + 0x7F7F7F7Fu, 0u, 0xBA98u);  // 0xFF where the row index is non-zero
+                const uint32_t res = (sum4 & keep8) | (qw & ~keep8);
+                uint8_t *dst = outp + (unsigned long long)hgrp * g.gbytes;  // + this thread's offset inside the group
+                if (wmode == 0) {
+                    *reinterpret_cast<unsigned int *>(dst) = res;
+                } else if (wmode == 1) {
+                    *reinterpret_cast<unsigned short *>(dst) = (unsigned short)res;
+                } else if (wmode == 2) {
+                    *reinterpret_cast<unsigned short *>(dst + 2) = (unsigned short)(res >> 16);
+                } else {
+#pragma unroll
+                    for (int b = 0; b < 4; ++b)
+                        if ((rowmask >> (8 * b)) & 1u) dst[b] = (uint8_t)(res >> (8 * b));
+                }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(bar0 + (sl.stages + stage) * 8);
             if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
-            if (!flag) continue;
-
-            const uint32_t u = qw + addnq;              // bit 7 <=> q >= nq: IndexError in the reference
-            const uint32_t w5 = qw + addq;
-            qbad |= u | qw;
-            const uint32_t vraw = w5 & ~u & ~qw;
-            const uint32_t vm8 = prmt(vraw, 0u, selv);  // 0xFF for owned bytes with minscore - 1 <= q < nq
-            const uint32_t qrow4 = w5 & vm8 & 0x3F3F3F3Fu;
-            const uint32_t q4p = qrow4 * mp;
-            const uint32_t pw = prmt(pb, sw, 0x6540u);
-            const uint32_t d4 = (pw & 0x06060606u) * 4u + (sw & 0x06060606u);
-            const uint32_t nm8 = prmt((sw | pw) * 16u, 0xFFFFFFFFu, seln);
-            const uint32_t q4d = (qrow4 & ~nm8) * md;
-            const uint32_t rev = (flag >> 1) * revoff;
-
-            uint32_t v[4];
-#pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const uint32_t pa = __dp4a(q4p, t.ohp[b], afwd[b] + rev);
-                uint32_t da = __dp4a(d4, t.ohd[b], din_base);
-                da = __dp4a(q4d, t.ohq[b], da);
-                da = __dp4a(q4d, t.ohq[b], da);
-                uint32_t x, y;
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(pa));
-                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(y) : "r"(da));
-                v[b] = x + y;
-            }
-            // low byte of every sum; qualities below minscore (row 0 selected nothing) pass through.
-            // q == minscore - 1 also has vm8 set with row 0: its "sum" must be q itself
-            const uint32_t sum4 = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
-            const uint32_t keep8 = prmt(qrow4 + 0x7F7F7F7Fu, 0u, 0xBA98u);  // 0xFF where the row index is non-zero
-            const uint32_t res = (sum4 & keep8) | (qw & ~keep8);
-            const long long off = (long long)((unsigned long long)hgrp * g.gbytes) + m.toff;
-            if (wmode == 0) {
-                *reinterpret_cast<unsigned int *>(a.out + off) = res;
-            } else if (wmode == 1) {
-                *reinterpret_cast<unsigned short *>(a.out + off) = (unsigned short)res;
-            } else if (wmode == 2) {
-                *reinterpret_cast<unsigned short *>(a.out + off + 2) = (unsigned short)(res >> 16);
-            } else {
-#pragma unroll
-                for (int b = 0; b < 4; ++b)
-                    if ((m.rowmask >> (8 * b)) & 1u) a.out[off + b] = (uint8_t)(res >> (8 * b));
-            }
         }
     }
-    if (qbad & m.rowmask & H4) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
+    if (qbad & rowmask & H4) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
 }
 
 // Generic path (any L): one thread per base, folded tables gathered from global memory (L1/L2).

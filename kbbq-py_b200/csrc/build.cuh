@@ -52,7 +52,7 @@ struct TableCfg {
     int revoff;       // bytes from the read-1 table to the read-2 table = nrows * rs
     int md, k1, k2;   // dinuc table: qrow * md, then * (k1 + k2); row stride dq = md * (k1 + k2)
     int dq;           // bytes, multiple of 128, >= 16 * 32 * 4
-    int pos_off, din_off, sums_off;  // byte offsets from the start of dynamic shared memory
+    int pos_off, din_off;            // byte offsets from the start of dynamic shared memory
     int table_bytes;  // zeroed at the start of every segment
     int flush_pos;    // iterations between flushes of the cycle table
     int fold_din;     // iterations between folds of the dinuc replicas
@@ -65,7 +65,7 @@ struct TableCfg {
     uint32_t ohe[4];  // 255: mismatch byte 0xFF -> 65025
 };
 
-inline bool make_table_cfg(const Geom &g, TableCfg *t) {
+inline bool make_table_cfg(const Geom &g, int kps, TableCfg *t) {
     if (g.minscore < 1) return false;  // row index * 6 must fit a byte
     t->nrows = NQ + 1 - g.minscore;
     t->sj = (g.L + 3) / 4;
@@ -78,12 +78,11 @@ inline bool make_table_cfg(const Geom &g, TableCfg *t) {
     t->md = 6; t->k1 = 192; t->k2 = 192; t->dq = 6 * 384;   // 2304 B >= 2048, multiple of 128
     t->pos_off = 0;
     t->din_off = 2 * t->revoff;
-    t->sums_off = t->din_off + t->nrows * t->dq;
-    t->table_bytes = t->sums_off + t->nrows * DIN_SLOTS * 2 * 8;
+    t->table_bytes = t->din_off + t->nrows * t->dq;
     // a cycle cell is hit at most once per (thread-group, row) and iteration; a dinuc replica cell
     // at most 4 times per thread of that lane id and iteration
-    t->flush_pos = (int)((ERR_UNIT - 1) / (uint32_t)(g.ng * g.G));
-    t->fold_din = (int)((ERR_UNIT - 1) / (uint32_t)(4 * (g.threads / 32)));
+    t->flush_pos = (int)((ERR_UNIT - 1) / (uint32_t)(kps * g.ng * g.G));
+    t->fold_din = (int)((ERR_UNIT - 1) / (uint32_t)(kps * 4 * (g.threads / 32)));
     t->addq = (uint32_t)(0x81 - g.minscore) * ONE4;
     for (int b = 0; b < 4; ++b) {
         t->ohp[b] = (uint32_t)t->kp << (8 * b);
@@ -168,13 +167,15 @@ __device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, int sj) {
     return m;
 }
 
-// Fold the per-lane dinuc replicas into the int64 sums (one warp per cell) and clear them.
-__device__ __forceinline__ void fold_din_replicas(const TableCfg &t, unsigned char *smem_raw, int nconsumers) {
+// Fold the per-lane dinuc replicas of this CTA into the global int64 tables of read group rg (one
+// warp per cell) and clear them.
+__device__ __forceinline__ void fold_din_replicas(const BuildArgs &a, unsigned char *smem_raw, int rg, int nconsumers) {
+    const TableCfg &t = a.t;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = nconsumers >> 5;
-    unsigned long long *sums = reinterpret_cast<unsigned long long *>(smem_raw + t.sums_off);
-    for (int cell = warp; cell < t.nrows * DIN_SLOTS; cell += nwarps) {
-        const int r = cell / DIN_SLOTS, s = cell - r * DIN_SLOTS;
-        unsigned int *p = reinterpret_cast<unsigned int *>(smem_raw + t.din_off + r * t.dq + s * (DIN_REP * 4)) + lane;
+    unsigned long long *gde = a.din_errs + (size_t)rg * NQ * 16, *gdt = a.din_total + (size_t)rg * NQ * 16;
+    for (int cell = DIN_SLOTS + warp; cell < t.nrows * DIN_SLOTS; cell += nwarps) {  // row 0 is the trash row
+        const int r = cell / DIN_SLOTS, dn = cell - r * DIN_SLOTS;
+        unsigned int *p = reinterpret_cast<unsigned int *>(smem_raw + t.din_off + r * t.dq + dn * (DIN_REP * 4)) + lane;
         const unsigned int v = *p;
         if (__any_sync(0xFFFFFFFFu, v != 0)) {
             *p = 0;
@@ -184,7 +185,13 @@ __device__ __forceinline__ void fold_din_replicas(const TableCfg &t, unsigned ch
                 tot += __shfl_xor_sync(0xFFFFFFFFu, tot, o);
                 er += __shfl_xor_sync(0xFFFFFFFFu, er, o);
             }
-            if (lane == 0) { sums[2 * cell] += tot; sums[2 * cell + 1] += er; }
+            if (lane == 0) {
+                // slot = 4 * code(prev) + code(cur) in natural order; the reference orders A T G C
+                const int dref = nat_to_ref(dn >> 2) * 4 + nat_to_ref(dn & 3);
+                const size_t o = (size_t)(r + a.g.minscore - 1) * 16 + dref;
+                atomicAdd(gdt + o, (unsigned long long)tot);
+                if (er) atomicAdd(gde + o, (unsigned long long)er);
+            }
         }
     }
 }
@@ -213,7 +220,7 @@ __device__ __forceinline__ void flush_pos_table(const BuildArgs &a, unsigned cha
     }
 }
 
-template <bool VALIDATE>
+template <int KPS, bool VALIDATE>
 __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid_constant__ BuildArgs a) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const Geom &g = a.g;
@@ -239,7 +246,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
         ProducerArgs p;
         p.arr[0] = a.seq; p.arr[1] = a.qual; p.arr[2] = a.corr;
         p.entries = a.entries; p.seg = a.seg; p.R = a.R; p.lo = lo; p.hi = hi;
-        p.gbytes = g.gbytes; p.ng = g.ng; p.total_bytes = a.total_bytes;
+        p.gbytes = g.gbytes; p.ng = sl.ngs; p.total_bytes = a.total_bytes;
         producer_loop(p, sl, smem_raw);
         return;
     }
@@ -254,9 +261,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
     for (int b = 0; b < 4; ++b) afwd[b] = pin(pos_base + m.cell[b]);
     const uint32_t selv = pin(m.selv), seln = pin(m.seln);
     const uint32_t rowsel = m.row >= 0 ? (uint32_t)m.row : 0u;  // prmt selector: flag byte of this thread's row
+    const uint32_t lanemask = pin(m.row >= 0 ? 0xFFu : 0u);     // padding lanes never see a live row
+    const uint32_t rowmask = pin(m.rowmask);
     const uint32_t data0 = smem_u32(smem_raw + sl.data_off) + m.toff;
     const uint32_t hdr0 = smem_u32(smem_raw + sl.hdr_off) + m.grp * 16;
-    const uint32_t stage_bytes = sl.narr * sl.abytes, abytes = sl.abytes, hdr_stride = g.ng * 16;
+    const uint32_t stage_bytes = sl.narr * sl.abytes, abytes = sl.abytes, hdr_stride = sl.ngs * 16, krec = g.ng * 16;
     const uint32_t mp = t.mp, md = t.md, revoff = t.revoff, addq = t.addq;
     uint32_t stage = 0, phase = 0;
     uint32_t qbad = 0, bbad = 0;
@@ -276,69 +285,71 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
         // total field could otherwise reach ERR_UNIT are folded.
         for (uint32_t first = s_lo; first < s_hi;) {
             const uint32_t chunk_end = (uint32_t)min((unsigned long long)s_hi,
-                                                     (unsigned long long)first + (unsigned long long)t.fold_din * g.ng);
+                                                     (unsigned long long)first + (unsigned long long)t.fold_din * sl.ngs);
             since_pos += t.fold_din;
-            for (; first < chunk_end; first += g.ng) {
-                const uint32_t nlive = min((uint32_t)g.ng, s_hi - first);  // thread-groups with a record
+            for (; first < chunk_end; first += sl.ngs) {
                 mbar_wait(bar0 + stage * 8, phase);
-                uint32_t soff, hgrp, flo, fhi;
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
-                             : "r"(hdr0 + stage * hdr_stride));
-                // flag byte of this thread's row: 0 = not in this segment, 1 = read 1, 3 = read 2
-                const uint32_t flag = (m.row >= 0 && (uint32_t)m.grp < nlive) ? (prmt(flo, fhi, rowsel) & 0xFFu) : 0u;
-                uint32_t sw = 0, qw = 0, cw = 0, pb = 0;
-                if (flag) {
-                    const uint32_t wa = data0 + stage * stage_bytes + soff;
+                const uint32_t sdata = data0 + stage * stage_bytes, shdr = hdr0 + stage * hdr_stride;
+#pragma unroll
+                for (int k = 0; k < KPS; ++k) {
+                    // this thread-group's k-th record of the stage
+                    uint32_t soff, hgrp, flo, fhi;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
+                                 : "r"(shdr + k * krec));
+                    // flag byte of this thread's row: 0 = not in this segment (or a padding lane), 1 = read 1, 3 = read 2
+                    const uint32_t flag = prmt(flo, fhi, rowsel) & lanemask;
+                    if (!flag) continue;
+                    const uint32_t wa = sdata + soff;
+                    uint32_t sw, qw, cw, pb;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sw) : "r"(wa));
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qw) : "r"(wa + abytes));
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(wa + 2 * abytes));
                     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pb) : "r"(wa - 1));
+
+                    // ---- quality -> row index, byte-parallel ----
+                    const uint32_t u = qw + 0x55555555u;        // bit 7 <=> q >= 43 (for q < 128)
+                    const uint32_t w5 = qw + addq;              // bit 7 <=> q >= minscore - 1, low bits q - (minscore - 1)
+                    qbad |= u | qw;
+                    const uint32_t vraw = w5 & ~u & ~qw;        // bit 7 <=> minscore - 1 <= q <= 42
+                    const uint32_t vm8 = prmt(vraw, 0u, selv);  // 0xFF for owned bytes in range
+                    const uint32_t qrow4 = w5 & vm8 & 0x3F3F3F3Fu;  // 0 = trash row
+                    const uint32_t q4p = qrow4 * mp;
+
+                    // ---- dinucleotide slot, byte-parallel: 2 * (4 * code(prev) + code(cur)), code = (b >> 1) & 3 ----
+                    const uint32_t pw = prmt(pb, sw, 0x6540u);  // previous base of every byte
+                    const uint32_t d4 = (pw & 0x06060606u) * 4u + (sw & 0x06060606u);
+                    // 'N' is the only accepted base with bit 3 set; cycle 0 and foreign bytes take 0xFF from the selector
+                    const uint32_t nm8 = prmt((sw | pw) * 16u, 0xFFFFFFFFu, seln);
+                    const uint32_t q4d = (qrow4 & ~nm8) * md;
+
+                    // ---- mismatch: 0xFF where the corrected base differs (bases are 7-bit) ----
+                    const uint32_t e8 = prmt((sw ^ cw) + 0x7F7F7F7Fu, 0u, 0xBA98u);
+
+                    if (VALIDATE) {
+                        // rebuild each byte from its 3-bit code with an 8-entry byte LUT; any difference = bad base
+                        const uint32_t code3 = (sw >> 1) & 0x07070707u;
+                        const uint32_t y = code3 | (code3 >> 4);
+                        const uint32_t sel = __byte_perm(y, 0, 0x4420);
+                        const uint32_t recon = __byte_perm(0x47544341u /* A C T G */, 0x4E000000u /* . . . N */, sel);
+                        bbad |= (recon ^ sw) & rowmask;
+                    }
+
+                    const uint32_t rev = (flag >> 1) * revoff;  // read-2 rows tally into the second cycle table
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) {
+                        const uint32_t inc = __dp4a(e8, t.ohe[b], 1u);
+                        const uint32_t pa = __dp4a(q4p, t.ohp[b], afwd[b] + rev);
+                        uint32_t da = __dp4a(d4, t.ohd[b], din_base);
+                        da = __dp4a(q4d, t.ohq[b], da);
+                        da = __dp4a(q4d, t.ohq[b], da);
+                        red_shared_add(pa, inc);
+                        red_shared_add(da, inc);
+                    }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(bar0 + (sl.stages + stage) * 8);  // the stage may be refilled
                 if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
-                if (!flag) continue;  // padding lane, or the row belongs to another read group
-
-                // ---- quality -> row index, byte-parallel ----
-                const uint32_t u = qw + 0x55555555u;        // bit 7 <=> q >= 43 (for q < 128)
-                const uint32_t w5 = qw + addq;              // bit 7 <=> q >= minscore - 1, low bits q - (minscore - 1)
-                qbad |= u | qw;
-                const uint32_t vraw = w5 & ~u & ~qw;        // bit 7 <=> minscore - 1 <= q <= 42
-                const uint32_t vm8 = prmt(vraw, 0u, selv);  // 0xFF for owned bytes in range
-                const uint32_t qrow4 = w5 & vm8 & 0x3F3F3F3Fu;  // 0 = trash row
-                const uint32_t q4p = qrow4 * mp;
-
-                // ---- dinucleotide slot, byte-parallel: 2 * (4 * code(prev) + code(cur)), code = (b >> 1) & 3 ----
-                const uint32_t pw = prmt(pb, sw, 0x6540u);  // previous base of every byte
-                const uint32_t d4 = (pw & 0x06060606u) * 4u + (sw & 0x06060606u);
-                // 'N' is the only accepted base with bit 3 set; cycle 0 and foreign bytes take 0xFF from the selector
-                const uint32_t nm8 = prmt((sw | pw) * 16u, 0xFFFFFFFFu, seln);
-                const uint32_t q4d = (qrow4 & ~nm8) * md;
-
-                // ---- mismatch: 0xFF where the corrected base differs (bases are 7-bit) ----
-                const uint32_t e8 = prmt((sw ^ cw) + 0x7F7F7F7Fu, 0u, 0xBA98u);
-
-                if (VALIDATE) {
-                    // rebuild each byte from its 3-bit code with an 8-entry byte LUT; any difference = bad base
-                    const uint32_t code3 = (sw >> 1) & 0x07070707u;
-                    const uint32_t y = code3 | (code3 >> 4);
-                    const uint32_t sel = __byte_perm(y, 0, 0x4420);
-                    const uint32_t recon = __byte_perm(0x47544341u /* A C T G */, 0x4E000000u /* . . . N */, sel);
-                    bbad |= (recon ^ sw) & m.rowmask;
-                }
-
-                const uint32_t rev = (flag >> 1) * revoff;  // read-2 rows tally into the second cycle table
-#pragma unroll
-                for (int b = 0; b < 4; ++b) {
-                    const uint32_t inc = __dp4a(e8, t.ohe[b], 1u);
-                    const uint32_t pa = __dp4a(q4p, t.ohp[b], afwd[b] + rev);
-                    uint32_t da = __dp4a(d4, t.ohd[b], din_base);
-                    da = __dp4a(q4d, t.ohq[b], da);
-                    da = __dp4a(q4d, t.ohq[b], da);
-                    red_shared_add(pa, inc);
-                    red_shared_add(da, inc);
-                }
             }
             if (first < s_hi) {
                 consumer_sync(nconsumers);
@@ -346,7 +357,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
                     flush_pos_table(a, smem_raw, rg, nconsumers);
                     since_pos = 0;
                 }
-                fold_din_replicas(t, smem_raw, nconsumers);
+                fold_din_replicas(a, smem_raw, rg, nconsumers);
                 consumer_sync(nconsumers);
             }
         }
@@ -354,21 +365,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
 
         // flush this read group's partial tables: u32 shared -> int64 global
         flush_pos_table(a, smem_raw, rg, nconsumers);
-        fold_din_replicas(t, smem_raw, nconsumers);
-        consumer_sync(nconsumers);
-        const unsigned long long *sums = reinterpret_cast<const unsigned long long *>(smem_raw + t.sums_off);
-        unsigned long long *gde = a.din_errs + (size_t)rg * NQ * 16, *gdt = a.din_total + (size_t)rg * NQ * 16;
-        for (int i = threadIdx.x; i < (t.nrows - 1) * DIN_SLOTS; i += nconsumers) {
-            const int r = i / DIN_SLOTS + 1, dn = i & (DIN_SLOTS - 1);
-            const unsigned long long tot = sums[2 * (r * DIN_SLOTS + dn)], er = sums[2 * (r * DIN_SLOTS + dn) + 1];
-            const int dref = nat_to_ref(dn >> 2) * 4 + nat_to_ref(dn & 3);
-            const size_t o = (size_t)(r + g.minscore - 1) * 16 + dref;
-            if (tot) atomicAdd(gdt + o, tot);
-            if (er) atomicAdd(gde + o, er);
-        }
+        fold_din_replicas(a, smem_raw, rg, nconsumers);
         consumer_sync(nconsumers);
     }
-    if (qbad & m.rowmask & H4) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
+    if (qbad & rowmask & H4) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
     if (VALIDATE && bbad) atomicOr(a.status, KBBQ_FLAG_BAD_BASE);
 }
 

@@ -55,31 +55,59 @@ static int current_device_info(int *device, int *sms, int *max_smem) {
 
 static bool misaligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) != 0; }
 
-// Deepest staging ring (at least 2 stages) that fits the CTA's shared memory behind the tables.
-static bool pick_stages(const Geom &g, int narr, int max_smem, size_t table_bytes, int *stages) {
-    for (int s = MAX_STAGES; s >= 2; --s) {
-        if (make_stage_layout(g, narr, s, table_bytes).total <= max_smem) {
-            *stages = s;
-            return true;
+// Staging ring that fits the CTA's shared memory behind the tables: as many groups per thread-group
+// and stage as still leave a ring of MIN_DEEP stages (barrier traffic is paid per stage), then the
+// deepest ring; at least 2 stages.  A stage never holds more than 32 groups (one per producer lane).
+static bool pick_stages(const Geom &g, int narr, int max_smem, size_t table_bytes, int *stages, int *kps) {
+    const int MIN_DEEP = 3;
+    const char *e = getenv("KBBQ_KPS");  // tuning / test hook
+    const int kmax = e ? std::max(1, std::min(4, atoi(e))) : 4;
+    for (int want = MIN_DEEP; want >= 2; --want) {
+        for (int k = kmax; k >= 1; --k) {
+            if (g.ng * k > 32) continue;
+            for (int s = MAX_STAGES; s >= want; --s) {
+                if (make_stage_layout(g, narr, s, k, table_bytes).total <= max_smem) {
+                    *stages = s; *kps = k;
+                    return true;
+                }
+            }
         }
     }
     return false;
 }
 
-static int launch_build_smem(const BuildArgs &a, int grid, size_t smem, cudaStream_t st) {
-    auto kern = build_smem_kernel<true>;
+template <int KPS>
+static int launch_build_kps(const BuildArgs &a, int grid, size_t smem, cudaStream_t st) {
+    auto kern = build_smem_kernel<KPS, true>;
     KBBQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, a.g.threads + 32, smem, st>>>(a);  // + the producer warp
     KBBQ_LAUNCHED();
     return KBBQ_OK;
 }
+static int launch_build_smem(const BuildArgs &a, int grid, size_t smem, cudaStream_t st) {
+    switch (a.sl.kps) {
+    case 4: return launch_build_kps<4>(a, grid, smem, st);
+    case 3: return launch_build_kps<3>(a, grid, smem, st);
+    case 2: return launch_build_kps<2>(a, grid, smem, st);
+    default: return launch_build_kps<1>(a, grid, smem, st);
+    }
+}
 
-static int launch_apply_smem(const ApplyArgs &a, int grid, size_t smem, cudaStream_t st) {
-    auto kern = apply_smem_kernel;
+template <int KPS>
+static int launch_apply_kps(const ApplyArgs &a, int grid, size_t smem, cudaStream_t st) {
+    auto kern = apply_smem_kernel<KPS>;
     KBBQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, a.g.threads + 32, smem, st>>>(a);  // + the producer warp
     KBBQ_LAUNCHED();
     return KBBQ_OK;
+}
+static int launch_apply_smem(const ApplyArgs &a, int grid, size_t smem, cudaStream_t st) {
+    switch (a.sl.kps) {
+    case 4: return launch_apply_kps<4>(a, grid, smem, st);
+    case 3: return launch_apply_kps<3>(a, grid, smem, st);
+    case 2: return launch_apply_kps<2>(a, grid, smem, st);
+    default: return launch_apply_kps<1>(a, grid, smem, st);
+    }
 }
 
 }  // namespace kbbq
@@ -131,8 +159,9 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
                    (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull &&
                    !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(corr, 16);
     TableCfg tc;
-    int stages = 0;
-    smem_ok = smem_ok && make_table_cfg(g, &tc) && pick_stages(g, 3, max_smem, tc.table_bytes, &stages);
+    int stages = 0, kps = 1;
+    smem_ok = smem_ok && make_table_cfg(g, 1, &tc) && pick_stages(g, 3, max_smem, tc.table_bytes, &stages, &kps) &&
+              make_table_cfg(g, kps, &tc);
     if (!smem_ok) {
         if (path == 1) return KBBQ_E_ARG;
         BuildGenericArgs a = {seq, qual, corr, rg, second, N, L, R, minscore,
@@ -144,8 +173,8 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
     }
     Workspace w = carve_workspace(workspace, N, L, R);
     if (!workspace || workspace_bytes < w.bytes) return KBBQ_E_WORKSPACE;
-    const StageLayout sl = make_stage_layout(g, 3, stages, tc.table_bytes);
-    rc = run_prepare(rg, second, N, g.G, R, w, status, sms, g.ng, g.gbytes, sl.slot, st);
+    const StageLayout sl = make_stage_layout(g, 3, stages, kps, tc.table_bytes);
+    rc = run_prepare(rg, second, N, g.G, R, w, status, sms, sl.ngs, g.gbytes, sl.slot, st);
     if (rc) return rc;
 
     BuildArgs a;
@@ -243,8 +272,8 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
                    (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull &&
                    !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(out_qual, 4);
     TableCfg tc;
-    int stages = 0;
-    smem_ok = smem_ok && make_table_cfg(g, &tc) && pick_stages(g, 2, max_smem, apply_table_bytes(tc), &stages);
+    int stages = 0, kps = 1;
+    smem_ok = smem_ok && make_table_cfg(g, 1, &tc) && pick_stages(g, 2, max_smem, apply_table_bytes(tc), &stages, &kps);
     if (!smem_ok) {
         if (path == 1) return KBBQ_E_ARG;
         ApplyGenericArgs a = {seq, qual, rg, second, out_qual, N, L, R, minscore, nq, w.fold_cyc, w.fold_din, status};
@@ -252,8 +281,8 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
         KBBQ_LAUNCHED();
         return KBBQ_OK;
     }
-    const StageLayout sl = make_stage_layout(g, 2, stages, apply_table_bytes(tc));
-    rc = run_prepare(rg, second, N, g.G, R, w, status, sms, g.ng, g.gbytes, sl.slot, st);
+    const StageLayout sl = make_stage_layout(g, 2, stages, kps, apply_table_bytes(tc));
+    rc = run_prepare(rg, second, N, g.G, R, w, status, sms, sl.ngs, g.gbytes, sl.slot, st);
     if (rc) return rc;
     ApplyArgs a;
     a.seq = seq; a.qual = qual; a.out = out_qual; a.total_bytes = N * L; a.g = g; a.t = tc; a.R = R; a.nq = nq;

@@ -27,6 +27,8 @@ constexpr int MAX_STAGES = 8;
 
 struct StageLayout {
     int stages;       // ring depth
+    int kps;          // groups every thread-group takes out of one stage
+    int ngs;          // groups per stage = ng * kps
     int narr;         // arrays staged (3 for build, 2 for apply)
     int abytes;       // bytes of one array inside a stage (multiple of 128)
     int slot;         // bytes reserved per group when the groups of a stage are not contiguous
@@ -36,15 +38,17 @@ struct StageLayout {
     int total;        // dynamic shared memory bytes including the tables in front
 };
 
-inline StageLayout make_stage_layout(const Geom &g, int narr, int stages, size_t table_bytes) {
+inline StageLayout make_stage_layout(const Geom &g, int narr, int stages, int kps, size_t table_bytes) {
     StageLayout s;
     s.stages = stages;
+    s.kps = kps;
+    s.ngs = g.ng * kps;
     s.narr = narr;
     s.slot = (g.gbytes + 15 + 15) / 16 * 16;           // group + worst-case misalignment, 16-byte units
-    s.abytes = (g.ng * s.slot + 127) / 128 * 128;      // also covers the contiguous span (ng*gbytes + 30)
+    s.abytes = (s.ngs * s.slot + 127) / 128 * 128;     // also covers the contiguous span (ngs*gbytes + 30)
     s.data_off = (int)((table_bytes + 127) / 128 * 128);
     s.hdr_off = s.data_off + stages * narr * s.abytes;
-    s.bar_off = s.hdr_off + stages * g.ng * 16;
+    s.bar_off = s.hdr_off + stages * s.ngs * 16;
     s.total = s.bar_off + 2 * stages * 8;
     return s;
 }
@@ -89,7 +93,7 @@ struct ProducerArgs {
     int R;
     uint32_t lo, hi;      // this CTA's slice of the work list
     uint32_t gbytes;
-    int ng;
+    int ng;                 // groups per stage (StageLayout::ngs)
     long long total_bytes;  // bytes of each array (N * L)
 };
 
@@ -118,6 +122,9 @@ __device__ __forceinline__ void producer_loop(const ProducerArgs &p, const Stage
             // the last group of a batch may be partial: stop at the end of the arrays
             bytes = src >= end16 ? 0u : (uint32_t)min((unsigned long long)bytes, end16 - src);
             mbar_wait(empty, phase ^ 1);
+            // a short last stage: the slots past the list must read as "no rows"
+            for (uint32_t j = n; j < (uint32_t)p.ng; ++j)
+                asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(hdr0 + (stage * p.ng + j) * 16u), "r"(0u) : "memory");
             mbar_arrive_expect_tx(full, bytes * sl.narr + n * 16u);
             const uint32_t dst = data0 + stage * sl.narr * sl.abytes;
             if (bytes) {
@@ -173,12 +180,14 @@ __device__ __forceinline__ void producer_loop(const ProducerArgs &p, const Stage
                 for (int k = 0; k < 3; ++k)
                     if (k < sl.narr) bulk_g2s(dst + k * sl.abytes, p.arr[k] + src, bytes, full);
             }
+            if ((uint32_t)lane >= n && lane < p.ng)  // a short last stage: "no rows" past the list
+                asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(hdr0 + (stage * p.ng + lane) * 16u), "r"(0u) : "memory");
             if (lane == 0) {
                 mbar_expect_tx(full, n * 16u);
                 bulk_g2s(hdr0 + stage * p.ng * 16u, p.entries + first, n * 16u, full);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(full);  // after every expect_tx of the stage
+            if (lane == 0) mbar_arrive(full);  // after every expect_tx and header store of the stage
             if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
         }
     }
