@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
     const ThreadMap m = make_thread_map(g, t.sj);
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
-    const uint32_t din_base = pin(smem_addr(smem_raw + t.din_off) + lane * 4);
+    const uint32_t din_base = pin(smem_addr(smem_raw + t.din_off) + (lane & (t.drep - 1)) * 4);
     uint32_t afwd[4];
 #pragma unroll
     for (int b = 0; b < 4; ++b) afwd[b] = pin(pos_base + m.cell[b]);
@@ -80,14 +80,18 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
     const uint32_t rowsel = m.row >= 0 ? (uint32_t)m.row : 0u;
     const uint32_t lanemask = pin(m.row >= 0 ? 0xFFu : 0u);
     const uint32_t rowmask = pin(m.rowmask);
-    uint8_t *const outp = a.out + m.toff;
+    // how this thread's word is written back: whole (0), one aligned half (1, the usual partial
+    // word: reads of even length start 2-byte aligned) or byte by byte (2)
+    const bool half_lo = m.rowmask == 0x0000FFFFu, half_hi = m.rowmask == 0xFFFF0000u;
+    const uint32_t wmode = pin(m.rowmask == 0xFFFFFFFFu ? 0u : (half_lo || half_hi) ? 1u : 2u);
+    const uint32_t wshift = pin(half_hi ? 16u : 0u);
+    unsigned long long outp = (unsigned long long)(a.out + m.toff + (half_hi ? 2 : 0));
+    asm volatile("" : "+l"(outp));
     const uint32_t data0 = smem_u32(smem_raw + sl.data_off) + m.toff;
     const uint32_t hdr0 = smem_u32(smem_raw + sl.hdr_off) + m.grp * 16;
     const uint32_t stage_bytes = sl.narr * sl.abytes, abytes = sl.abytes, hdr_stride = sl.ngs * 16, krec = g.ng * 16;
-    const uint32_t mp = t.mp, md = t.md, revoff = t.revoff, addq = t.addq;
+    const uint32_t mp = t.mp, md = t.md, revoff = t.revoff, addq = t.addq, gbytes = g.gbytes;
     const uint32_t addnq = (uint32_t)(128 - a.nq) * ONE4;  // q + this has bit 7 set iff q >= nq (q < 128)
-    // how this thread's word is written back: whole, one aligned half, or byte by byte
-    const uint32_t wmode = pin(m.rowmask == 0xFFFFFFFFu ? 0u : m.rowmask == 0x0000FFFFu ? 1u : m.rowmask == 0xFFFF0000u ? 2u : 3u);
     uint32_t stage = 0, phase = 0;
     uint32_t qbad = 0;
 
@@ -111,9 +115,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
             *p = fc[(size_t)(r + g.minscore - 1) * L2 + c2];
         }
         const short *fd = a.fold_din + (size_t)rg * NQ * DIN_SLOTS;
-        for (int i = threadIdx.x; i < (t.nrows - 1) * DIN_SLOTS * DIN_REP; i += nconsumers) {
-            const int cell = i / DIN_REP, r = cell / DIN_SLOTS + 1, s = cell & (DIN_SLOTS - 1);
-            int *p = reinterpret_cast<int *>(smem_raw + t.din_off + r * t.dq + s * (DIN_REP * 4)) + (i & (DIN_REP - 1));
+        for (int i = threadIdx.x; i < (t.nrows - 1) * DIN_SLOTS * t.drep; i += nconsumers) {
+            const int cell = i / t.drep, r = cell / DIN_SLOTS + 1, s = cell & (DIN_SLOTS - 1);
+            int *p = reinterpret_cast<int *>(smem_raw + t.din_off + r * t.dq + s * (t.drep * 4)) + (i & (t.drep - 1));
             *p = fd[(r + g.minscore - 1) * DIN_SLOTS + s];
         }
         consumer_sync(nconsumers);
@@ -165,17 +169,17 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
                 const uint32_t sum4 = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
                 const uint32_t keep8 = prmt(qrow4 + 0x7F7F7F7Fu, 0u, 0xBA98u);  // 0xFF where the row index is non-zero
                 const uint32_t res = (sum4 & keep8) | (qw & ~keep8);
-                uint8_t *dst = outp + (unsigned long long)hgrp * g.gbytes;  // + this thread's offset inside the group
+                // group base + this thread's offset inside the group (64-bit multiply-add, one instruction)
+                const unsigned long long dst = outp + (unsigned long long)hgrp * gbytes;
                 if (wmode == 0) {
-                    *reinterpret_cast<unsigned int *>(dst) = res;
+                    asm volatile("st.global.u32 [%0], %1;" ::"l"(dst), "r"(res) : "memory");
                 } else if (wmode == 1) {
-                    *reinterpret_cast<unsigned short *>(dst) = (unsigned short)res;
-                } else if (wmode == 2) {
-                    *reinterpret_cast<unsigned short *>(dst + 2) = (unsigned short)(res >> 16);
+                    asm volatile("st.global.u16 [%0], %1;" ::"l"(dst), "h"((unsigned short)(res >> wshift)) : "memory");
                 } else {
 #pragma unroll
                     for (int b = 0; b < 4; ++b)
-                        if ((rowmask >> (8 * b)) & 1u) dst[b] = (uint8_t)(res >> (8 * b));
+                        if ((rowmask >> (8 * b)) & 1u)
+                            asm volatile("st.global.u8 [%0], %1;" ::"l"(dst + b), "r"(res >> (8 * b)) : "memory");
                 }
             }
             __syncwarp();

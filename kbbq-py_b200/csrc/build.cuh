@@ -39,7 +39,7 @@ namespace kbbq {
 
 constexpr uint32_t ERR_UNIT = 65025u;  // 255 * 255: what a mismatching base adds on top of the 1
 constexpr int DIN_SLOTS = 16;
-constexpr int DIN_REP = 32;            // dinuc table replicas = lanes of a warp
+constexpr int DIN_REP = 32;            // dinuc table replicas when they fit: bank == lane
 constexpr int MAX_WARPS = MAX_THREADS / 32;
 
 // Shared-memory table geometry, chosen on the host (make_table_cfg).
@@ -51,7 +51,8 @@ struct TableCfg {
     int sj;           // plane stride in words: cell of cycle c at word (c & 3) * sj + (c >> 2)
     int revoff;       // bytes from the read-1 table to the read-2 table = nrows * rs
     int md, k1, k2;   // dinuc table: qrow * md, then * (k1 + k2); row stride dq = md * (k1 + k2)
-    int dq;           // bytes, multiple of 128, >= 16 * 32 * 4
+    int dq;           // bytes, multiple of 128, >= 16 * drep * 4
+    int drep;         // replicas of the dinuc table (32: bank == lane; 16: lanes l and l + 16 share one)
     int pos_off, din_off;            // byte offsets from the start of dynamic shared memory
     int table_bytes;  // zeroed at the start of every segment
     int flush_pos;    // iterations between flushes of the cycle table
@@ -61,11 +62,11 @@ struct TableCfg {
     // Kept in the kernel parameters so that the instruction reads them straight from the constant bank.
     uint32_t ohp[4];  // kp: cycle-table row
     uint32_t ohq[4];  // k1 (= k2): dinuc-table row, applied twice
-    uint32_t ohd[4];  // 64: the slot byte holds 2 * slot, a slot is 32 lanes x 4 B
+    uint32_t ohd[4];  // drep * 2: the slot byte holds 2 * slot, a slot is drep x 4 B
     uint32_t ohe[4];  // 255: mismatch byte 0xFF -> 65025
 };
 
-inline bool make_table_cfg(const Geom &g, int kps, TableCfg *t) {
+inline bool make_table_cfg(const Geom &g, int kps, int drep, TableCfg *t) {
     if (g.minscore < 1) return false;  // row index * 6 must fit a byte
     t->nrows = NQ + 1 - g.minscore;
     t->sj = (g.L + 3) / 4;
@@ -75,19 +76,22 @@ inline bool make_table_cfg(const Geom &g, int kps, TableCfg *t) {
     else if (rs <= 1152) { t->mp = 6; t->kp = 192; t->rs = 1152; }
     else return false;
     t->revoff = t->nrows * t->rs;
-    t->md = 6; t->k1 = 192; t->k2 = 192; t->dq = 6 * 384;   // 2304 B >= 2048, multiple of 128
+    t->drep = drep;
+    if (drep == 32) { t->md = 6; t->k1 = 192; t->k2 = 192; t->dq = 6 * 384; }   // 2304 B >= 2048, multiple of 128
+    else if (drep == 16) { t->md = 4; t->k1 = 128; t->k2 = 128; t->dq = 1024; }
+    else return false;
     t->pos_off = 0;
     t->din_off = 2 * t->revoff;
     t->table_bytes = t->din_off + t->nrows * t->dq;
     // a cycle cell is hit at most once per (thread-group, row) and iteration; a dinuc replica cell
     // at most 4 times per thread of that lane id and iteration
     t->flush_pos = (int)((ERR_UNIT - 1) / (uint32_t)(kps * g.ng * g.G));
-    t->fold_din = (int)((ERR_UNIT - 1) / (uint32_t)(kps * 4 * (g.threads / 32)));
+    t->fold_din = (int)((ERR_UNIT - 1) / (uint32_t)(kps * 4 * (g.threads / drep)));
     t->addq = (uint32_t)(0x81 - g.minscore) * ONE4;
     for (int b = 0; b < 4; ++b) {
         t->ohp[b] = (uint32_t)t->kp << (8 * b);
         t->ohq[b] = (uint32_t)t->k1 << (8 * b);
-        t->ohd[b] = (uint32_t)(DIN_REP * 4 / 2) << (8 * b);
+        t->ohd[b] = (uint32_t)(drep * 4 / 2) << (8 * b);
         t->ohe[b] = 255u << (8 * b);
     }
     return true;
@@ -175,10 +179,10 @@ __device__ __forceinline__ void fold_din_replicas(const BuildArgs &a, unsigned c
     unsigned long long *gde = a.din_errs + (size_t)rg * NQ * 16, *gdt = a.din_total + (size_t)rg * NQ * 16;
     for (int cell = DIN_SLOTS + warp; cell < t.nrows * DIN_SLOTS; cell += nwarps) {  // row 0 is the trash row
         const int r = cell / DIN_SLOTS, dn = cell - r * DIN_SLOTS;
-        unsigned int *p = reinterpret_cast<unsigned int *>(smem_raw + t.din_off + r * t.dq + dn * (DIN_REP * 4)) + lane;
-        const unsigned int v = *p;
+        unsigned int *p = reinterpret_cast<unsigned int *>(smem_raw + t.din_off + r * t.dq + dn * (t.drep * 4)) + lane;
+        const unsigned int v = lane < t.drep ? *p : 0u;
         if (__any_sync(0xFFFFFFFFu, v != 0)) {
-            *p = 0;
+            if (lane < t.drep) *p = 0;
             unsigned int tot = v % ERR_UNIT, er = v / ERR_UNIT;
 #pragma unroll
             for (int o = 16; o; o >>= 1) {
@@ -255,7 +259,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
     const ThreadMap m = make_thread_map(g, t.sj);
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
-    const uint32_t din_base = pin(smem_addr(smem_raw + t.din_off) + lane * 4);
+    const uint32_t din_base = pin(smem_addr(smem_raw + t.din_off) + (lane & (t.drep - 1)) * 4);
     uint32_t afwd[4];  // shared address of row 0 of the read-1 cycle table at this thread's cycles
 #pragma unroll
     for (int b = 0; b < 4; ++b) afwd[b] = pin(pos_base + m.cell[b]);

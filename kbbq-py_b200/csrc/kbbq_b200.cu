@@ -55,20 +55,25 @@ static int current_device_info(int *device, int *sms, int *max_smem) {
 
 static bool misaligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) != 0; }
 
-// Staging ring that fits the CTA's shared memory behind the tables: as many groups per thread-group
-// and stage as still leave a ring of MIN_DEEP stages (barrier traffic is paid per stage), then the
-// deepest ring; at least 2 stages.  A stage never holds more than 32 groups (one per producer lane).
-static bool pick_stages(const Geom &g, int narr, int max_smem, size_t table_bytes, int *stages, int *kps) {
-    const int MIN_DEEP = 3;
-    const char *e = getenv("KBBQ_KPS");  // tuning / test hook
+// Shared-memory plan of a kernel: table geometry + staging ring.  Barrier traffic is paid per stage,
+// so with 32 dinuc replicas (conflict free; 16 if that does not fit) take as many groups per
+// thread-group and stage (kps <= 4, at most 32 groups per stage: one per producer lane) as still
+// leave a ring of 3 stages; failing that, whatever ring of at least 2 stages fits.
+// Measured on 10M x 150 bp: build kps 2 / drep 32 1.24 ms vs kps 4 / drep 16 1.30 ms.
+static bool plan_smem(const Geom &g, int narr, int max_smem, TableCfg *tc, StageLayout *sl) {
+    const char *e = getenv("KBBQ_KPS");  // tuning / test hooks
     const int kmax = e ? std::max(1, std::min(4, atoi(e))) : 4;
-    for (int want = MIN_DEEP; want >= 2; --want) {
-        for (int k = kmax; k >= 1; --k) {
-            if (g.ng * k > 32) continue;
-            for (int s = MAX_STAGES; s >= want; --s) {
-                if (make_stage_layout(g, narr, s, k, table_bytes).total <= max_smem) {
-                    *stages = s; *kps = k;
-                    return true;
+    const char *d = getenv("KBBQ_DREP");
+    const int dmax = d ? atoi(d) : 32;
+    for (int want = 3; want >= 2; --want) {
+        for (int drep = 32; drep >= 16; drep >>= 1) {
+            if (drep > dmax) continue;
+            for (int k = kmax; k >= 1; --k) {
+                if (g.ng * k > 32) continue;
+                if (!make_table_cfg(g, k, drep, tc)) return false;
+                for (int s = MAX_STAGES; s >= want; --s) {
+                    *sl = make_stage_layout(g, narr, s, k, tc->table_bytes);
+                    if (sl->total <= max_smem) return true;
                 }
             }
         }
@@ -159,9 +164,8 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
                    (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull &&
                    !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(corr, 16);
     TableCfg tc;
-    int stages = 0, kps = 1;
-    smem_ok = smem_ok && make_table_cfg(g, 1, &tc) && pick_stages(g, 3, max_smem, tc.table_bytes, &stages, &kps) &&
-              make_table_cfg(g, kps, &tc);
+    StageLayout sl;
+    smem_ok = smem_ok && plan_smem(g, 3, max_smem, &tc, &sl);
     if (!smem_ok) {
         if (path == 1) return KBBQ_E_ARG;
         BuildGenericArgs a = {seq, qual, corr, rg, second, N, L, R, minscore,
@@ -173,7 +177,6 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
     }
     Workspace w = carve_workspace(workspace, N, L, R);
     if (!workspace || workspace_bytes < w.bytes) return KBBQ_E_WORKSPACE;
-    const StageLayout sl = make_stage_layout(g, 3, stages, kps, tc.table_bytes);
     rc = run_prepare(rg, second, N, g.G, R, w, status, sms, sl.ngs, g.gbytes, sl.slot, st);
     if (rc) return rc;
 
@@ -272,8 +275,8 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
                    (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull &&
                    !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(out_qual, 4);
     TableCfg tc;
-    int stages = 0, kps = 1;
-    smem_ok = smem_ok && make_table_cfg(g, 1, &tc) && pick_stages(g, 2, max_smem, apply_table_bytes(tc), &stages, &kps);
+    StageLayout sl;
+    smem_ok = smem_ok && plan_smem(g, 2, max_smem, &tc, &sl);
     if (!smem_ok) {
         if (path == 1) return KBBQ_E_ARG;
         ApplyGenericArgs a = {seq, qual, rg, second, out_qual, N, L, R, minscore, nq, w.fold_cyc, w.fold_din, status};
@@ -281,7 +284,6 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
         KBBQ_LAUNCHED();
         return KBBQ_OK;
     }
-    const StageLayout sl = make_stage_layout(g, 2, stages, kps, apply_table_bytes(tc));
     rc = run_prepare(rg, second, N, g.G, R, w, status, sms, sl.ngs, g.gbytes, sl.slot, st);
     if (rc) return rc;
     ApplyArgs a;
