@@ -120,12 +120,17 @@ int kbbq_apply(const uint8_t *seq_dev, const uint8_t *qual_dev, const uint16_t *
  * recalibrate.recalibrate_fastq (kbbq/recalibrate.py:123-156) does between parsing and printing.
  * Reads are streamed in chunks over two CUDA streams; tables_host (optional, may be NULL) receives
  * [pos_errs | pos_total | din_errs | din_total]; deltas_host (optional) receives
- * [meanq R | rgdq R | qdq R*43 | posdq R*43*2L | dindq R*43*17].  Synchronous.
+ * [meanq R | rgdq R | qdq R*43 | posdq R*43*2L | dindq R*43*17].  Synchronous; calls on one device
+ * are serialised.
  */
 int kbbq_recalibrate_host(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr,
                           const uint16_t *rg, const uint8_t *second, int64_t N, int L, int R,
                           int minscore, uint8_t *out_qual, int64_t *tables_host,
                           int64_t *deltas_host, int *status_out, int device);
+
+/* kbbq_recalibrate_host keeps its device buffers and streams between calls (allocating several GB
+ * per call costs far more than the kernels); this frees them for `device`. */
+int kbbq_host_release(int device);
 
 /* Host-buffer variants of the two halves (drop-in backing of fastq_to_covariate_arrays and of
  * the apply loop when the caller keeps the tables). Synchronous. */

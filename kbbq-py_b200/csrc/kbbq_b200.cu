@@ -321,20 +321,51 @@ struct DevBuf {
     template <class T> T *as() { return (T *)p; }
 };
 
-struct Streams {
+// Device memory and streams kbbq_recalibrate_host keeps between calls (per device): allocating
+// and freeing several GB per call costs from tens of milliseconds to a second (driver page
+// scrubbing), far more than the kernels.  Grown on demand, released by kbbq_host_release().
+struct HostArena {
+    std::mutex mu;
+    void *base = nullptr;
+    size_t cap = 0;
     cudaStream_t copy = nullptr, comp = nullptr;
-    std::vector<cudaEvent_t> ev;
-    ~Streams() {
-        for (auto e : ev) cudaEventDestroy(e);
-        if (copy) cudaStreamDestroy(copy);
-        if (comp) cudaStreamDestroy(comp);
-    }
-    int init() {
-        KBBQ_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
-        KBBQ_CUDA(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return KBBQ_OK;
+        if (base) { KBBQ_CUDA(cudaFree(base)); base = nullptr; cap = 0; }
+        KBBQ_CUDA(cudaMalloc(&base, bytes));
+        cap = bytes;
         return KBBQ_OK;
     }
-    int event(cudaEvent_t *e) {
+    int streams() {
+        if (!copy) KBBQ_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+        if (!comp) KBBQ_CUDA(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
+        return KBBQ_OK;
+    }
+    void release() {
+        if (base) cudaFree(base);
+        if (copy) cudaStreamDestroy(copy);
+        if (comp) cudaStreamDestroy(comp);
+        base = nullptr; cap = 0; copy = comp = nullptr;
+    }
+};
+HostArena g_arena[64];
+
+// bump allocator over the arena (first pass with base == nullptr measures)
+struct Carver {
+    char *base;
+    size_t off = 0;
+    explicit Carver(void *b) : base((char *)b) {}
+    template <class T> T *take(size_t n_elems) {
+        T *p = base ? (T *)(base + off) : nullptr;
+        off = (off + n_elems * sizeof(T) + 255) / 256 * 256;
+        return p;
+    }
+};
+
+struct Events {
+    std::vector<cudaEvent_t> ev;
+    ~Events() { for (auto e : ev) cudaEventDestroy(e); }
+    int make(cudaEvent_t *e) {
         KBBQ_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
         ev.push_back(*e);
         return KBBQ_OK;
@@ -369,30 +400,37 @@ ModelPtrs carve_model(int64_t *base, int L, int R) {
 
 extern "C" {
 
+int kbbq_host_release(int device) {
+    if (device < 0 || device >= 64) return KBBQ_E_ARG;
+    HostArena &A = g_arena[device];
+    std::lock_guard<std::mutex> lock(A.mu);
+    if (A.base || A.copy || A.comp) {
+        KBBQ_CUDA(cudaSetDevice(device));
+        A.release();
+    }
+    return KBBQ_OK;
+}
+
 int kbbq_recalibrate_host(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,
                           const uint8_t *second, int64_t N, int L, int R, int minscore, uint8_t *out_qual,
                           int64_t *tables_host, int64_t *deltas_host, int *status_out, int device) {
-    if (N < 0 || L < 1 || R < 1 || R > 65535) return KBBQ_E_ARG;
+    if (N < 0 || L < 1 || R < 1 || R > 65535 || device < 0 || device >= 64) return KBBQ_E_ARG;
     if (N > 0 && (!seq || !qual || !corr || !out_qual)) return KBBQ_E_ARG;
     KBBQ_CUDA(cudaSetDevice(device));
-    Streams S;
-    KBBQ_TRY(S.init());
+    HostArena &A = g_arena[device];
+    std::lock_guard<std::mutex> lock(A.mu);
+    KBBQ_TRY(A.streams());
+    cudaStream_t s_copy = A.copy, s_comp = A.comp;
+    Events E;
 
     const size_t npos = (size_t)R * NQ * 2 * L, ndin = (size_t)R * NQ * 16;
     const size_t ntab = 2 * npos + 2 * ndin;
-    DevBuf d_tab, d_model, d_status;
-    KBBQ_TRY(d_tab.alloc(ntab * 8));
-    ModelPtrs mp = carve_model(nullptr, L, R);
-    KBBQ_TRY(d_model.alloc(mp.elems * 8));
-    mp = carve_model(d_model.as<int64_t>(), L, R);
-    KBBQ_TRY(d_status.alloc(sizeof(int)));
-    KBBQ_CUDA(cudaMemsetAsync(d_tab.p, 0, ntab * 8, S.comp));
-    KBBQ_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(int), S.comp));
-    int64_t *pe = d_tab.as<int64_t>(), *pt = pe + npos, *de = pt + npos, *dt = de + ndin;
+    const size_t nmodel = carve_model(nullptr, L, R).elems;
 
     // chunking: whole batch resident when it fits, otherwise two passes through rotating buffers
     size_t free_b = 0, total_b = 0;
     KBBQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    free_b += A.cap;  // what the arena already holds is ours to use
     const size_t per_read_resident = (size_t)4 * L + 3;
     bool resident = (double)N * per_read_resident < 0.8 * (double)free_b;
     int64_t chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / L);   // ~256 MiB per array per chunk
@@ -404,26 +442,40 @@ int kbbq_recalibrate_host(const uint8_t *seq, const uint8_t *qual, const uint8_t
     const int64_t nchunks = N ? (N + chunk - 1) / chunk : 0;
     const int nbuf = resident ? 1 : 2;
     const int64_t buf_reads = resident ? N : chunk;
-
-    DevBuf d_seq[2], d_qual[2], d_corr[2], d_out[2], d_rg[2], d_sec[2], d_ws;
-    for (int b = 0; b < nbuf; ++b) {
-        KBBQ_TRY(d_seq[b].alloc((size_t)buf_reads * L));
-        KBBQ_TRY(d_qual[b].alloc((size_t)buf_reads * L));
-        KBBQ_TRY(d_corr[b].alloc((size_t)(resident ? chunk : buf_reads) * L));
-        KBBQ_TRY(d_out[b].alloc((size_t)(resident ? chunk : buf_reads) * L));
-        if (rg) KBBQ_TRY(d_rg[b].alloc((size_t)buf_reads * 2));
-        if (second) KBBQ_TRY(d_sec[b].alloc((size_t)buf_reads));
-    }
-    if (resident) {  // corrected reads and outputs still rotate through two chunk buffers
-        KBBQ_TRY(d_corr[1].alloc((size_t)chunk * L));
-        KBBQ_TRY(d_out[1].alloc((size_t)chunk * L));
-    }
     size_t ws_bytes = 0;
     KBBQ_TRY(kbbq_workspace_bytes(chunk, L, R, &ws_bytes));
-    KBBQ_TRY(d_ws.alloc(ws_bytes));
+
+    // carve everything out of the arena: measure, grow if needed, carve for real
+    int64_t *d_tab = nullptr, *d_model = nullptr;
+    int *d_status = nullptr;
+    uint8_t *d_seq[2] = {}, *d_qual[2] = {}, *d_corr[2] = {}, *d_out[2] = {}, *d_sec[2] = {};
+    uint16_t *d_rg[2] = {};
+    void *d_ws = nullptr;
+    for (int pass = 0; pass < 2; ++pass) {
+        Carver c(pass ? A.base : nullptr);
+        d_tab = c.take<int64_t>(ntab);
+        d_model = c.take<int64_t>(nmodel);
+        d_status = c.take<int>(64);
+        for (int b = 0; b < nbuf; ++b) {
+            d_seq[b] = c.take<uint8_t>((size_t)buf_reads * L + 16);
+            d_qual[b] = c.take<uint8_t>((size_t)buf_reads * L + 16);
+            d_rg[b] = rg ? c.take<uint16_t>((size_t)buf_reads + 8) : nullptr;
+            d_sec[b] = second ? c.take<uint8_t>((size_t)buf_reads + 16) : nullptr;
+        }
+        for (int b = 0; b < 2; ++b) {  // corrected reads and outputs always rotate through two chunk buffers
+            d_corr[b] = c.take<uint8_t>((size_t)chunk * L + 16);
+            d_out[b] = c.take<uint8_t>((size_t)chunk * L + 16);
+        }
+        d_ws = c.take<uint8_t>(ws_bytes);
+        if (!pass) KBBQ_TRY(A.ensure(c.off));
+    }
+    ModelPtrs mp = carve_model(d_model, L, R);
+    KBBQ_CUDA(cudaMemsetAsync(d_tab, 0, ntab * 8, s_comp));
+    KBBQ_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int), s_comp));
+    int64_t *pe = d_tab, *pt = pe + npos, *de = pt + npos, *dt = de + ndin;
 
     std::vector<cudaEvent_t> copied(nchunks), consumed(nchunks);
-    for (int64_t k = 0; k < nchunks; ++k) { KBBQ_TRY(S.event(&copied[k])); KBBQ_TRY(S.event(&consumed[k])); }
+    for (int64_t k = 0; k < nchunks; ++k) { KBBQ_TRY(E.make(&copied[k])); KBBQ_TRY(E.make(&consumed[k])); }
 
     auto rd = [&](int64_t k) { return std::min(chunk, N - k * chunk); };
     // ---- pass 1: H2D + build ----
@@ -431,65 +483,64 @@ int kbbq_recalibrate_host(const uint8_t *seq, const uint8_t *qual, const uint8_t
         const int b = resident ? 0 : (int)(k & 1), cb = (int)(k & 1);
         const int64_t r0 = k * chunk, n = rd(k);
         const size_t doff = resident ? (size_t)r0 * L : 0, roff = resident ? (size_t)r0 : 0;
-        if (k >= 2) KBBQ_CUDA(cudaStreamWaitEvent(S.copy, consumed[k - 2], 0));
-        KBBQ_CUDA(cudaMemcpyAsync(d_seq[b].as<uint8_t>() + doff, seq + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, S.copy));
-        KBBQ_CUDA(cudaMemcpyAsync(d_qual[b].as<uint8_t>() + doff, qual + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, S.copy));
-        KBBQ_CUDA(cudaMemcpyAsync(d_corr[cb].as<uint8_t>(), corr + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, S.copy));
-        if (rg) KBBQ_CUDA(cudaMemcpyAsync(d_rg[b].as<uint16_t>() + roff, rg + r0, (size_t)n * 2, cudaMemcpyHostToDevice, S.copy));
-        if (second) KBBQ_CUDA(cudaMemcpyAsync(d_sec[b].as<uint8_t>() + roff, second + r0, (size_t)n, cudaMemcpyHostToDevice, S.copy));
-        KBBQ_CUDA(cudaEventRecord(copied[k], S.copy));
-        KBBQ_CUDA(cudaStreamWaitEvent(S.comp, copied[k], 0));
-        KBBQ_TRY(kbbq_build(d_seq[b].as<uint8_t>() + doff, d_qual[b].as<uint8_t>() + doff, d_corr[cb].as<uint8_t>(),
-                            rg ? d_rg[b].as<uint16_t>() + roff : nullptr, second ? d_sec[b].as<uint8_t>() + roff : nullptr,
-                            n, L, R, minscore, pe, pt, de, dt, d_ws.p, ws_bytes, d_status.as<int>(), 0, S.comp));
-        KBBQ_CUDA(cudaEventRecord(consumed[k], S.comp));
+        if (k >= 2) KBBQ_CUDA(cudaStreamWaitEvent(s_copy, consumed[k - 2], 0));
+        KBBQ_CUDA(cudaMemcpyAsync(d_seq[b] + doff, seq + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, s_copy));
+        KBBQ_CUDA(cudaMemcpyAsync(d_qual[b] + doff, qual + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, s_copy));
+        KBBQ_CUDA(cudaMemcpyAsync(d_corr[cb], corr + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, s_copy));
+        if (rg) KBBQ_CUDA(cudaMemcpyAsync(d_rg[b] + roff, rg + r0, (size_t)n * 2, cudaMemcpyHostToDevice, s_copy));
+        if (second) KBBQ_CUDA(cudaMemcpyAsync(d_sec[b] + roff, second + r0, (size_t)n, cudaMemcpyHostToDevice, s_copy));
+        KBBQ_CUDA(cudaEventRecord(copied[k], s_copy));
+        KBBQ_CUDA(cudaStreamWaitEvent(s_comp, copied[k], 0));
+        KBBQ_TRY(kbbq_build(d_seq[b] + doff, d_qual[b] + doff, d_corr[cb], rg ? d_rg[b] + roff : nullptr,
+                            second ? d_sec[b] + roff : nullptr, n, L, R, minscore, pe, pt, de, dt, d_ws, ws_bytes,
+                            d_status, 0, s_comp));
+        KBBQ_CUDA(cudaEventRecord(consumed[k], s_comp));
     }
     // ---- model ----
-    KBBQ_TRY(kbbq_marginals(pe, pt, L, R, mp.q_errs, mp.q_total, mp.rg_errs, mp.rg_total, mp.meanq, S.comp));
+    KBBQ_TRY(kbbq_marginals(pe, pt, L, R, mp.q_errs, mp.q_total, mp.rg_errs, mp.rg_total, mp.meanq, s_comp));
     KBBQ_TRY(kbbq_get_delta_qs(mp.meanq, mp.rg_errs, mp.rg_total, mp.q_errs, mp.q_total, pe, pt, de, dt, R, NQ,
-                               2 * L, 16, mp.rgdq, mp.qdq, mp.posdq, mp.dindq, S.comp));
-    if (tables_host) KBBQ_CUDA(cudaMemcpyAsync(tables_host, d_tab.p, ntab * 8, cudaMemcpyDeviceToHost, S.comp));
+                               2 * L, 16, mp.rgdq, mp.qdq, mp.posdq, mp.dindq, s_comp));
+    if (tables_host) KBBQ_CUDA(cudaMemcpyAsync(tables_host, d_tab, ntab * 8, cudaMemcpyDeviceToHost, s_comp));
     if (deltas_host)
         KBBQ_CUDA(cudaMemcpyAsync(deltas_host, mp.meanq, ((size_t)2 * R + (size_t)R * NQ * (1 + 2 * L + 17)) * 8,
-                                  cudaMemcpyDeviceToHost, S.comp));
+                                  cudaMemcpyDeviceToHost, s_comp));
     // ---- pass 2: (H2D) + apply + D2H ----
     std::vector<cudaEvent_t> applied(nchunks), drained(nchunks), copied2(nchunks);
     for (int64_t k = 0; k < nchunks; ++k) {
-        KBBQ_TRY(S.event(&applied[k])); KBBQ_TRY(S.event(&drained[k])); KBBQ_TRY(S.event(&copied2[k]));
+        KBBQ_TRY(E.make(&applied[k])); KBBQ_TRY(E.make(&drained[k])); KBBQ_TRY(E.make(&copied2[k]));
     }
     cudaEvent_t model_done;
-    KBBQ_TRY(S.event(&model_done));
-    KBBQ_CUDA(cudaEventRecord(model_done, S.comp));
+    KBBQ_TRY(E.make(&model_done));
+    KBBQ_CUDA(cudaEventRecord(model_done, s_comp));
     for (int64_t k = 0; k < nchunks; ++k) {
         const int b = resident ? 0 : (int)(k & 1), ob = (int)(k & 1);
         const int64_t r0 = k * chunk, n = rd(k);
         const size_t doff = resident ? (size_t)r0 * L : 0, roff = resident ? (size_t)r0 : 0;
         if (!resident) {
             // the build pass finished with these buffers long ago; only the previous apply pass matters
-            if (k >= 2) KBBQ_CUDA(cudaStreamWaitEvent(S.copy, applied[k - 2], 0));
-            else KBBQ_CUDA(cudaStreamWaitEvent(S.copy, model_done, 0));
-            KBBQ_CUDA(cudaMemcpyAsync(d_seq[b].as<uint8_t>(), seq + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, S.copy));
-            KBBQ_CUDA(cudaMemcpyAsync(d_qual[b].as<uint8_t>(), qual + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, S.copy));
-            if (rg) KBBQ_CUDA(cudaMemcpyAsync(d_rg[b].as<uint16_t>(), rg + r0, (size_t)n * 2, cudaMemcpyHostToDevice, S.copy));
-            if (second) KBBQ_CUDA(cudaMemcpyAsync(d_sec[b].as<uint8_t>(), second + r0, (size_t)n, cudaMemcpyHostToDevice, S.copy));
-            KBBQ_CUDA(cudaEventRecord(copied2[k], S.copy));
-            KBBQ_CUDA(cudaStreamWaitEvent(S.comp, copied2[k], 0));
+            if (k >= 2) KBBQ_CUDA(cudaStreamWaitEvent(s_copy, applied[k - 2], 0));
+            else KBBQ_CUDA(cudaStreamWaitEvent(s_copy, model_done, 0));
+            KBBQ_CUDA(cudaMemcpyAsync(d_seq[b], seq + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, s_copy));
+            KBBQ_CUDA(cudaMemcpyAsync(d_qual[b], qual + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, s_copy));
+            if (rg) KBBQ_CUDA(cudaMemcpyAsync(d_rg[b], rg + r0, (size_t)n * 2, cudaMemcpyHostToDevice, s_copy));
+            if (second) KBBQ_CUDA(cudaMemcpyAsync(d_sec[b], second + r0, (size_t)n, cudaMemcpyHostToDevice, s_copy));
+            KBBQ_CUDA(cudaEventRecord(copied2[k], s_copy));
+            KBBQ_CUDA(cudaStreamWaitEvent(s_comp, copied2[k], 0));
         }
-        if (k >= 2) KBBQ_CUDA(cudaStreamWaitEvent(S.comp, drained[k - 2], 0));
-        KBBQ_TRY(kbbq_apply(d_seq[b].as<uint8_t>() + doff, d_qual[b].as<uint8_t>() + doff,
-                            rg ? d_rg[b].as<uint16_t>() + roff : nullptr, second ? d_sec[b].as<uint8_t>() + roff : nullptr,
-                            n, L, R, minscore, mp.meanq, mp.rgdq, mp.qdq, mp.posdq, mp.dindq, NQ, 17,
-                            d_out[ob].as<uint8_t>(), d_ws.p, ws_bytes, d_status.as<int>(), 0, S.comp));
-        KBBQ_CUDA(cudaEventRecord(applied[k], S.comp));
+        if (k >= 2) KBBQ_CUDA(cudaStreamWaitEvent(s_comp, drained[k - 2], 0));
+        KBBQ_TRY(kbbq_apply(d_seq[b] + doff, d_qual[b] + doff, rg ? d_rg[b] + roff : nullptr,
+                            second ? d_sec[b] + roff : nullptr, n, L, R, minscore, mp.meanq, mp.rgdq, mp.qdq, mp.posdq,
+                            mp.dindq, NQ, 17, d_out[ob], d_ws, ws_bytes, d_status, 0, s_comp));
+        KBBQ_CUDA(cudaEventRecord(applied[k], s_comp));
         // D2H on the copy stream so that it overlaps the next chunk's apply (and H2D when streaming)
-        KBBQ_CUDA(cudaStreamWaitEvent(S.copy, applied[k], 0));
-        KBBQ_CUDA(cudaMemcpyAsync(out_qual + (size_t)r0 * L, d_out[ob].as<uint8_t>(), (size_t)n * L, cudaMemcpyDeviceToHost, S.copy));
-        KBBQ_CUDA(cudaEventRecord(drained[k], S.copy));
+        KBBQ_CUDA(cudaStreamWaitEvent(s_copy, applied[k], 0));
+        KBBQ_CUDA(cudaMemcpyAsync(out_qual + (size_t)r0 * L, d_out[ob], (size_t)n * L, cudaMemcpyDeviceToHost, s_copy));
+        KBBQ_CUDA(cudaEventRecord(drained[k], s_copy));
     }
     int st_host = 0;
-    KBBQ_CUDA(cudaStreamSynchronize(S.copy));
-    KBBQ_CUDA(cudaMemcpyAsync(&st_host, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, S.comp));
-    KBBQ_CUDA(cudaStreamSynchronize(S.comp));
+    KBBQ_CUDA(cudaStreamSynchronize(s_copy));
+    KBBQ_CUDA(cudaMemcpyAsync(&st_host, d_status, sizeof(int), cudaMemcpyDeviceToHost, s_comp));
+    KBBQ_CUDA(cudaStreamSynchronize(s_comp));
     if (status_out) *status_out = st_host;
     return st_host ? KBBQ_E_DATA : KBBQ_OK;
 }

@@ -33,6 +33,7 @@ SIGNATURES = {
     "kbbq_get_delta_qs": (_i, [_vp] * 9 + [_i, _i, _i, _i] + [_vp] * 4 + [_vp]),
     "kbbq_apply": (_i, [_vp] * 4 + [_i64, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, _vp, _sz, _vp, _i, _vp]),
     "kbbq_recalibrate_host": (_i, [_vp] * 5 + [_i64, _i, _i, _i] + [_vp] * 3 + [C.POINTER(_i), _i]),
+    "kbbq_host_release": (_i, [_i]),
     "kbbq_build_host": (_i, [_vp] * 5 + [_i64, _i, _i, _i] + [_vp] * 4 + [C.POINTER(_i), _i]),
     "kbbq_apply_host": (_i, [_vp] * 4 + [_i64, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, C.POINTER(_i), _i]),
     "kbbq_get_delta_qs_host": (_i, [_vp] * 9 + [_i, _i, _i, _i] + [_vp] * 4 + [_i]),
