@@ -73,9 +73,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
     const uint32_t din_base = pin(smem_addr(smem_raw + t.din_off) + (lane & (t.drep - 1)) * 4);
-    uint32_t afwd[4];
+    uint32_t aeff[4];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) afwd[b] = pin(pos_base + m.cell[b]);
+    for (int b = 0; b < 4; ++b) aeff[b] = pos_base + m.cell[b];
+    uint32_t cur_flag = 1;
     const uint32_t selv = pin(m.selv), seln = pin(m.seln);
     const uint32_t rowsel = m.row >= 0 ? (uint32_t)m.row : 0u;
     const uint32_t lanemask = pin(m.row >= 0 ? 0xFFu : 0u);
@@ -93,7 +94,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
     const uint32_t mp = t.mp, md = t.md, revoff = t.revoff, addq = t.addq, gbytes = g.gbytes;
     const uint32_t addnq = (uint32_t)(128 - a.nq) * ONE4;  // q + this has bit 7 set iff q >= nq (q < 128)
     uint32_t stage = 0, phase = 0;
-    uint32_t qbad = 0;
+    uint32_t qgood = 0xFFFFFFFFu;
 
     for (int rg = 0; rg < a.R; ++rg) {
         uint32_t s_lo = a.seg[rg], s_hi = a.seg[rg + 1];
@@ -124,25 +125,32 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
 
         for (uint32_t first = s_lo; first < s_hi; first += sl.ngs) {
             mbar_wait(bar0 + stage * 8, phase);
-            const uint32_t sdata = data0 + stage * stage_bytes, shdr = hdr0 + stage * hdr_stride;
+            const uint32_t sdata = pin(data0 + stage * stage_bytes), shdr = pin(hdr0 + stage * hdr_stride);
 #pragma unroll
             for (int k = 0; k < KPS; ++k) {
                 uint32_t soff, hgrp, flo, fhi;
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                              : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
                              : "r"(shdr + k * krec));
+                // cycle-table addresses are kept for the last row flag seen (see build.cuh)
                 const uint32_t flag = prmt(flo, fhi, rowsel) & lanemask;
-                if (!flag) continue;
+                if (flag != cur_flag) {
+                    if (!flag) continue;
+                    const uint32_t delta = ((flag >> 1) - (cur_flag >> 1)) * revoff;
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) aeff[b] += delta;
+                    cur_flag = flag;
+                }
                 const uint32_t wa = sdata + soff;
                 uint32_t sw, qw, pb;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sw) : "r"(wa));
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qw) : "r"(wa + abytes));
                 asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pb) : "r"(wa - 1));
 
-                const uint32_t u = qw + addnq;              // bit 7 <=> q >= nq: IndexError in the reference
+                const uint32_t nu = ~(qw + addnq);          // bit 7 clear <=> q >= nq: IndexError in the reference
                 const uint32_t w5 = qw + addq;
-                qbad |= u | qw;
-                const uint32_t vraw = w5 & ~u & ~qw;
+                qgood &= nu & ~qw;
+                const uint32_t vraw = w5 & nu & ~qw;
                 const uint32_t vm8 = prmt(vraw, 0u, selv);  // 0xFF for owned bytes with minscore - 1 <= q < nq
                 const uint32_t qrow4 = w5 & vm8 & 0x3F3F3F3Fu;
                 const uint32_t q4p = qrow4 * mp;
@@ -150,12 +158,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
                 const uint32_t d4 = (pw & 0x06060606u) * 4u + (sw & 0x06060606u);
                 const uint32_t nm8 = prmt((sw | pw) * 16u, 0xFFFFFFFFu, seln);
                 const uint32_t q4d = (qrow4 & ~nm8) * md;
-                const uint32_t rev = (flag >> 1) * revoff;
 
                 uint32_t v[4];
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    const uint32_t pa = __dp4a(q4p, t.ohp[b], afwd[b] + rev);
+                    const uint32_t pa = __dp4a(q4p, t.ohp[b], aeff[b]);
                     uint32_t da = __dp4a(d4, t.ohd[b], din_base);
                     da = __dp4a(q4d, t.ohq[b], da);
                     da = __dp4a(q4d, t.ohq[b], da);
@@ -187,7 +194,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
             if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
         }
     }
-    if (qbad & rowmask & H4) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
+    if (~qgood & rowmask & H4) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
 }
 
 // Generic path (any L): one thread per base, folded tables gathered from global memory (L1/L2).

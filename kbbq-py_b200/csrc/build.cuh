@@ -150,6 +150,7 @@ __device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, int sj) {
 #pragma unroll
     for (int k = 0; k < MAX_G; ++k)
         if (k < g.G && t >= g.wstart[k] && t < g.wstart[k + 1]) { m.row = k; w = t - g.wstart[k]; }
+    if (m.grp >= g.ng) { m.grp = 0; m.row = -1; }  // padding lanes of the last warp
     m.rowmask = 0; m.toff = 0; m.selv = 0x4444u; m.seln = 0x4444u;
 #pragma unroll
     for (int b = 0; b < 4; ++b) { m.cell[b] = 0; m.cyc[b] = -1; }
@@ -260,9 +261,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
     const uint32_t din_base = pin(smem_addr(smem_raw + t.din_off) + (lane & (t.drep - 1)) * 4);
-    uint32_t afwd[4];  // shared address of row 0 of the read-1 cycle table at this thread's cycles
+    uint32_t aeff[4];  // shared address of row 0 of the read-1 (cur_flag 1) or read-2 (3) cycle table at this thread's cycles
 #pragma unroll
-    for (int b = 0; b < 4; ++b) afwd[b] = pin(pos_base + m.cell[b]);
+    for (int b = 0; b < 4; ++b) aeff[b] = pos_base + m.cell[b];
+    uint32_t cur_flag = 1;
     const uint32_t selv = pin(m.selv), seln = pin(m.seln);
     const uint32_t rowsel = m.row >= 0 ? (uint32_t)m.row : 0u;  // prmt selector: flag byte of this thread's row
     const uint32_t lanemask = pin(m.row >= 0 ? 0xFFu : 0u);     // padding lanes never see a live row
@@ -271,8 +273,9 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
     const uint32_t hdr0 = smem_u32(smem_raw + sl.hdr_off) + m.grp * 16;
     const uint32_t stage_bytes = sl.narr * sl.abytes, abytes = sl.abytes, hdr_stride = sl.ngs * 16, krec = g.ng * 16;
     const uint32_t mp = t.mp, md = t.md, revoff = t.revoff, addq = t.addq;
+    const uint32_t one = pin(1u), lut_acgt = pin(0x47544341u);  // 'A' 'C' 'T' 'G' by 2-bit code
     uint32_t stage = 0, phase = 0;
-    uint32_t qbad = 0, bbad = 0;
+    uint32_t qgood = 0xFFFFFFFFu, bbad = 0;
 
     for (int rg = 0; rg < a.R; ++rg) {
         uint32_t s_lo = a.seg[rg], s_hi = a.seg[rg + 1];
@@ -293,7 +296,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
             since_pos += t.fold_din;
             for (; first < chunk_end; first += sl.ngs) {
                 mbar_wait(bar0 + stage * 8, phase);
-                const uint32_t sdata = data0 + stage * stage_bytes, shdr = hdr0 + stage * hdr_stride;
+                const uint32_t sdata = pin(data0 + stage * stage_bytes), shdr = pin(hdr0 + stage * hdr_stride);
 #pragma unroll
                 for (int k = 0; k < KPS; ++k) {
                     // this thread-group's k-th record of the stage
@@ -301,9 +304,17 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
                     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                                  : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
                                  : "r"(shdr + k * krec));
-                    // flag byte of this thread's row: 0 = not in this segment (or a padding lane), 1 = read 1, 3 = read 2
+                    // flag byte of this thread's row: 0 = not in this segment (or a padding lane), 1 = read 1, 3 = read 2.
+                    // A row usually keeps its flag from group to group (interleaved pairs), so the cycle-table
+                    // addresses are kept ready for the last flag seen and only re-based when it changes.
                     const uint32_t flag = prmt(flo, fhi, rowsel) & lanemask;
-                    if (!flag) continue;
+                    if (flag != cur_flag) {
+                        if (!flag) continue;
+                        const uint32_t delta = ((flag >> 1) - (cur_flag >> 1)) * revoff;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) aeff[b] += delta;
+                        cur_flag = flag;
+                    }
                     const uint32_t wa = sdata + soff;
                     uint32_t sw, qw, cw, pb;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sw) : "r"(wa));
@@ -312,10 +323,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
                     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pb) : "r"(wa - 1));
 
                     // ---- quality -> row index, byte-parallel ----
-                    const uint32_t u = qw + 0x55555555u;        // bit 7 <=> q >= 43 (for q < 128)
+                    const uint32_t nu = ~(qw + 0x55555555u);    // bit 7 clear <=> q >= 43 (for q < 128)
                     const uint32_t w5 = qw + addq;              // bit 7 <=> q >= minscore - 1, low bits q - (minscore - 1)
-                    qbad |= u | qw;
-                    const uint32_t vraw = w5 & ~u & ~qw;        // bit 7 <=> minscore - 1 <= q <= 42
+                    qgood &= nu & ~qw;                          // bit 7 stays set while every quality is <= 42
+                    const uint32_t vraw = w5 & nu & ~qw;        // bit 7 <=> minscore - 1 <= q <= 42
                     const uint32_t vm8 = prmt(vraw, 0u, selv);  // 0xFF for owned bytes in range
                     const uint32_t qrow4 = w5 & vm8 & 0x3F3F3F3Fu;  // 0 = trash row
                     const uint32_t q4p = qrow4 * mp;
@@ -335,15 +346,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
                         const uint32_t code3 = (sw >> 1) & 0x07070707u;
                         const uint32_t y = code3 | (code3 >> 4);
                         const uint32_t sel = __byte_perm(y, 0, 0x4420);
-                        const uint32_t recon = __byte_perm(0x47544341u /* A C T G */, 0x4E000000u /* . . . N */, sel);
-                        bbad |= (recon ^ sw) & rowmask;
+                        const uint32_t recon = __byte_perm(lut_acgt, 0x4E000000u /* . . . N */, sel);
+                        bbad |= recon ^ sw;  // foreign bytes are masked off at the end (ownership is per byte position)
                     }
 
-                    const uint32_t rev = (flag >> 1) * revoff;  // read-2 rows tally into the second cycle table
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
-                        const uint32_t inc = __dp4a(e8, t.ohe[b], 1u);
-                        const uint32_t pa = __dp4a(q4p, t.ohp[b], afwd[b] + rev);
+                        const uint32_t inc = __dp4a(e8, t.ohe[b], one);
+                        const uint32_t pa = __dp4a(q4p, t.ohp[b], aeff[b]);
                         uint32_t da = __dp4a(d4, t.ohd[b], din_base);
                         da = __dp4a(q4d, t.ohq[b], da);
                         da = __dp4a(q4d, t.ohq[b], da);
@@ -372,8 +382,8 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
         fold_din_replicas(a, smem_raw, rg, nconsumers);
         consumer_sync(nconsumers);
     }
-    if (qbad & rowmask & H4) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
-    if (VALIDATE && bbad) atomicOr(a.status, KBBQ_FLAG_BAD_BASE);
+    if (~qgood & rowmask & H4) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
+    if (VALIDATE && (bbad & rowmask)) atomicOr(a.status, KBBQ_FLAG_BAD_BASE);
 }
 
 // Generic path: one thread per base, global 64-bit reductions.  Used when the shared-memory tables

@@ -1,5 +1,6 @@
 // common.cuh -- shared definitions of the B200 kbbq hot-path kernels (sm_100a only).
 #pragma once
+#include <algorithm>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -49,8 +50,11 @@ extern char g_last_cuda_error[256];
 // so the cycles of its 4 bytes -- and therefore its shared-memory table offsets -- are fixed for
 // the whole kernel, and all its bytes belong to one read (one read group, one `second` flag).
 // Words that straddle two rows are loaded by both neighbours; each uses only its own bytes.
-// A thread-group is LPS = roundup(sum W_k, 32) lanes, i.e. whole warps.  G (<= 8) is chosen to
-// minimise the padding lanes (L = 150: G = 4, 152 of 160 lanes busy).
+// A thread-group is the sum W_k lanes of one group; thread-groups are packed back to back over the
+// CTA's consumer threads (a warp may hold lanes of two thread-groups -- everything a lane needs is a
+// per-thread constant), so only the last warp has padding lanes.  G (<= 8) is the smallest group
+// with the fewest straddling words (L = 150: G = 4, 152 lanes for 150 words; 6 thread-groups = 912
+// lanes in 29 warps).
 //
 // Shared-memory cycle tables are laid out [q - minscore][plane = c2 & 3][c2 >> 2] with a plane
 // stride SJ that makes the row stride a multiple of 32 words: lanes that own consecutive words of
@@ -63,9 +67,9 @@ struct Geom {
     int G;            // reads per group
     int gbytes;       // bytes per group = G * L (multiple of 4)
     int lanes;        // busy lanes per thread-group = sum of words per row
-    int lps;          // lanes per thread-group (multiple of 32)
+    int lps;          // lanes per thread-group (= lanes)
     int ng;           // thread-groups (groups in flight) per CTA
-    int threads;      // ng * lps
+    int threads;      // consumer threads: ng * lps rounded up to whole warps
     int sj;           // plane stride (words)
     int row;          // words per quality row = 4 * sj
     int minscore;     // first tallied quality
@@ -81,15 +85,14 @@ __host__ __device__ inline int gcd_int(int a, int b) {
 inline bool make_geom(int L, int minscore, Geom *g) {
     if (L < 4 || minscore < 0 || minscore >= NQ) return false;
     const int rps = 4 / gcd_int(L, 4);
-    int best_g = 0, best_lanes = 0, best_lps = 1;
+    int best_g = 0, best_lanes = 0;
     for (int G = rps; G <= MAX_G; G += rps) {
         int lanes = 0;
         for (int k = 0; k < G; ++k) lanes += ((k * L) % 4 + L + 3) / 4;
-        const int lps = (lanes + 31) / 32 * 32;
-        if (lps > MAX_THREADS - 32) break;  // one warp is the TMA producer
-        // strictly better lane efficiency wins; ties keep the smaller group
-        if (best_g == 0 || (long long)lanes * best_lps > (long long)best_lanes * lps) {
-            best_g = G; best_lanes = lanes; best_lps = lps;
+        if (lanes > MAX_THREADS - 32) break;  // one warp is the TMA producer
+        // fewer lanes per read wins; ties keep the smaller group
+        if (best_g == 0 || (long long)lanes * best_g < (long long)best_lanes * G) {
+            best_g = G; best_lanes = lanes;
         }
     }
     if (best_g == 0) return false;
@@ -97,9 +100,9 @@ inline bool make_geom(int L, int minscore, Geom *g) {
     g->G = best_g;
     g->gbytes = best_g * L;
     g->lanes = best_lanes;
-    g->lps = best_lps;
-    g->ng = (MAX_THREADS - 32) / g->lps;
-    g->threads = g->ng * g->lps;
+    g->lps = best_lanes;
+    g->ng = std::min(32, (MAX_THREADS - 32) / g->lps);  // a stage holds at most 32 groups (one per producer lane)
+    g->threads = (g->ng * g->lps + 31) / 32 * 32;
     int w = 0;
     for (int k = 0; k <= MAX_G; ++k) {
         g->wstart[k] = w;
