@@ -31,6 +31,7 @@ struct ApplyArgs {
     int R, nq;
     const entry_t *entries;
     const unsigned int *seg;
+    const unsigned int *uni;  // see BuildArgs
     const short *fold_cyc;  // [R][43][2L]
     const short *fold_din;  // [R][43][16]   natural dinuc order (code = (base >> 1) & 3)
     int *status;
@@ -39,36 +40,15 @@ struct ApplyArgs {
 // bytes of shared memory the apply tables take
 __host__ __device__ inline int apply_table_bytes(const TableCfg &t) { return t.table_bytes; }
 
-template <int KPS>
-__global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid_constant__ ApplyArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+// Consumer side of the apply kernel; UNI as in build_consume (build.cuh).
+template <int KPS, bool UNI>
+__device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char *smem_raw, uint32_t lo, uint32_t hi,
+                                              uint32_t uni_flo, uint32_t uni_fhi) {
     const Geom &g = a.g;
     const TableCfg &t = a.t;
     const StageLayout &sl = a.sl;
     const int nconsumers = g.threads;
-
-    const unsigned long long E = a.seg[a.R];
-    const uint32_t lo = (uint32_t)(E * blockIdx.x / gridDim.x), hi = (uint32_t)(E * (blockIdx.x + 1) / gridDim.x);
-
     const uint32_t bar0 = smem_u32(smem_raw + sl.bar_off);
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < sl.stages; ++s) {
-            mbar_init(bar0 + s * 8, 1);
-            mbar_init(bar0 + (sl.stages + s) * 8, nconsumers / 32);
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    if ((int)threadIdx.x >= nconsumers) {  // ---- producer warp ----
-        ProducerArgs p;
-        p.arr[0] = a.seq; p.arr[1] = a.qual; p.arr[2] = nullptr;
-        p.entries = a.entries; p.seg = a.seg; p.R = a.R; p.lo = lo; p.hi = hi;
-        p.gbytes = g.gbytes; p.ng = sl.ngs; p.total_bytes = a.total_bytes;
-        producer_loop(p, sl, smem_raw);
-        return;
-    }
-
     const ThreadMap m = make_thread_map(g, t.sj);
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
@@ -81,6 +61,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
     const uint32_t rowsel = m.row >= 0 ? (uint32_t)m.row : 0u;
     const uint32_t lanemask = pin(m.row >= 0 ? 0xFFu : 0u);
     const uint32_t rowmask = pin(m.rowmask);
+    if (UNI) {
+        const uint32_t f = prmt(uni_flo, uni_fhi, rowsel) & lanemask;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) aeff[b] += (f >> 1) * t.revoff;
+        cur_flag = f;
+    }
+    const bool live = cur_flag != 0;
+    const uint32_t kgrp = g.ng * g.gbytes;
     // how this thread's word is written back: whole (0), one aligned half (1, the usual partial
     // word: reads of even length start 2-byte aligned) or byte by byte (2)
     const bool half_lo = m.rowmask == 0x0000FFFFu, half_hi = m.rowmask == 0xFFFF0000u;
@@ -88,7 +76,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
     const uint32_t wshift = pin(half_hi ? 16u : 0u);
     unsigned long long outp = (unsigned long long)(a.out + m.toff + (half_hi ? 2 : 0));
     asm volatile("" : "+l"(outp));
-    const uint32_t data0 = smem_u32(smem_raw + sl.data_off) + m.toff;
+    const uint32_t data0 = smem_u32(smem_raw + sl.data_off) + m.toff + (UNI ? m.grp * g.gbytes : 0);
     const uint32_t hdr0 = smem_u32(smem_raw + sl.hdr_off) + m.grp * 16;
     const uint32_t stage_bytes = sl.narr * sl.abytes, abytes = sl.abytes, hdr_stride = sl.ngs * 16, krec = g.ng * 16;
     const uint32_t mp = t.mp, md = t.md, revoff = t.revoff, addq = t.addq, gbytes = g.gbytes;
@@ -103,9 +91,12 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
         if (s_lo < lo) s_lo = lo;
         if (s_hi > hi) s_hi = hi;
 
-        // stage this read group's folded tables; row 0 (qualities that stay as they are, invalid dinucs) = 0
+        // stage this read group's folded tables; row 0 = "leave the quality alone": the dinuc table holds 0
+        // there (invalid dinucs of any quality land on it), the cycle tables hold minscore - 1, the only
+        // quality that reaches row 0 with its byte selected
         consumer_sync(nconsumers);
-        for (int i = threadIdx.x; i < apply_table_bytes(t) / 4; i += nconsumers) reinterpret_cast<int *>(smem_raw)[i] = 0;
+        for (int i = threadIdx.x; i < apply_table_bytes(t) / 4; i += nconsumers)
+            reinterpret_cast<int *>(smem_raw)[i] = i * 4 < t.din_off && (i * 4) % t.revoff < t.rs ? g.minscore - 1 : 0;
         consumer_sync(nconsumers);
         const int L = g.L, L2 = 2 * g.L;
         const short *fc = a.fold_cyc + (size_t)rg * NQ * L2;
@@ -125,21 +116,35 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
 
         for (uint32_t first = s_lo; first < s_hi; first += sl.ngs) {
             mbar_wait(bar0 + stage * 8, phase);
-            const uint32_t sdata = pin(data0 + stage * stage_bytes), shdr = pin(hdr0 + stage * hdr_stride);
+            const uint32_t shdr = pin(hdr0 + stage * hdr_stride);
+            uint32_t sdata = data0 + stage * stage_bytes;
+            uint32_t nlive = sl.ngs;
+            if (UNI) {
+                sdata += (uint32_t)((unsigned long long)first * g.gbytes) & 15u;
+                nlive = s_hi - first;
+            }
+            sdata = pin(sdata);
 #pragma unroll
             for (int k = 0; k < KPS; ++k) {
-                uint32_t soff, hgrp, flo, fhi;
-                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                             : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
-                             : "r"(shdr + k * krec));
-                // cycle-table addresses are kept for the last row flag seen (see build.cuh)
-                const uint32_t flag = prmt(flo, fhi, rowsel) & lanemask;
-                if (flag != cur_flag) {
-                    if (!flag) continue;
-                    const uint32_t delta = ((flag >> 1) - (cur_flag >> 1)) * revoff;
+                uint32_t soff, hgrp;
+                if (UNI) {
+                    if (!live || (uint32_t)(m.grp + k * g.ng) >= nlive) continue;
+                    soff = k * kgrp;
+                    hgrp = first + m.grp + k * g.ng;
+                } else {
+                    uint32_t flo, fhi;
+                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                 : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
+                                 : "r"(shdr + k * krec));
+                    // cycle-table addresses are kept for the last row flag seen (see build.cuh)
+                    const uint32_t flag = prmt(flo, fhi, rowsel) & lanemask;
+                    if (flag != cur_flag) {
+                        if (!flag) continue;
+                        const uint32_t delta = ((flag >> 1) - (cur_flag >> 1)) * revoff;
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) aeff[b] += delta;
-                    cur_flag = flag;
+                        for (int b = 0; b < 4; ++b) aeff[b] += delta;
+                        cur_flag = flag;
+                    }
                 }
                 const uint32_t wa = sdata + soff;
                 uint32_t sw, qw, pb;
@@ -171,11 +176,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(y) : "r"(da));
                     v[b] = x + y;
                 }
-                // low byte of every sum; qualities below minscore (row 0 selected nothing) pass through.
-                // q == minscore - 1 also has vm8 set with row 0: its "sum" must be q itself
+                // low byte of every sum; qualities that do not pass vm8 stay as they are.  q == minscore - 1
+                // passes vm8 with row 0, whose cycle table holds minscore - 1 and whose dinuc table holds 0.
                 const uint32_t sum4 = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
-                const uint32_t keep8 = prmt(qrow4 + 0x7F7F7F7Fu, 0u, 0xBA98u);  // 0xFF where the row index is non-zero
-                const uint32_t res = (sum4 & keep8) | (qw & ~keep8);
+                const uint32_t res = (sum4 & vm8) | (qw & ~vm8);
                 // group base + this thread's offset inside the group (64-bit multiply-add, one instruction)
                 const unsigned long long dst = outp + (unsigned long long)hgrp * gbytes;
                 if (wmode == 0) {
@@ -195,6 +199,41 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
         }
     }
     if (~qgood & rowmask & H4) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
+}
+
+
+template <int KPS>
+__global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid_constant__ ApplyArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const Geom &g = a.g;
+    const StageLayout &sl = a.sl;
+    const int nconsumers = g.threads;
+
+    const unsigned long long E = a.seg[a.R];
+    const uint32_t lo = (uint32_t)(E * blockIdx.x / gridDim.x), hi = (uint32_t)(E * (blockIdx.x + 1) / gridDim.x);
+
+    const uint32_t bar0 = smem_u32(smem_raw + sl.bar_off);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < sl.stages; ++s) {
+            mbar_init(bar0 + s * 8, 1);
+            mbar_init(bar0 + (sl.stages + s) * 8, nconsumers / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if ((int)threadIdx.x >= nconsumers) {  // ---- producer warp ----
+        ProducerArgs p;
+        p.arr[0] = a.seq; p.arr[1] = a.qual; p.arr[2] = nullptr;
+        p.entries = a.entries; p.seg = a.seg; p.R = a.R; p.lo = lo; p.hi = hi;
+        p.gbytes = g.gbytes; p.ng = sl.ngs; p.total_bytes = a.total_bytes;
+        producer_loop(p, sl, smem_raw);
+        return;
+    }
+
+    const bool uniform = a.R == 1 && a.uni[0] == 0u;
+    if (uniform) apply_consume<KPS, true>(a, smem_raw, lo, hi, a.uni[1], a.uni[2]);
+    else apply_consume<KPS, false>(a, smem_raw, lo, hi, 0u, 0u);
 }
 
 // Generic path (any L): one thread per base, folded tables gathered from global memory (L1/L2).

@@ -106,6 +106,7 @@ struct BuildArgs {
     int R;
     const entry_t *entries;
     const unsigned int *seg;  // [R + 1]
+    const unsigned int *uni;  // prepare.cuh: {0 = every group has the row flags of group 0, flags 0-3, flags 4-7}
     unsigned long long *pos_errs, *pos_total, *din_errs, *din_total;
     int *status;
 };
@@ -225,38 +226,18 @@ __device__ __forceinline__ void flush_pos_table(const BuildArgs &a, unsigned cha
     }
 }
 
-template <int KPS, bool VALIDATE>
-__global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid_constant__ BuildArgs a) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+// Consumer side of the build kernel.  UNI: one read group and every group of the batch has the row
+// flags of group 0 (interleaved pairs, single-end reads: the usual case, detected by the prepare
+// pass), so nothing has to be read from the stage headers: the place of a group in the stage and its
+// index follow from the iteration, and the row flag is a per-thread constant.
+template <int KPS, bool VALIDATE, bool UNI>
+__device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char *smem_raw, uint32_t lo, uint32_t hi,
+                                              uint32_t uni_flo, uint32_t uni_fhi) {
     const Geom &g = a.g;
     const TableCfg &t = a.t;
     const StageLayout &sl = a.sl;
-    const int nconsumers = g.threads;  // + one producer warp
-
-    // this CTA's slice of the concatenated work list
-    const unsigned long long E = a.seg[a.R];
-    const uint32_t lo = (uint32_t)(E * blockIdx.x / gridDim.x), hi = (uint32_t)(E * (blockIdx.x + 1) / gridDim.x);
-
+    const int nconsumers = g.threads;
     const uint32_t bar0 = smem_u32(smem_raw + sl.bar_off);
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < sl.stages; ++s) {
-            mbar_init(bar0 + s * 8, 1);                               // full: the producer's arrive + tx bytes
-            mbar_init(bar0 + (sl.stages + s) * 8, nconsumers / 32);   // empty: one arrive per consumer warp
-        }
-        mbar_fence_init();
-    }
-    __syncthreads();
-
-    if ((int)threadIdx.x >= nconsumers) {  // ---- producer warp ----
-        ProducerArgs p;
-        p.arr[0] = a.seq; p.arr[1] = a.qual; p.arr[2] = a.corr;
-        p.entries = a.entries; p.seg = a.seg; p.R = a.R; p.lo = lo; p.hi = hi;
-        p.gbytes = g.gbytes; p.ng = sl.ngs; p.total_bytes = a.total_bytes;
-        producer_loop(p, sl, smem_raw);
-        return;
-    }
-
-    // ---- consumer warps ----
     const ThreadMap m = make_thread_map(g, t.sj);
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
@@ -269,8 +250,17 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
     const uint32_t rowsel = m.row >= 0 ? (uint32_t)m.row : 0u;  // prmt selector: flag byte of this thread's row
     const uint32_t lanemask = pin(m.row >= 0 ? 0xFFu : 0u);     // padding lanes never see a live row
     const uint32_t rowmask = pin(m.rowmask);
-    const uint32_t data0 = smem_u32(smem_raw + sl.data_off) + m.toff;
+    if (UNI) {  // the row flag never changes: re-base the cycle-table addresses once
+        const uint32_t f = prmt(uni_flo, uni_fhi, rowsel) & lanemask;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) aeff[b] += (f >> 1) * t.revoff;
+        cur_flag = f;
+    }
+    const bool live = cur_flag != 0;
+    // UNI: group j of a stage starts at (misalignment of the stage's first group) + j * gbytes
+    const uint32_t data0 = smem_u32(smem_raw + sl.data_off) + m.toff + (UNI ? m.grp * g.gbytes : 0);
     const uint32_t hdr0 = smem_u32(smem_raw + sl.hdr_off) + m.grp * 16;
+    const uint32_t kgrp = g.ng * g.gbytes;
     const uint32_t stage_bytes = sl.narr * sl.abytes, abytes = sl.abytes, hdr_stride = sl.ngs * 16, krec = g.ng * 16;
     const uint32_t mp = t.mp, md = t.md, revoff = t.revoff, addq = t.addq;
     const uint32_t one = pin(1u), lut_acgt = pin(0x47544341u);  // 'A' 'C' 'T' 'G' by 2-bit code
@@ -296,24 +286,37 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
             since_pos += t.fold_din;
             for (; first < chunk_end; first += sl.ngs) {
                 mbar_wait(bar0 + stage * 8, phase);
-                const uint32_t sdata = pin(data0 + stage * stage_bytes), shdr = pin(hdr0 + stage * hdr_stride);
+                const uint32_t shdr = pin(hdr0 + stage * hdr_stride);
+                uint32_t sdata = data0 + stage * stage_bytes;
+                uint32_t nlive = sl.ngs;
+                if (UNI) {
+                    sdata += (uint32_t)((unsigned long long)first * g.gbytes) & 15u;
+                    nlive = s_hi - first;  // groups in this stage (>= ngs except in the last one)
+                }
+                sdata = pin(sdata);
 #pragma unroll
                 for (int k = 0; k < KPS; ++k) {
-                    // this thread-group's k-th record of the stage
-                    uint32_t soff, hgrp, flo, fhi;
-                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
-                                 : "r"(shdr + k * krec));
-                    // flag byte of this thread's row: 0 = not in this segment (or a padding lane), 1 = read 1, 3 = read 2.
-                    // A row usually keeps its flag from group to group (interleaved pairs), so the cycle-table
-                    // addresses are kept ready for the last flag seen and only re-based when it changes.
-                    const uint32_t flag = prmt(flo, fhi, rowsel) & lanemask;
-                    if (flag != cur_flag) {
-                        if (!flag) continue;
-                        const uint32_t delta = ((flag >> 1) - (cur_flag >> 1)) * revoff;
+                    uint32_t soff;
+                    if (UNI) {
+                        if (!live || (uint32_t)(m.grp + k * g.ng) >= nlive) continue;
+                        soff = k * kgrp;
+                    } else {
+                        // this thread-group's k-th record of the stage
+                        uint32_t hgrp, flo, fhi;
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
+                                     : "r"(shdr + k * krec));
+                        // flag byte of this thread's row: 0 = not in this segment (or a padding lane), 1 = read 1,
+                        // 3 = read 2.  A row usually keeps its flag from group to group, so the cycle-table
+                        // addresses are kept ready for the last flag seen and only re-based when it changes.
+                        const uint32_t flag = prmt(flo, fhi, rowsel) & lanemask;
+                        if (flag != cur_flag) {
+                            if (!flag) continue;
+                            const uint32_t delta = ((flag >> 1) - (cur_flag >> 1)) * revoff;
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) aeff[b] += delta;
-                        cur_flag = flag;
+                            for (int b = 0; b < 4; ++b) aeff[b] += delta;
+                            cur_flag = flag;
+                        }
                     }
                     const uint32_t wa = sdata + soff;
                     uint32_t sw, qw, cw, pb;
@@ -384,6 +387,43 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
     }
     if (~qgood & rowmask & H4) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
     if (VALIDATE && (bbad & rowmask)) atomicOr(a.status, KBBQ_FLAG_BAD_BASE);
+}
+
+
+template <int KPS, bool VALIDATE>
+__global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid_constant__ BuildArgs a) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const Geom &g = a.g;
+    const StageLayout &sl = a.sl;
+    const int nconsumers = g.threads;  // + one producer warp
+
+    // this CTA's slice of the concatenated work list
+    const unsigned long long E = a.seg[a.R];
+    const uint32_t lo = (uint32_t)(E * blockIdx.x / gridDim.x), hi = (uint32_t)(E * (blockIdx.x + 1) / gridDim.x);
+
+    const uint32_t bar0 = smem_u32(smem_raw + sl.bar_off);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < sl.stages; ++s) {
+            mbar_init(bar0 + s * 8, 1);                               // full: the producer's arrive + tx bytes
+            mbar_init(bar0 + (sl.stages + s) * 8, nconsumers / 32);   // empty: one arrive per consumer warp
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if ((int)threadIdx.x >= nconsumers) {  // ---- producer warp ----
+        ProducerArgs p;
+        p.arr[0] = a.seq; p.arr[1] = a.qual; p.arr[2] = a.corr;
+        p.entries = a.entries; p.seg = a.seg; p.R = a.R; p.lo = lo; p.hi = hi;
+        p.gbytes = g.gbytes; p.ng = sl.ngs; p.total_bytes = a.total_bytes;
+        producer_loop(p, sl, smem_raw);
+        return;
+    }
+
+    // ---- consumer warps ----
+    const bool uniform = a.R == 1 && a.uni[0] == 0u;
+    if (uniform) build_consume<KPS, VALIDATE, true>(a, smem_raw, lo, hi, a.uni[1], a.uni[2]);
+    else build_consume<KPS, VALIDATE, false>(a, smem_raw, lo, hi, 0u, 0u);
 }
 
 // Generic path: one thread per base, global 64-bit reductions.  Used when the shared-memory tables

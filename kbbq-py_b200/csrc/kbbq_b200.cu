@@ -183,7 +183,7 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
     BuildArgs a;
     a.seq = seq; a.qual = qual; a.corr = corr; a.total_bytes = N * L; a.g = g; a.t = tc; a.R = R;
     a.sl = sl;
-    a.entries = w.entries; a.seg = w.seg;
+    a.entries = w.entries; a.seg = w.seg; a.uni = w.uni;
     a.pos_errs = (unsigned long long *)pos_errs; a.pos_total = (unsigned long long *)pos_total;
     a.din_errs = (unsigned long long *)din_errs; a.din_total = (unsigned long long *)din_total;
     a.status = status;
@@ -289,7 +289,7 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
     ApplyArgs a;
     a.seq = seq; a.qual = qual; a.out = out_qual; a.total_bytes = N * L; a.g = g; a.t = tc; a.R = R; a.nq = nq;
     a.sl = sl;
-    a.entries = w.entries; a.seg = w.seg; a.fold_cyc = w.fold_cyc; a.fold_din = w.fold_din; a.status = status;
+    a.entries = w.entries; a.seg = w.seg; a.uni = w.uni; a.fold_cyc = w.fold_cyc; a.fold_din = w.fold_din; a.status = status;
     return launch_apply_smem(a, sms, a.sl.total, st);
 }
 

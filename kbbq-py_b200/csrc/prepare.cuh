@@ -25,6 +25,7 @@ struct PrepArgs {
     unsigned int *seg;      // [R + 1] segment offsets (out)
     unsigned int *cursor;   // [R] scratch
     entry_t *entries;       // (out)
+    unsigned int *uni;      // (out) [0] != 0: some group's row flags differ from group 0's; [1], [2]: those flags
     int *status;
     // staging geometry of the kernel that will walk the list (stage.cuh)
     int grid;               // its number of CTAs
@@ -98,7 +99,19 @@ __global__ void prep_identity_kernel(PrepArgs a) {
     const unsigned long long lo = slice_lo(E, slice_of(E, (unsigned long long)grp, a.grid), a.grid);
     const unsigned int j = (unsigned int)(((unsigned long long)grp - lo) % (unsigned int)a.ng);
     const unsigned int mis0 = (unsigned int)((((unsigned long long)grp - j) * a.gbytes) & 15ull);
-    a.entries[grp] = make_entry(mis0 + j * a.gbytes, grp, exist, sec);
+    const entry_t e = make_entry(mis0 + j * a.gbytes, grp, exist, sec);
+    a.entries[grp] = e;
+    // do all groups look like group 0, with every row tallied?  (lets the kernels skip the headers)
+    unsigned int rgv0[MAX_G], sec0, exist0;
+    load_rows(a, 0, rgv0, sec0, exist0);
+    if (a.rg) {
+#pragma unroll
+        for (int k = 0; k < MAX_G; ++k)
+            if (((exist0 >> k) & 1) && rgv0[k] != 0) exist0 &= ~(1u << k);
+    }
+    const entry_t p0 = make_entry(0u, 0, exist0, sec0);
+    if (e.z != p0.z || e.w != p0.w || exist0 != (1u << a.G) - 1u) a.uni[0] = 1u;
+    if (grp == 0) { a.uni[1] = p0.z; a.uni[2] = p0.w; }
 }
 
 // mode 0: count list entries per read group into a.cursor; mode 1: scatter entries.
@@ -198,6 +211,7 @@ __global__ void prep_scan_kernel(PrepArgs a) {
 struct Workspace {
     unsigned int *seg;
     unsigned int *cursor;
+    unsigned int *uni;     // [4]
     entry_t *entries;
     short *fold_cyc;   // [R][43][2L]   apply only
     short *fold_din;   // [R][43][16]   apply only (natural dinuc order, relative to the pad column)
@@ -215,6 +229,7 @@ inline Workspace carve_workspace(void *base, long long N, int L, int R) {
     const size_t max_entries = (size_t)N + MAX_G;
     w.seg = (unsigned int *)(p + off);      off = align_up(off + sizeof(unsigned int) * ((size_t)R + 1), 256);
     w.cursor = (unsigned int *)(p + off);   off = align_up(off + sizeof(unsigned int) * (size_t)R, 256);
+    w.uni = (unsigned int *)(p + off);      off = align_up(off + sizeof(unsigned int) * 4, 256);
     w.entries = (entry_t *)(p + off);       off = align_up(off + sizeof(entry_t) * max_entries, 256);
     w.fold_cyc = (short *)(p + off);        off = align_up(off + sizeof(short) * (size_t)R * NQ * 2 * L, 256);
     w.fold_din = (short *)(p + off);        off = align_up(off + sizeof(short) * (size_t)R * NQ * 16, 256);
@@ -229,8 +244,10 @@ inline int run_prepare(const uint16_t *rg, const uint8_t *second, long long N, i
     PrepArgs a;
     a.rg = rg; a.second = second; a.N = N; a.G = G;
     a.ngroups = (N + G - 1) / G; a.R = R;
-    a.seg = w.seg; a.cursor = w.cursor; a.entries = w.entries; a.status = status;
+    a.seg = w.seg; a.cursor = w.cursor; a.entries = w.entries; a.uni = w.uni; a.status = status;
     a.grid = grid; a.ng = ng; a.gbytes = gbytes; a.slot = slot;
+    // several read groups (or nothing to do): not uniform; one read group: the identity pass decides
+    KBBQ_CUDA(cudaMemsetAsync(w.uni, (R == 1 && a.ngroups > 0) ? 0 : 0xFF, sizeof(unsigned int) * 4, st));
     if (a.ngroups == 0) {
         KBBQ_CUDA(cudaMemsetAsync(w.seg, 0, sizeof(unsigned int) * ((size_t)R + 1), st));
         return KBBQ_OK;
