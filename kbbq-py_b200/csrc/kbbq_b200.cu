@@ -177,6 +177,19 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
     }
     Workspace w = carve_workspace(workspace, N, L, R);
     if (!workspace || workspace_bytes < w.bytes) return KBBQ_E_WORKSPACE;
+    // One read group: a partial last group would be the only one with untallied rows and cost the
+    // whole batch its header-free fast path; its few reads go through the generic kernel instead.
+    const int64_t tail = (R == 1 && N > g.G) ? N % g.G : 0;
+    if (tail) {
+        const int64_t n0 = N - tail;
+        BuildGenericArgs ga = {seq + n0 * L, qual + n0 * L, corr + n0 * L, rg ? rg + n0 : nullptr,
+                               second ? second + n0 : nullptr, tail, L, R, minscore,
+                               (unsigned long long *)pos_errs, (unsigned long long *)pos_total,
+                               (unsigned long long *)din_errs, (unsigned long long *)din_total, status};
+        build_generic_kernel<<<1, 256, 0, st>>>(ga);
+        KBBQ_LAUNCHED();
+        N = n0;
+    }
     rc = run_prepare(rg, second, N, g.G, R, w, status, sms, sl.ngs, g.gbytes, sl.slot, st);
     if (rc) return rc;
 
@@ -283,6 +296,15 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
         apply_generic_kernel<<<sms * 8, 256, 0, st>>>(a);
         KBBQ_LAUNCHED();
         return KBBQ_OK;
+    }
+    const int64_t tail = (R == 1 && N > g.G) ? N % g.G : 0;  // see kbbq_build
+    if (tail) {
+        const int64_t n0 = N - tail;
+        ApplyGenericArgs ga = {seq + n0 * L, qual + n0 * L, rg ? rg + n0 : nullptr, second ? second + n0 : nullptr,
+                               out_qual + n0 * L, tail, L, R, minscore, nq, w.fold_cyc, w.fold_din, status};
+        apply_generic_kernel<<<1, 256, 0, st>>>(ga);
+        KBBQ_LAUNCHED();
+        N = n0;
     }
     rc = run_prepare(rg, second, N, g.G, R, w, status, sms, sl.ngs, g.gbytes, sl.slot, st);
     if (rc) return rc;

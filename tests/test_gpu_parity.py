@@ -122,6 +122,7 @@ def test_device_synth_equals_numpy_twin(torch_cuda):
 SYNTH_CASES = [
     # (name, seed, N, L, R)  -- the BASELINE.json configs at oracle-sized N
     ("c2_l150_r1", 1002, 200_000, 150, 1),
+    ("c2_l150_r1_partial_last_group", 1002, 100_003, 150, 1),
     ("c3_l150_r8", 1003, 120_000, 150, 8),
     ("c4_l250_r32", 1004, 60_000, 250, 32),
     ("c1_l151_r1", 1001, 24_000, 151, 1),
