@@ -70,6 +70,7 @@ struct Geom {
     int lps;          // lanes per thread-group (= lanes)
     int ng;           // thread-groups (groups in flight) per CTA
     int threads;      // consumer threads: ng * lps rounded up to whole warps
+    int nprod;        // producer warps behind the consumers (1 with one read group, 4 otherwise)
     int sj;           // plane stride (words)
     int row;          // words per quality row = 4 * sj
     int minscore;     // first tallied quality
@@ -82,18 +83,28 @@ __host__ __device__ inline int gcd_int(int a, int b) {
     return a;
 }
 
-inline bool make_geom(int L, int minscore, Geom *g) {
+// `single_rg`: with one read group every row of a group is tallied, so the group only has to be
+// large enough to leave at most 16 thread-groups (several groups per thread-group and stage then fit
+// the 32-groups-per-stage limit).  With several read groups the smallest group is taken: mates of a
+// pair normally share their read group, so a group of one pair is staged once, while a larger group
+// would be staged once per read group present in it.
+inline bool make_geom(int L, int minscore, bool single_rg, Geom *g) {
     if (L < 4 || minscore < 0 || minscore >= NQ) return false;
     const int rps = 4 / gcd_int(L, 4);
+    // With several read groups every group of a stage is a copy of its own per array; one warp
+    // issues a bulk copy every ~90 cycles, so four warps share the stages round-robin.
+    const int nprod = single_rg ? 1 : 4;
+    const int budget = MAX_THREADS - 32 * nprod;
     int best_g = 0, best_lanes = 0;
     for (int G = rps; G <= MAX_G; G += rps) {
         int lanes = 0;
         for (int k = 0; k < G; ++k) lanes += ((k * L) % 4 + L + 3) / 4;
-        if (lanes > MAX_THREADS - 32) break;  // one warp is the TMA producer
-        // fewer lanes per read wins; ties keep the smaller group
-        if (best_g == 0 || (long long)lanes * best_g < (long long)best_lanes * G) {
-            best_g = G; best_lanes = lanes;
-        }
+        if (lanes > budget) break;
+        if (best_g == 0) { best_g = G; best_lanes = lanes; continue; }
+        if (!single_rg) break;
+        // fewer lanes per read wins; on a tie a larger group only while the smaller one leaves > 16 thread-groups
+        const long long a = (long long)lanes * best_g, b = (long long)best_lanes * G;
+        if (a < b || (a == b && budget / best_lanes > 16)) { best_g = G; best_lanes = lanes; }
     }
     if (best_g == 0) return false;
     g->L = L;
@@ -101,7 +112,8 @@ inline bool make_geom(int L, int minscore, Geom *g) {
     g->gbytes = best_g * L;
     g->lanes = best_lanes;
     g->lps = best_lanes;
-    g->ng = std::min(32, (MAX_THREADS - 32) / g->lps);  // a stage holds at most 32 groups (one per producer lane)
+    g->nprod = nprod;
+    g->ng = std::min(32, budget / g->lps);  // a stage holds at most 32 groups (one per producer lane)
     g->threads = (g->ng * g->lps + 31) / 32 * 32;
     int w = 0;
     for (int k = 0; k <= MAX_G; ++k) {

@@ -59,21 +59,27 @@ static bool misaligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)
 // so with 32 dinuc replicas (conflict free; 16 if that does not fit) take as many groups per
 // thread-group and stage (kps <= 4, at most 32 groups per stage: one per producer lane) as still
 // leave a ring of 3 stages; failing that, whatever ring of at least 2 stages fits.
-// Measured on 10M x 150 bp: build kps 2 / drep 32 1.24 ms vs kps 4 / drep 16 1.30 ms.
+// Measured on 10M x 150 bp: build kps 1 / drep 32 1.51 ms, kps 2 / drep 32 1.24 ms, kps 4 / drep 16 1.30 ms.
 static bool plan_smem(const Geom &g, int narr, int max_smem, TableCfg *tc, StageLayout *sl) {
     const char *e = getenv("KBBQ_KPS");  // tuning / test hooks
     const int kmax = e ? std::max(1, std::min(4, atoi(e))) : 4;
     const char *d = getenv("KBBQ_DREP");
     const int dmax = d ? atoi(d) : 32;
     for (int want = 3; want >= 2; --want) {
-        for (int drep = 32; drep >= 16; drep >>= 1) {
-            if (drep > dmax) continue;
-            for (int k = kmax; k >= 1; --k) {
-                if (g.ng * k > 32) continue;
-                if (!make_table_cfg(g, k, drep, tc)) return false;
-                for (int s = MAX_STAGES; s >= want; --s) {
-                    *sl = make_stage_layout(g, narr, s, k, tc->table_bytes);
-                    if (sl->total <= max_smem) return true;
+        for (int kmin = 2; kmin >= 1; --kmin) {       // two groups per barrier round are worth more ...
+            for (int drep = 32; drep >= 16; drep >>= 1) {  // ... than conflict-free dinuc replicas
+                if (drep > dmax) continue;
+                for (int k = kmax; k >= kmin; --k) {
+                    if (g.ng * k > 32) continue;
+                    if (!make_table_cfg(g, k, drep, tc)) return false;
+                    for (int s = MAX_STAGES; s >= want; --s) {
+                        // several producer warps take the iterations round-robin: a stage must always be
+                        // refilled by the same warp (its waits are only one phase deep), so the ring
+                        // depth has to be a multiple of their number
+                        if (s % g.nprod) continue;
+                        *sl = make_stage_layout(g, narr, s, k, tc->table_bytes);
+                        if (sl->total <= max_smem) return true;
+                    }
                 }
             }
         }
@@ -85,7 +91,7 @@ template <int KPS>
 static int launch_build_kps(const BuildArgs &a, int grid, size_t smem, cudaStream_t st) {
     auto kern = build_smem_kernel<KPS, true>;
     KBBQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, a.g.threads + 32, smem, st>>>(a);  // + the producer warp
+    kern<<<grid, a.g.threads + 32 * a.g.nprod, smem, st>>>(a);  // + the producer warp(s)
     KBBQ_LAUNCHED();
     return KBBQ_OK;
 }
@@ -102,7 +108,7 @@ template <int KPS>
 static int launch_apply_kps(const ApplyArgs &a, int grid, size_t smem, cudaStream_t st) {
     auto kern = apply_smem_kernel<KPS>;
     KBBQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, a.g.threads + 32, smem, st>>>(a);  // + the producer warp
+    kern<<<grid, a.g.threads + 32 * a.g.nprod, smem, st>>>(a);  // + the producer warp(s)
     KBBQ_LAUNCHED();
     return KBBQ_OK;
 }
@@ -160,7 +166,7 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
     if (rc) return rc;
 
     Geom g;
-    bool smem_ok = path != 2 && make_geom(L, minscore, &g) && g.row < 65536 &&
+    bool smem_ok = path != 2 && make_geom(L, minscore, R == 1, &g) && g.row < 65536 &&
                    (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull &&
                    !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(corr, 16);
     TableCfg tc;
@@ -284,7 +290,7 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
     KBBQ_LAUNCHED();
 
     Geom g;
-    bool smem_ok = path != 2 && make_geom(L, minscore, &g) && g.row < 65536 &&
+    bool smem_ok = path != 2 && make_geom(L, minscore, R == 1, &g) && g.row < 65536 &&
                    (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull &&
                    !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(out_qual, 4);
     TableCfg tc;

@@ -95,6 +95,7 @@ struct ProducerArgs {
     uint32_t gbytes;
     int ng;                 // groups per stage (StageLayout::ngs)
     long long total_bytes;  // bytes of each array (N * L)
+    int pw, nprod;          // this producer warp / number of producer warps
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -110,8 +111,8 @@ __device__ __forceinline__ void producer_loop(const ProducerArgs &p, const Stage
     uint32_t stage = 0, phase = 0;
     const unsigned long long end16 = ((unsigned long long)p.total_bytes + 15ull) & ~15ull;
 
-    if (p.R == 1) {  // identity list: one contiguous span per stage
-        if (lane != 0) return;
+    if (p.R == 1) {  // identity list: one contiguous span per stage, one producer warp
+        if (lane != 0 || p.pw != 0) return;
         for (uint32_t first = p.lo; first < p.hi; first += p.ng) {
             const uint32_t n = min((uint32_t)p.ng, p.hi - first);
             const uint32_t full = bar0 + stage * 8, empty = bar0 + (sl.stages + stage) * 8;
@@ -138,31 +139,33 @@ __device__ __forceinline__ void producer_loop(const ProducerArgs &p, const Stage
         return;
     }
 
-    // Several read groups: lane j copies group j of the stage into slot j.  The group indices are
-    // fetched a batch (up to 32 records = several stages) ahead, so that no global-load latency
-    // sits between a stage being released and its refill being issued.
-    const uint32_t per_batch = (uint32_t)(32 / p.ng) * p.ng;  // whole iterations only
+    // Several read groups: lane j copies group j of the stage into slot j; the producer warps take
+    // the iterations round-robin (one warp issues a bulk copy every ~90 cycles).  The group indices of
+    // a warp's next iteration are fetched while the current one is issued.
+    uint32_t it = 0;  // iteration counter over all segments: stage = it % stages
     for (int rg = 0; rg < p.R; ++rg) {
         uint32_t s_lo = p.seg[rg], s_hi = p.seg[rg + 1];
         if (s_hi <= p.lo) continue;
         if (s_lo >= p.hi) break;
         if (s_lo < p.lo) s_lo = p.lo;
         if (s_hi > p.hi) s_hi = p.hi;
-        auto fetch = [&](uint32_t base) -> uint32_t {
-            const unsigned long long i = (unsigned long long)base + lane;
-            return ((uint32_t)lane < per_batch && i < s_hi) ? __ldg(&p.entries[i].y) : 0u;
+        const uint32_t iters = (s_hi - s_lo + p.ng - 1) / p.ng;
+        // first iteration of this segment that is this warp's: it0 + i with (it0 + i) % nprod == pw
+        uint32_t i = (uint32_t)((p.pw + p.nprod - (int)(it % p.nprod)) % p.nprod);
+        auto fetch = [&](uint32_t iter) -> uint32_t {
+            const unsigned long long e = (unsigned long long)s_lo + (unsigned long long)iter * p.ng + lane;
+            return (iter < iters && lane < p.ng && e < s_hi) ? __ldg(&p.entries[e].y) : 0u;
         };
-        uint32_t bbase = s_lo;
-        uint32_t cur = fetch(bbase), nxt = fetch(bbase + per_batch);
-        for (uint32_t first = s_lo; first < s_hi; first += p.ng) {
-            if (first - bbase >= per_batch) {
-                bbase += per_batch;
-                cur = nxt;
-                nxt = fetch(bbase + per_batch);
-            }
+        uint32_t nxt = fetch(i);
+        for (; i < iters; i += p.nprod) {
+            const uint32_t first = s_lo + i * p.ng;
+            const uint32_t grp = nxt;
+            nxt = fetch(i + p.nprod);
+            const uint32_t g_it = it + i;
+            stage = g_it % (uint32_t)sl.stages;
+            phase = (g_it / (uint32_t)sl.stages) & 1u;
             const uint32_t n = min((uint32_t)p.ng, s_hi - first);
             const uint32_t full = bar0 + stage * 8, empty = bar0 + (sl.stages + stage) * 8;
-            const uint32_t grp = __shfl_sync(0xFFFFFFFFu, cur, (first - bbase + lane) & 31);
             const unsigned long long start = (unsigned long long)grp * p.gbytes;
             const uint32_t mis = (uint32_t)start & 15u;
             const unsigned long long src = start - mis;
@@ -188,8 +191,8 @@ __device__ __forceinline__ void producer_loop(const ProducerArgs &p, const Stage
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(full);  // after every expect_tx and header store of the stage
-            if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
         }
+        it += iters;
     }
 }
 
