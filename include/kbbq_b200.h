@@ -163,6 +163,15 @@ int kbbq_synth_reads(uint64_t seed, int64_t first_read, int64_t n, int L, int R,
                      uint8_t *seq_dev, uint8_t *qual_dev, uint8_t *corr_dev, uint16_t *rg_dev,
                      uint8_t *second_dev, void *stream);
 
+/*
+ * Shared-memory plan the build (arrays = 3) or apply (arrays = 2) kernel would run with for reads of
+ * length L and R read groups (max_smem: opt-in shared memory per block, 0 = 232448 of sm_100):
+ * out[10] = {reads per group, lanes per group, thread-groups, consumer threads, producer warps,
+ * groups per thread-group and stage, ring depth, dinuc replicas, dynamic shared memory, table bytes}.
+ * KBBQ_E_ARG when the shape falls back to the generic kernels.  Diagnostics / tests.
+ */
+int kbbq_plan_info(int L, int R, int minscore, int arrays, int max_smem, int *out);
+
 /* Number of kernel launches this library has issued since load (bench.py's gpu_launches). */
 int64_t kbbq_launch_count(void);
 

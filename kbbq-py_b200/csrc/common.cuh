@@ -113,7 +113,8 @@ inline bool make_geom(int L, int minscore, bool single_rg, Geom *g) {
     g->lanes = best_lanes;
     g->lps = best_lanes;
     g->nprod = nprod;
-    g->ng = std::min(32, budget / g->lps);  // a stage holds at most 32 groups (one per producer lane)
+    // several read groups: a stage holds at most 32 groups (one per producer lane)
+    g->ng = single_rg ? budget / g->lps : std::min(32, budget / g->lps);
     g->threads = (g->ng * g->lps + 31) / 32 * 32;
     int w = 0;
     for (int k = 0; k <= MAX_G; ++k) {

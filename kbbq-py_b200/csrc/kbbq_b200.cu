@@ -70,7 +70,7 @@ static bool plan_smem(const Geom &g, int narr, int max_smem, TableCfg *tc, Stage
             for (int drep = 32; drep >= 16; drep >>= 1) {  // ... than conflict-free dinuc replicas
                 if (drep > dmax) continue;
                 for (int k = kmax; k >= kmin; --k) {
-                    if (g.ng * k > 32) continue;
+                    if (g.nprod > 1 && g.ng * k > 32) continue;  // one producer lane per group of a stage
                     if (!make_table_cfg(g, k, drep, tc)) return false;
                     for (int s = MAX_STAGES; s >= want; --s) {
                         // several producer warps take the iterations round-robin: a stage must always be
@@ -145,6 +145,18 @@ const char *kbbq_last_cuda_error(void) { return g_last_cuda_error; }
 int64_t kbbq_pos_table_elems(int L, int R) { return (int64_t)R * NQ * 2 * L; }
 int64_t kbbq_din_table_elems(int R) { return (int64_t)R * NQ * 16; }
 int64_t kbbq_launch_count(void) { return g_launches; }
+
+int kbbq_plan_info(int L, int R, int minscore, int arrays, int max_smem, int *out) {
+    if (!out || L < 1 || R < 1 || (arrays != 2 && arrays != 3)) return KBBQ_E_ARG;
+    Geom g;
+    TableCfg tc;
+    StageLayout sl;
+    if (!make_geom(L, minscore, R == 1, &g) || !plan_smem(g, arrays, max_smem > 0 ? max_smem : 232448, &tc, &sl))
+        return KBBQ_E_ARG;  // the generic kernels would be used
+    const int v[10] = {g.G, g.lanes, g.ng, g.threads, g.nprod, sl.kps, sl.stages, tc.drep, sl.total, tc.table_bytes};
+    for (int i = 0; i < 10; ++i) out[i] = v[i];
+    return KBBQ_OK;
+}
 
 int kbbq_workspace_bytes(int64_t N, int L, int R, size_t *bytes) {
     if (N < 0 || L < 1 || R < 1 || R > 65535 || !bytes) return KBBQ_E_ARG;

@@ -38,6 +38,8 @@ struct StageLayout {
     int total;        // dynamic shared memory bytes including the tables in front
 };
 
+// With one producer warp (one read group) a stage is always one contiguous span, so the per-group
+// slots with their alignment slack are not needed.
 inline StageLayout make_stage_layout(const Geom &g, int narr, int stages, int kps, size_t table_bytes) {
     StageLayout s;
     s.stages = stages;
@@ -45,7 +47,7 @@ inline StageLayout make_stage_layout(const Geom &g, int narr, int stages, int kp
     s.ngs = g.ng * kps;
     s.narr = narr;
     s.slot = (g.gbytes + 15 + 15) / 16 * 16;           // group + worst-case misalignment, 16-byte units
-    s.abytes = (s.ngs * s.slot + 127) / 128 * 128;     // also covers the contiguous span (ngs*gbytes + 30)
+    s.abytes = ((g.nprod == 1 ? s.ngs * g.gbytes + 32 : s.ngs * s.slot) + 127) / 128 * 128;
     s.data_off = (int)((table_bytes + 127) / 128 * 128);
     s.hdr_off = s.data_off + stages * narr * s.abytes;
     s.bar_off = s.hdr_off + stages * s.ngs * 16;

@@ -41,6 +41,7 @@ SIGNATURES = {
     "kbbq_marginals_host": (_i, [_vp, _vp, _i, _i] + [_vp] * 5 + [_i]),
     "kbbq_synth_reads": (_i, [C.c_uint64, _i64, _i64, _i, _i] + [_vp] * 5 + [_vp]),
     "kbbq_launch_count": (_i64, []),
+    "kbbq_plan_info": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i)]),
 }
 
 
@@ -103,6 +104,15 @@ def u8(a):
 
 def i64(a):
     return np.ascontiguousarray(a, dtype=np.int64)
+
+
+def plan_info(L, R=1, minscore=6, arrays=3, max_smem=0):
+    """Shared-memory plan of the build (arrays=3) / apply (arrays=2) kernel, or None for the generic path."""
+    out = (C.c_int * 10)()
+    if lib().kbbq_plan_info(L, R, minscore, arrays, max_smem, out) != 0:
+        return None
+    keys = ("G", "lanes", "ng", "threads", "nprod", "kps", "stages", "drep", "smem", "table_bytes")
+    return dict(zip(keys, out))
 
 
 DEVICE = int(os.environ.get("KBBQ_DEVICE", os.environ.get("LOCAL_RANK", "0")))

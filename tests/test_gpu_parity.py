@@ -127,6 +127,7 @@ SYNTH_CASES = [
     ("c4_l250_r32", 1004, 60_000, 250, 32),
     ("c1_l151_r1", 1001, 24_000, 151, 1),
     ("l100_r3_ragged_n", 5, 33_333, 100, 3),
+    ("l150_r1_ragged_second", 9, 50_001, 150, 1),
     ("l37_r5", 6, 10_007, 37, 5),
     ("l8_r2", 8, 4_099, 8, 2),
 ]
