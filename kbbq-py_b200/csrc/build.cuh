@@ -417,6 +417,7 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
         p.entries = a.entries; p.seg = a.seg; p.R = a.R; p.lo = lo; p.hi = hi;
         p.gbytes = g.gbytes; p.ng = sl.ngs; p.total_bytes = a.total_bytes;
         p.pw = ((int)threadIdx.x - nconsumers) >> 5; p.nprod = g.nprod;
+        p.uniform = a.R == 1 && a.uni[0] == 0u;
         producer_loop(p, sl, smem_raw);
         return;
     }

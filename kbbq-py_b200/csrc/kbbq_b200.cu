@@ -65,7 +65,9 @@ static bool plan_smem(const Geom &g, int narr, int max_smem, TableCfg *tc, Stage
     const int kmax = e ? std::max(1, std::min(4, atoi(e))) : 4;
     const char *d = getenv("KBBQ_DREP");
     const int dmax = d ? atoi(d) : 32;
-    for (int want = 3; want >= 2; --want) {
+    const char *w = getenv("KBBQ_MIN_STAGES");
+    const int want0 = w ? std::max(2, std::min(8, atoi(w))) : 3;
+    for (int want = want0; want >= 2; --want) {
         for (int kmin = 2; kmin >= 1; --kmin) {       // two groups per barrier round are worth more ...
             for (int drep = 32; drep >= 16; drep >>= 1) {  // ... than conflict-free dinuc replicas
                 if (drep > dmax) continue;

@@ -73,15 +73,10 @@ __device__ __forceinline__ void load_rows(const PrepArgs &a, long long grp, unsi
     }
 }
 
-// Single read group: the list is the identity, no counting needed.
-__global__ void prep_identity_kernel(PrepArgs a) {
-    const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (grp == 0) {
-        a.seg[0] = 0;
-        a.seg[1] = (unsigned int)a.ngroups;
-    }
-    if (grp >= a.ngroups) return;
-    unsigned int rgv[MAX_G], sec, exist;
+// flags of a group with one read group: rows that exist and have rg == 0 (anything else is an error)
+__device__ __forceinline__ void identity_rows(const PrepArgs &a, long long grp, unsigned int &exist, unsigned int &sec,
+                                              bool report) {
+    unsigned int rgv[MAX_G];
     load_rows(a, grp, rgv, sec, exist);
     if (a.rg) {
         unsigned int ok = 0;
@@ -89,29 +84,46 @@ __global__ void prep_identity_kernel(PrepArgs a) {
         for (int k = 0; k < MAX_G; ++k)
             if ((exist >> k) & 1) {
                 if (rgv[k] == 0) ok |= 1u << k;
-                else atomicOr(a.status, KBBQ_FLAG_RG_RANGE);
+                else if (report) atomicOr(a.status, KBBQ_FLAG_RG_RANGE);
             }
         exist = ok;
     }
-    // the list is the identity, so a stage is one contiguous span: ng consecutive groups from the
-    // start of the CTA's slice, the first one 16-byte aligned down
+}
+
+// Single read group, pass 1: do all groups look like group 0, with every row tallied?  Then the
+// kernels need no work list at all (uni[0] stays 0) and pass 2 returns at once.  Reads 1-3 B/read.
+__global__ void prep_uniform_kernel(PrepArgs a) {
+    const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (grp == 0) {
+        a.seg[0] = 0;
+        a.seg[1] = (unsigned int)a.ngroups;
+    }
+    if (grp >= a.ngroups) return;
+    unsigned int exist, sec, exist0, sec0;
+    identity_rows(a, grp, exist, sec, true);
+    identity_rows(a, 0, exist0, sec0, false);
+    if (exist != exist0 || sec != sec0 || exist0 != (1u << a.G) - 1u) a.uni[0] = 1u;
+    if (grp == 0) {
+        const entry_t p0 = make_entry(0u, 0, exist0, sec0);
+        a.uni[1] = p0.z;
+        a.uni[2] = p0.w;
+    }
+}
+
+// Single read group, pass 2 (only when the groups differ): the list is the identity.
+__global__ void prep_identity_kernel(PrepArgs a) {
+    if (a.uni[0] == 0u) return;
+    const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (grp >= a.ngroups) return;
+    unsigned int exist, sec;
+    identity_rows(a, grp, exist, sec, false);
+    // a stage is one contiguous span: ng consecutive groups from the start of the CTA's slice, the
+    // first one 16-byte aligned down
     const unsigned long long E = (unsigned long long)a.ngroups;
     const unsigned long long lo = slice_lo(E, slice_of(E, (unsigned long long)grp, a.grid), a.grid);
     const unsigned int j = (unsigned int)(((unsigned long long)grp - lo) % (unsigned int)a.ng);
     const unsigned int mis0 = (unsigned int)((((unsigned long long)grp - j) * a.gbytes) & 15ull);
-    const entry_t e = make_entry(mis0 + j * a.gbytes, grp, exist, sec);
-    a.entries[grp] = e;
-    // do all groups look like group 0, with every row tallied?  (lets the kernels skip the headers)
-    unsigned int rgv0[MAX_G], sec0, exist0;
-    load_rows(a, 0, rgv0, sec0, exist0);
-    if (a.rg) {
-#pragma unroll
-        for (int k = 0; k < MAX_G; ++k)
-            if (((exist0 >> k) & 1) && rgv0[k] != 0) exist0 &= ~(1u << k);
-    }
-    const entry_t p0 = make_entry(0u, 0, exist0, sec0);
-    if (e.z != p0.z || e.w != p0.w || exist0 != (1u << a.G) - 1u) a.uni[0] = 1u;
-    if (grp == 0) { a.uni[1] = p0.z; a.uni[2] = p0.w; }
+    a.entries[grp] = make_entry(mis0 + j * a.gbytes, grp, exist, sec);
 }
 
 // mode 0: count list entries per read group into a.cursor; mode 1: scatter entries.
@@ -254,6 +266,8 @@ inline int run_prepare(const uint16_t *rg, const uint8_t *second, long long N, i
     }
     const unsigned int blocks = (unsigned int)((a.ngroups + PREP_THREADS - 1) / PREP_THREADS);
     if (R == 1) {
+        prep_uniform_kernel<<<blocks, PREP_THREADS, 0, st>>>(a);
+        KBBQ_LAUNCHED();
         prep_identity_kernel<<<blocks, PREP_THREADS, 0, st>>>(a);
         KBBQ_LAUNCHED();
         return KBBQ_OK;

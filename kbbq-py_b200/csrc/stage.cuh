@@ -98,6 +98,7 @@ struct ProducerArgs {
     int ng;                 // groups per stage (StageLayout::ngs)
     long long total_bytes;  // bytes of each array (N * L)
     int pw, nprod;          // this producer warp / number of producer warps
+    bool uniform;           // one read group, no work list: the consumers do not read the stage headers
 };
 
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
@@ -126,16 +127,17 @@ __device__ __forceinline__ void producer_loop(const ProducerArgs &p, const Stage
             bytes = src >= end16 ? 0u : (uint32_t)min((unsigned long long)bytes, end16 - src);
             mbar_wait(empty, phase ^ 1);
             // a short last stage: the slots past the list must read as "no rows"
-            for (uint32_t j = n; j < (uint32_t)p.ng; ++j)
-                asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(hdr0 + (stage * p.ng + j) * 16u), "r"(0u) : "memory");
-            mbar_arrive_expect_tx(full, bytes * sl.narr + n * 16u);
+            if (!p.uniform)
+                for (uint32_t j = n; j < (uint32_t)p.ng; ++j)
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(hdr0 + (stage * p.ng + j) * 16u), "r"(0u) : "memory");
+            mbar_arrive_expect_tx(full, bytes * sl.narr + (p.uniform ? 0u : n * 16u));
             const uint32_t dst = data0 + stage * sl.narr * sl.abytes;
             if (bytes) {
 #pragma unroll
                 for (int k = 0; k < 3; ++k)
                     if (k < sl.narr) bulk_g2s(dst + k * sl.abytes, p.arr[k] + src, bytes, full);
             }
-            bulk_g2s(hdr0 + stage * p.ng * 16u, p.entries + first, n * 16u, full);
+            if (!p.uniform) bulk_g2s(hdr0 + stage * p.ng * 16u, p.entries + first, n * 16u, full);
             if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
         }
         return;
