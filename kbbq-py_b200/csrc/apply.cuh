@@ -48,7 +48,7 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
     const TableCfg &t = a.t;
     const StageLayout &sl = a.sl;
     const int nconsumers = g.threads;
-    const uint32_t bar0 = smem_u32(smem_raw + sl.bar_off);
+    const uint32_t bar0 = pin(smem_u32(smem_raw + sl.bar_off));
     const ThreadMap m = make_thread_map(g, t.sj);
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
@@ -76,9 +76,10 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
     const uint32_t wshift = pin(half_hi ? 16u : 0u);
     unsigned long long outp = (unsigned long long)(a.out + m.toff + (half_hi ? 2 : 0));
     asm volatile("" : "+l"(outp));
-    const uint32_t data0 = smem_u32(smem_raw + sl.data_off) + m.toff + (UNI ? m.grp * g.gbytes : 0);
-    const uint32_t hdr0 = smem_u32(smem_raw + sl.hdr_off) + m.grp * 16;
-    const uint32_t stage_bytes = sl.narr * sl.abytes, abytes = sl.abytes, hdr_stride = sl.ngs * 16, krec = g.ng * 16;
+    const uint32_t data0 = pin(smem_u32(smem_raw + sl.data_off) + m.toff + (UNI ? m.grp * g.gbytes : 0));
+    const uint32_t hdr0 = pin(smem_u32(smem_raw + sl.hdr_off) + m.grp * 16);
+    const uint32_t stage_bytes = pin(sl.narr * sl.abytes), abytes = pin(sl.abytes), hdr_stride = sl.ngs * 16, krec = g.ng * 16;
+    const uint32_t nstages = pin(sl.stages), ngs = pin(sl.ngs);
     const uint32_t mp = t.mp, md = t.md, revoff = t.revoff, addq = t.addq, gbytes = g.gbytes;
     const uint32_t addnq = (uint32_t)(128 - a.nq) * ONE4;  // q + this has bit 7 set iff q >= nq (q < 128)
     uint32_t stage = 0, phase = 0;
@@ -114,7 +115,7 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
         }
         consumer_sync(nconsumers);
 
-        for (uint32_t first = s_lo; first < s_hi; first += sl.ngs) {
+        for (uint32_t first = s_lo; first < s_hi; first += ngs) {
             mbar_wait(bar0 + stage * 8, phase);
             const uint32_t shdr = pin(hdr0 + stage * hdr_stride);
             uint32_t sdata = data0 + stage * stage_bytes;
@@ -194,8 +195,8 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
                 }
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(bar0 + (sl.stages + stage) * 8);
-            if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
+            if (lane == 0) mbar_arrive(bar0 + (nstages + stage) * 8);
+            if (++stage == nstages) { stage = 0; phase ^= 1; }
         }
     }
     if (~qgood & rowmask & H4) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);

@@ -237,7 +237,7 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
     const TableCfg &t = a.t;
     const StageLayout &sl = a.sl;
     const int nconsumers = g.threads;
-    const uint32_t bar0 = smem_u32(smem_raw + sl.bar_off);
+    const uint32_t bar0 = pin(smem_u32(smem_raw + sl.bar_off));
     const ThreadMap m = make_thread_map(g, t.sj);
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
@@ -258,10 +258,11 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
     }
     const bool live = cur_flag != 0;
     // UNI: group j of a stage starts at (misalignment of the stage's first group) + j * gbytes
-    const uint32_t data0 = smem_u32(smem_raw + sl.data_off) + m.toff + (UNI ? m.grp * g.gbytes : 0);
-    const uint32_t hdr0 = smem_u32(smem_raw + sl.hdr_off) + m.grp * 16;
+    const uint32_t data0 = pin(smem_u32(smem_raw + sl.data_off) + m.toff + (UNI ? m.grp * g.gbytes : 0));
+    const uint32_t hdr0 = pin(smem_u32(smem_raw + sl.hdr_off) + m.grp * 16);
     const uint32_t kgrp = g.ng * g.gbytes;
-    const uint32_t stage_bytes = sl.narr * sl.abytes, abytes = sl.abytes, hdr_stride = sl.ngs * 16, krec = g.ng * 16;
+    const uint32_t stage_bytes = pin(sl.narr * sl.abytes), abytes = pin(sl.abytes), hdr_stride = sl.ngs * 16, krec = g.ng * 16;
+    const uint32_t nstages = pin(sl.stages), ngs = pin(sl.ngs);
     const uint32_t mp = t.mp, md = t.md, revoff = t.revoff, addq = t.addq;
     const uint32_t one = pin(1u), lut_acgt = pin(0x47544341u);  // 'A' 'C' 'T' 'G' by 2-bit code
     uint32_t stage = 0, phase = 0;
@@ -284,7 +285,7 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
             const uint32_t chunk_end = (uint32_t)min((unsigned long long)s_hi,
                                                      (unsigned long long)first + (unsigned long long)t.fold_din * sl.ngs);
             since_pos += t.fold_din;
-            for (; first < chunk_end; first += sl.ngs) {
+            for (; first < chunk_end; first += ngs) {
                 mbar_wait(bar0 + stage * 8, phase);
                 const uint32_t shdr = pin(hdr0 + stage * hdr_stride);
                 uint32_t sdata = data0 + stage * stage_bytes;
@@ -365,8 +366,8 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
                     }
                 }
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar0 + (sl.stages + stage) * 8);  // the stage may be refilled
-                if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
+                if (lane == 0) mbar_arrive(bar0 + (nstages + stage) * 8);  // the stage may be refilled
+                if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
             if (first < s_hi) {
                 consumer_sync(nconsumers);
