@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <stdio.h>
 
 #include "../../include/kbbq_b200.h"
@@ -88,12 +89,13 @@ __host__ __device__ inline int gcd_int(int a, int b) {
 // the 32-groups-per-stage limit).  With several read groups the smallest group is taken: mates of a
 // pair normally share their read group, so a group of one pair is staged once, while a larger group
 // would be staged once per read group present in it.
-inline bool make_geom(int L, int minscore, bool single_rg, Geom *g) {
+inline bool make_geom(int L, int minscore, bool single_rg, int nprod, Geom *g) {
     if (L < 4 || minscore < 0 || minscore >= NQ) return false;
     const int rps = 4 / gcd_int(L, 4);
-    // With several read groups every group of a stage is a copy of its own per array; one warp
-    // issues a bulk copy every ~90 cycles, so four warps share the stages round-robin.
-    const int nprod = single_rg ? 1 : 4;
+    // With several read groups every group of a stage is a copy of its own per array and one warp
+    // issues a bulk copy every ~90 cycles, so `nprod` producer warps share the stages round-robin
+    // (measured, R = 8 x 150 bp build: 2 warps 2.93 ms, 4 warps 2.13 ms, 8 warps 1.74 ms).
+    if (single_rg) nprod = 1;
     const int budget = MAX_THREADS - 32 * nprod;
     int best_g = 0, best_lanes = 0;
     for (int G = rps; G <= MAX_G; G += rps) {

@@ -89,6 +89,18 @@ static bool plan_smem(const Geom &g, int narr, int max_smem, TableCfg *tc, Stage
     return false;
 }
 
+// Geometry + shared-memory plan; with several read groups the producer-warp count falls back from 8
+// when a ring of that many stages does not fit.
+static bool plan_kernel(int L, int R, int minscore, int narr, int max_smem, Geom *g, TableCfg *tc, StageLayout *sl) {
+    int first = 8;
+    if (const char *e = getenv("KBBQ_NPROD")) first = std::max(1, std::min(8, atoi(e)));  // tuning hook
+    for (int nprod = (R == 1 ? 1 : first); nprod >= 1; nprod >>= 1) {
+        if (!make_geom(L, minscore, R == 1, nprod, g)) return false;
+        if (g->row < 65536 && plan_smem(*g, narr, max_smem, tc, sl)) return true;
+    }
+    return false;
+}
+
 template <int KPS>
 static int launch_build_kps(const BuildArgs &a, int grid, size_t smem, cudaStream_t st) {
     auto kern = build_smem_kernel<KPS, true>;
@@ -153,7 +165,7 @@ int kbbq_plan_info(int L, int R, int minscore, int arrays, int max_smem, int *ou
     Geom g;
     TableCfg tc;
     StageLayout sl;
-    if (!make_geom(L, minscore, R == 1, &g) || !plan_smem(g, arrays, max_smem > 0 ? max_smem : 232448, &tc, &sl))
+    if (!plan_kernel(L, R, minscore, arrays, max_smem > 0 ? max_smem : 232448, &g, &tc, &sl))
         return KBBQ_E_ARG;  // the generic kernels would be used
     const int v[10] = {g.G, g.lanes, g.ng, g.threads, g.nprod, sl.kps, sl.stages, tc.drep, sl.total, tc.table_bytes};
     for (int i = 0; i < 10; ++i) out[i] = v[i];
@@ -180,12 +192,11 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
     if (rc) return rc;
 
     Geom g;
-    bool smem_ok = path != 2 && make_geom(L, minscore, R == 1, &g) && g.row < 65536 &&
-                   (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull &&
-                   !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(corr, 16);
     TableCfg tc;
     StageLayout sl;
-    smem_ok = smem_ok && plan_smem(g, 3, max_smem, &tc, &sl);
+    const bool smem_ok = path != 2 && !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(corr, 16) &&
+                         plan_kernel(L, R, minscore, 3, max_smem, &g, &tc, &sl) &&
+                         (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull;
     if (!smem_ok) {
         if (path == 1) return KBBQ_E_ARG;
         BuildGenericArgs a = {seq, qual, corr, rg, second, N, L, R, minscore,
@@ -304,12 +315,11 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
     KBBQ_LAUNCHED();
 
     Geom g;
-    bool smem_ok = path != 2 && make_geom(L, minscore, R == 1, &g) && g.row < 65536 &&
-                   (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull &&
-                   !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(out_qual, 4);
     TableCfg tc;
     StageLayout sl;
-    smem_ok = smem_ok && plan_smem(g, 2, max_smem, &tc, &sl);
+    const bool smem_ok = path != 2 && !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(out_qual, 4) &&
+                         plan_kernel(L, R, minscore, 2, max_smem, &g, &tc, &sl) &&
+                         (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull;
     if (!smem_ok) {
         if (path == 1) return KBBQ_E_ARG;
         ApplyGenericArgs a = {seq, qual, rg, second, out_qual, N, L, R, minscore, nq, w.fold_cyc, w.fold_din, status};
