@@ -43,6 +43,12 @@ extern "C" {
 #define KBBQ_E_CUDA (-2)      /* a CUDA runtime call failed; see kbbq_last_cuda_error() */
 #define KBBQ_E_WORKSPACE (-3) /* workspace too small */
 #define KBBQ_E_DATA (-4)      /* host-API only: device status word was non-zero (see flags) */
+#define KBBQ_E_IO (-5)            /* FASTQ ingest: open / read / write failed */
+#define KBBQ_E_FORMAT (-6)        /* FASTQ ingest: not 4-line records, or sequence / quality lengths differ */
+#define KBBQ_E_RAGGED (-7)        /* FASTQ ingest: reads of unequal length (ValueError on this path) */
+#define KBBQ_E_NAME_FIELD (-8)    /* --infer-rg: a name without a second '_' field (IndexError in the reference) */
+#define KBBQ_E_NAME_RG (-9)       /* --infer-rg: the second '_' field does not start with RG (AssertionError) */
+#define KBBQ_E_NAME_MISMATCH (-10) /* corrected read's name does not start with the read's (AssertionError) */
 
 /* bits of the device status word */
 #define KBBQ_FLAG_QUAL_RANGE 1 /* a quality > 42: IndexError in the reference */
@@ -171,6 +177,34 @@ int kbbq_synth_reads(uint64_t seed, int64_t first_read, int64_t n, int L, int R,
  * KBBQ_E_ARG when the shape falls back to the generic kernels.  Diagnostics / tests.
  */
 int kbbq_plan_info(int L, int R, int minscore, int arrays, int max_smem, int *out);
+
+/*
+ * Host FASTQ ingest / egress: multithreaded replacement of what the
+ * reference does read by read in Python around the hot path -- pysam.FastxFile + get_quality_array
+ * (kbbq/recalibrate.py:56-57,92,141-142), fastq_infer_rg / fastq_infer_secondinpair
+ * (kbbq/compare_reads.py:304-318, first-seen numbering kbbq/recalibrate.py:59-64), the name check of
+ * find_corrected_sites (kbbq/recalibrate.py:17) and the FASTQ print (kbbq/recalibrate.py:152-156).
+ * Host pointers only, no CUDA.  `threads` <= 0: all hardware threads.  4-line records; .gz by suffix.
+ */
+typedef struct kbbq_fastq kbbq_fastq;
+int kbbq_fastq_open(const char *path, int threads, kbbq_fastq **out);
+int kbbq_fastq_open_mem(const void *data, size_t len, int threads, kbbq_fastq **out); /* caller keeps data alive */
+void kbbq_fastq_close(kbbq_fastq *f);
+int64_t kbbq_fastq_num_reads(const kbbq_fastq *f);
+int kbbq_fastq_read_len(const kbbq_fastq *f); /* uniform read length; -1 when reads differ; 0 when empty */
+/* reads [first, first + n) -> seq u8[n*L] (bytes as they are), qual u8[n*L] (ASCII - 33) */
+int kbbq_fastq_pack(const kbbq_fastq *f, int64_t first, int64_t n, uint8_t *seq, uint8_t *qual, int threads);
+/* name of read i = header after '@' up to the first blank (points into the file; not NUL terminated) */
+int kbbq_fastq_name(const kbbq_fastq *f, int64_t i, const char **name, int *len);
+/* second[i] = first '_' field ends in "/2"; rg[i] = 0, or with infer_rg the first-seen number of the
+ * text after the last ':' of the second '_' field; *n_rg = number of read groups (>= 1) */
+int kbbq_fastq_infer(kbbq_fastq *f, int infer_rg, uint16_t *rg, uint8_t *second, int *n_rg, int threads);
+int kbbq_fastq_rg_key(const kbbq_fastq *f, int k, const char **key, int *len); /* after kbbq_fastq_infer */
+/* corr.name.startswith(uncorr.name) for the first n reads; *first_bad = first offender */
+int kbbq_fastq_check_names(const kbbq_fastq *uncorr, const kbbq_fastq *corr, int64_t n, int threads,
+                           int64_t *first_bad);
+/* '@' name '\n' seq '\n+\n' (out_qual + 33) '\n' for reads [first, first + n); out_qual u8[n*L] */
+int kbbq_fastq_write(int fd, const kbbq_fastq *f, int64_t first, int64_t n, const uint8_t *out_qual, int threads);
 
 /* Number of kernel launches this library has issued since load (bench.py's gpu_launches). */
 int64_t kbbq_launch_count(void);

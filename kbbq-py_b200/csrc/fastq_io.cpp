@@ -1,0 +1,393 @@
+// fastq_io.cpp -- host FASTQ ingest / egress of libkbbq_b200.so.
+//
+// Replaces what the reference does read by read in Python around the hot path:
+//   pysam.FastxFile iteration + get_quality_array            (kbbq/recalibrate.py:56-57,92,141-142)
+//   fastq_infer_rg / fastq_infer_secondinpair on every name  (kbbq/compare_reads.py:304-318, kbbq/recalibrate.py:59-64)
+//   the name check of find_corrected_sites                   (kbbq/recalibrate.py:17)
+//   the per-read print of the recalibrated FASTQ             (kbbq/recalibrate.py:152-156)
+// with a multithreaded tokenizer that packs straight into the structure-of-arrays buffers the CUDA
+// entry points take, and a multithreaded formatter.  Plain host C++ (no CUDA): line index by parallel
+// newline counting, records packed in parallel, read-group numbering in first-seen FILE order
+// (thread-local first-seen lists merged in thread order).
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/kbbq_b200.h"
+
+struct kbbq_fastq {
+    const char *data = nullptr;   // whole file (mmap, inflated copy, or caller's buffer)
+    size_t len = 0;
+    void *map = nullptr;          // non-null: munmap on close
+    size_t map_len = 0;
+    std::vector<char> owned;      // inflated .gz
+    std::vector<int64_t> rec;     // rec[i] = offset of record i's '@'; rec[N] = end of data
+    int64_t n = 0;
+    int L = -1;                   // uniform read length, -1 = reads differ, 0 = no reads
+    std::vector<std::string> rg_keys;
+};
+
+namespace {
+
+int n_threads(int want, int64_t work_items) {
+    int t = want > 0 ? want : (int)std::thread::hardware_concurrency();
+    if (t < 1) t = 1;
+    if (t > 64) t = 64;
+    if ((int64_t)t > work_items) t = (int)std::max<int64_t>(1, work_items);
+    return t;
+}
+
+template <class F> void parallel_for(int threads, F f) {  // f(thread index)
+    if (threads <= 1) { f(0); return; }
+    std::vector<std::thread> pool;
+    pool.reserve(threads);
+    for (int t = 0; t < threads; ++t) pool.emplace_back(f, t);
+    for (auto &th : pool) th.join();
+}
+
+inline const char *line_end(const char *p, const char *end) {
+    const char *nl = (const char *)memchr(p, '\n', (size_t)(end - p));
+    return nl ? nl : end;
+}
+
+// the four lines of the record starting at p: [h0,h1) header without '@', [s0,s1) sequence, [q0,q1) quality
+struct Rec { const char *h0, *h1, *s0, *s1, *q0, *q1; bool ok; };
+inline Rec parse_record(const char *p, const char *end) {
+    Rec r{};
+    const char *e = line_end(p, end);
+    r.ok = p < end && *p == '@';
+    r.h0 = p + 1; r.h1 = e;
+    p = e < end ? e + 1 : end;
+    e = line_end(p, end);
+    r.s0 = p; r.s1 = e;
+    p = e < end ? e + 1 : end;
+    e = line_end(p, end);
+    r.ok = r.ok && p < end && *p == '+';
+    p = e < end ? e + 1 : end;
+    e = line_end(p, end);
+    r.q0 = p; r.q1 = e;
+    if (r.h1 > r.h0 && r.h1[-1] == '\r') --r.h1;
+    if (r.s1 > r.s0 && r.s1[-1] == '\r') --r.s1;
+    if (r.q1 > r.q0 && r.q1[-1] == '\r') --r.q1;
+    return r;
+}
+
+// name = header up to the first whitespace (pysam's FastxRecord.name)
+inline const char *name_end(const char *h0, const char *h1) {
+    const char *p = h0;
+    while (p < h1 && *p != ' ' && *p != '\t') ++p;
+    return p;
+}
+
+int build_index(kbbq_fastq *f, int threads) {
+    const char *d = f->data;
+    const size_t len = f->len;
+    if (len == 0) { f->n = 0; f->L = 0; f->rec.assign(1, 0); return KBBQ_OK; }
+    const int T = n_threads(threads, (int64_t)(len >> 20) + 1);
+    std::vector<int64_t> lines(T + 1, 0);
+    auto lo = [&](int t) { return len * (size_t)t / (size_t)T; };
+    parallel_for(T, [&](int t) {
+        int64_t c = 0;
+        const char *p = d + lo(t), *e = d + lo(t + 1);
+        while (p < e) {
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
+            if (!nl) break;
+            ++c;
+            p = nl + 1;
+        }
+        lines[t + 1] = c;
+    });
+    for (int t = 0; t < T; ++t) lines[t + 1] += lines[t];
+    int64_t total = lines[T] + (d[len - 1] != '\n' ? 1 : 0);  // last line without a newline
+    if (total % 4) return KBBQ_E_FORMAT;
+    f->n = total / 4;
+    f->rec.assign((size_t)f->n + 1, (int64_t)len);
+    // line k starts after the k-th newline; record i starts at line 4 i
+    f->rec[0] = 0;
+    parallel_for(T, [&](int t) {
+        int64_t k = lines[t];  // newlines before this chunk
+        const char *p = d + lo(t), *e = d + lo(t + 1);
+        while (p < e) {
+            const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
+            if (!nl) break;
+            ++k;  // the line after this newline has index k
+            if ((k & 3) == 0 && k / 4 < f->n) f->rec[(size_t)(k / 4)] = (int64_t)(nl + 1 - d);
+            p = nl + 1;
+        }
+    });
+    // uniform length?
+    const Rec r0 = parse_record(d + f->rec[0], d + f->rec[1]);
+    if (!r0.ok) return KBBQ_E_FORMAT;
+    f->L = (int)(r0.s1 - r0.s0);
+    const int T2 = n_threads(threads, f->n);
+    std::vector<int> state(T2, 0);  // 1 = format error, 2 = ragged
+    parallel_for(T2, [&](int t) {
+        const int64_t a = f->n * t / T2, b = f->n * (t + 1) / T2;
+        for (int64_t i = a; i < b; ++i) {
+            const Rec r = parse_record(d + f->rec[(size_t)i], d + f->rec[(size_t)i + 1]);
+            if (!r.ok || (r.s1 - r.s0) != (r.q1 - r.q0)) { state[t] |= 1; return; }
+            if ((int)(r.s1 - r.s0) != f->L) state[t] |= 2;
+        }
+    });
+    int st = 0;
+    for (int v : state) st |= v;
+    if (st & 1) return KBBQ_E_FORMAT;
+    if (st & 2) f->L = -1;
+    return KBBQ_OK;
+}
+
+bool ends_with(const std::string &s, const char *suf) {
+    const size_t n = strlen(suf);
+    return s.size() >= n && s.compare(s.size() - n, n, suf) == 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int kbbq_fastq_open_mem(const void *data, size_t len, int threads, kbbq_fastq **out) {
+    if (!out || (!data && len)) return KBBQ_E_ARG;
+    kbbq_fastq *f = new kbbq_fastq;
+    f->data = (const char *)data;
+    f->len = len;
+    const int rc = build_index(f, threads);
+    if (rc) { delete f; return rc; }
+    *out = f;
+    return KBBQ_OK;
+}
+
+int kbbq_fastq_open(const char *path, int threads, kbbq_fastq **out) {
+    if (!path || !out) return KBBQ_E_ARG;
+    kbbq_fastq *f = new kbbq_fastq;
+    if (ends_with(path, ".gz")) {
+        gzFile g = gzopen(path, "rb");
+        if (!g) { delete f; return KBBQ_E_IO; }
+        gzbuffer(g, 1 << 20);
+        std::vector<char> &buf = f->owned;
+        size_t used = 0;
+        for (;;) {
+            if (buf.size() - used < (1u << 22)) buf.resize(std::max<size_t>(buf.size() * 2, 1u << 24));
+            const int got = gzread(g, buf.data() + used, (unsigned)std::min<size_t>(buf.size() - used, 1u << 30));
+            if (got < 0) { gzclose(g); delete f; return KBBQ_E_IO; }
+            if (got == 0) break;
+            used += (size_t)got;
+        }
+        gzclose(g);
+        buf.resize(used);
+        f->data = buf.data();
+        f->len = used;
+    } else {
+        const int fd = open(path, O_RDONLY);
+        if (fd < 0) { delete f; return KBBQ_E_IO; }
+        struct stat st;
+        if (fstat(fd, &st) != 0) { close(fd); delete f; return KBBQ_E_IO; }
+        if (st.st_size > 0) {
+            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+            if (m == MAP_FAILED) { close(fd); delete f; return KBBQ_E_IO; }
+            madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+            f->map = m;
+            f->map_len = (size_t)st.st_size;
+            f->data = (const char *)m;
+            f->len = (size_t)st.st_size;
+        }
+        close(fd);
+    }
+    const int rc = build_index(f, threads);
+    if (rc) { kbbq_fastq_close(f); return rc; }
+    *out = f;
+    return KBBQ_OK;
+}
+
+void kbbq_fastq_close(kbbq_fastq *f) {
+    if (!f) return;
+    if (f->map) munmap(f->map, f->map_len);
+    delete f;
+}
+
+int64_t kbbq_fastq_num_reads(const kbbq_fastq *f) { return f ? f->n : -1; }
+int kbbq_fastq_read_len(const kbbq_fastq *f) { return f ? f->L : -1; }
+
+int kbbq_fastq_pack(const kbbq_fastq *f, int64_t first, int64_t n, uint8_t *seq, uint8_t *qual, int threads) {
+    if (!f || first < 0 || n < 0 || first + n > f->n || (n && (!seq || !qual))) return KBBQ_E_ARG;
+    if (f->L < 0) return KBBQ_E_RAGGED;
+    const int L = f->L;
+    const int T = n_threads(threads, n);
+    std::vector<int> bad(T, 0);
+    parallel_for(T, [&](int t) {
+        const int64_t a = n * t / T, b = n * (t + 1) / T;
+        for (int64_t i = a; i < b; ++i) {
+            const size_t ri = (size_t)(first + i);
+            const Rec r = parse_record(f->data + f->rec[ri], f->data + f->rec[ri + 1]);
+            memcpy(seq + (size_t)i * L, r.s0, (size_t)L);
+            const uint8_t *q = (const uint8_t *)r.q0;
+            uint8_t *o = qual + (size_t)i * L;
+            for (int c = 0; c < L; ++c) {
+                bad[t] |= q[c] < 33;
+                o[c] = (uint8_t)(q[c] - 33);
+            }
+        }
+    });
+    for (int v : bad) if (v) return KBBQ_E_FORMAT;
+    return KBBQ_OK;
+}
+
+int kbbq_fastq_name(const kbbq_fastq *f, int64_t i, const char **name, int *len) {
+    if (!f || i < 0 || i >= f->n || !name || !len) return KBBQ_E_ARG;
+    const Rec r = parse_record(f->data + f->rec[(size_t)i], f->data + f->rec[(size_t)i + 1]);
+    *name = r.h0;
+    *len = (int)(name_end(r.h0, r.h1) - r.h0);
+    return KBBQ_OK;
+}
+
+int kbbq_fastq_infer(kbbq_fastq *f, int infer_rg, uint16_t *rg, uint8_t *second, int *n_rg, int threads) {
+    if (!f || !rg || !second || !n_rg) return KBBQ_E_ARG;
+    const int64_t n = f->n;
+    const int T = n_threads(threads, n);
+    std::vector<std::vector<std::string>> keys(T);
+    std::vector<int> err(T, 0);
+    std::vector<uint32_t> local((size_t)n);
+    parallel_for(T, [&](int t) {
+        const int64_t a = n * t / T, b = n * (t + 1) / T;
+        std::unordered_map<std::string, uint32_t> seen;
+        for (int64_t i = a; i < b; ++i) {
+            const Rec r = parse_record(f->data + f->rec[(size_t)i], f->data + f->rec[(size_t)i + 1]);
+            const char *h1 = name_end(r.h0, r.h1);
+            // first '_' field: second in pair <=> it ends in "/2" (kbbq/compare_reads.py:304-306)
+            const char *u = (const char *)memchr(r.h0, '_', (size_t)(h1 - r.h0));
+            const char *f0e = u ? u : h1;
+            second[i] = (f0e - r.h0 >= 2 && f0e[-2] == '/' && f0e[-1] == '2') ? 1 : 0;
+            if (!infer_rg) { local[(size_t)i] = 0; continue; }
+            // second '_' field must exist and start with "RG"; key = text after its last ':' (:308-318)
+            if (!u) { err[t] |= 1; return; }  // IndexError in the reference
+            const char *f1 = u + 1;
+            const char *u2 = (const char *)memchr(f1, '_', (size_t)(h1 - f1));
+            const char *f1e = u2 ? u2 : h1;
+            if (f1e - f1 < 2 || f1[0] != 'R' || f1[1] != 'G') { err[t] |= 2; return; }  // AssertionError
+            const char *k = f1e;
+            while (k > f1 && k[-1] != ':') --k;
+            std::string key(k, (size_t)(f1e - k));
+            auto it = seen.find(key);
+            if (it == seen.end()) {
+                it = seen.emplace(key, (uint32_t)keys[t].size()).first;
+                keys[t].push_back(key);
+            }
+            local[(size_t)i] = it->second;
+        }
+    });
+    int e = 0;
+    for (int v : err) e |= v;
+    if (e & 1) return KBBQ_E_NAME_FIELD;
+    if (e & 2) return KBBQ_E_NAME_RG;
+    f->rg_keys.clear();
+    if (!infer_rg) {
+        std::fill(rg, rg + n, (uint16_t)0);
+        *n_rg = 1;
+        return KBBQ_OK;
+    }
+    // first-seen order over the file = thread order, then each thread's own first-seen order
+    std::unordered_map<std::string, uint32_t> global;
+    std::vector<std::vector<uint32_t>> remap(T);
+    for (int t = 0; t < T; ++t) {
+        remap[t].resize(keys[t].size());
+        for (size_t k = 0; k < keys[t].size(); ++k) {
+            auto it = global.find(keys[t][k]);
+            if (it == global.end()) {
+                it = global.emplace(keys[t][k], (uint32_t)f->rg_keys.size()).first;
+                f->rg_keys.push_back(keys[t][k]);
+            }
+            remap[t][k] = it->second;
+        }
+    }
+    if (f->rg_keys.size() > 65535) return KBBQ_E_ARG;
+    parallel_for(T, [&](int t) {
+        const int64_t a = n * t / T, b = n * (t + 1) / T;
+        for (int64_t i = a; i < b; ++i) rg[i] = (uint16_t)remap[t][local[(size_t)i]];
+    });
+    *n_rg = (int)std::max<size_t>(1, f->rg_keys.size());
+    return KBBQ_OK;
+}
+
+int kbbq_fastq_rg_key(const kbbq_fastq *f, int k, const char **key, int *len) {
+    if (!f || k < 0 || (size_t)k >= f->rg_keys.size() || !key || !len) return KBBQ_E_ARG;
+    *key = f->rg_keys[(size_t)k].data();
+    *len = (int)f->rg_keys[(size_t)k].size();
+    return KBBQ_OK;
+}
+
+int kbbq_fastq_check_names(const kbbq_fastq *uncorr, const kbbq_fastq *corr, int64_t n, int threads,
+                           int64_t *first_bad) {
+    if (!uncorr || !corr || n < 0 || n > uncorr->n || n > corr->n) return KBBQ_E_ARG;
+    const int T = n_threads(threads, n);
+    std::vector<int64_t> bad(T, -1);
+    parallel_for(T, [&](int t) {
+        const int64_t a = n * t / T, b = n * (t + 1) / T;
+        for (int64_t i = a; i < b; ++i) {
+            const Rec u = parse_record(uncorr->data + uncorr->rec[(size_t)i], uncorr->data + uncorr->rec[(size_t)i + 1]);
+            const Rec c = parse_record(corr->data + corr->rec[(size_t)i], corr->data + corr->rec[(size_t)i + 1]);
+            const size_t ul = (size_t)(name_end(u.h0, u.h1) - u.h0), cl = (size_t)(name_end(c.h0, c.h1) - c.h0);
+            if (cl < ul || memcmp(u.h0, c.h0, ul) != 0) { bad[t] = i; return; }  // corr.name.startswith(uncorr.name)
+        }
+    });
+    for (int64_t v : bad)
+        if (v >= 0) {
+            if (first_bad) *first_bad = v;
+            return KBBQ_E_NAME_MISMATCH;
+        }
+    return KBBQ_OK;
+}
+
+int kbbq_fastq_write(int fd, const kbbq_fastq *f, int64_t first, int64_t n, const uint8_t *out_qual, int threads) {
+    if (!f || fd < 0 || first < 0 || n < 0 || first + n > f->n || (n && !out_qual)) return KBBQ_E_ARG;
+    if (f->L < 0) return KBBQ_E_RAGGED;
+    const int L = f->L;
+    const int T = n_threads(threads, (n >> 12) + 1);
+    const int64_t wave = 1 << 15;  // reads per thread and wave: bounds the formatting buffers
+    std::vector<std::vector<char>> buf(T);
+    for (int64_t base = 0; base < n; base += wave * T) {
+        parallel_for(T, [&](int t) {
+            const int64_t a = std::min(n, base + wave * t), b = std::min(n, a + wave);
+            std::vector<char> &o = buf[t];
+            o.clear();
+            for (int64_t i = a; i < b; ++i) {
+                const size_t ri = (size_t)(first + i);
+                const Rec r = parse_record(f->data + f->rec[ri], f->data + f->rec[ri + 1]);
+                const size_t nl = (size_t)(name_end(r.h0, r.h1) - r.h0);
+                const size_t at = o.size();
+                o.resize(at + nl + 2 * (size_t)L + 6);
+                char *w = o.data() + at;
+                *w++ = '@';
+                memcpy(w, r.h0, nl); w += nl;  // the comment is dropped (kbbq/recalibrate.py:153)
+                *w++ = '\n';
+                memcpy(w, r.s0, (size_t)L); w += L;
+                *w++ = '\n'; *w++ = '+'; *w++ = '\n';
+                const uint8_t *q = out_qual + (size_t)i * L;
+                for (int c = 0; c < L; ++c) w[c] = (char)(q[c] + 33);
+                w[L] = '\n';
+            }
+        });
+        for (int t = 0; t < T; ++t) {
+            const char *p = buf[t].data();
+            size_t left = buf[t].size();
+            while (left) {
+                const ssize_t k = write(fd, p, left);
+                if (k < 0) return KBBQ_E_IO;
+                p += k;
+                left -= (size_t)k;
+            }
+        }
+    }
+    return KBBQ_OK;
+}
+
+}  // extern "C"

@@ -150,6 +150,12 @@ const char *kbbq_strerror(int code) {
     case KBBQ_E_CUDA: return "CUDA runtime error";
     case KBBQ_E_WORKSPACE: return "workspace too small";
     case KBBQ_E_DATA: return "input data error (see status flags)";
+    case KBBQ_E_IO: return "FASTQ file could not be opened, read or written";
+    case KBBQ_E_FORMAT: return "malformed FASTQ (4-line records expected)";
+    case KBBQ_E_RAGGED: return "reads of unequal length";
+    case KBBQ_E_NAME_FIELD: return "read name has no read-group field";
+    case KBBQ_E_NAME_RG: return "read-group field does not start with RG";
+    case KBBQ_E_NAME_MISMATCH: return "corrected read name does not start with the read name";
     default: return "unknown error";
     }
 }

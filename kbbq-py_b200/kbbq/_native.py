@@ -41,6 +41,17 @@ SIGNATURES = {
     "kbbq_marginals_host": (_i, [_vp, _vp, _i, _i] + [_vp] * 5 + [_i]),
     "kbbq_synth_reads": (_i, [C.c_uint64, _i64, _i64, _i, _i] + [_vp] * 5 + [_vp]),
     "kbbq_launch_count": (_i64, []),
+    "kbbq_fastq_open": (_i, [C.c_char_p, _i, C.POINTER(_vp)]),
+    "kbbq_fastq_open_mem": (_i, [_vp, _sz, _i, C.POINTER(_vp)]),
+    "kbbq_fastq_close": (None, [_vp]),
+    "kbbq_fastq_num_reads": (_i64, [_vp]),
+    "kbbq_fastq_read_len": (_i, [_vp]),
+    "kbbq_fastq_pack": (_i, [_vp, _i64, _i64, _vp, _vp, _i]),
+    "kbbq_fastq_name": (_i, [_vp, _i64, C.POINTER(C.c_char_p), C.POINTER(_i)]),
+    "kbbq_fastq_infer": (_i, [_vp, _i, _vp, _vp, C.POINTER(_i), _i]),
+    "kbbq_fastq_rg_key": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_i)]),
+    "kbbq_fastq_check_names": (_i, [_vp, _vp, _i64, _i, C.POINTER(_i64)]),
+    "kbbq_fastq_write": (_i, [_i, _vp, _i64, _i64, _vp, _i]),
     "kbbq_plan_info": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i)]),
 }
 

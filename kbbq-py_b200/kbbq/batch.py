@@ -49,25 +49,44 @@ def infer_rg(names, infer):
 
 
 class ReadBatch:
-    """Packed reads: names, seq/qual/corr u8[N, L], rg u16[N], second u8[N], R, L."""
+    """Packed reads: seq/qual/corr u8[N, L], rg u16[N], second u8[N], R, L; names on demand.
 
-    def __init__(self, names, seq, qual, corr, rg, second, rg_keys):
-        self.names, self.seq, self.qual, self.corr = names, seq, qual, corr
+    Built by the native tokenizer (kbbq.fastx.NativeFastq); `source` keeps the indexed file of the
+    reads so that names are only materialised when somebody asks and the recalibrated FASTQ can be
+    written by the native formatter.
+    """
+
+    def __init__(self, names, seq, qual, corr, rg, second, rg_keys, source=None):
+        self._names, self.seq, self.qual, self.corr = names, seq, qual, corr
         self.rg, self.second, self.rg_keys = rg, second, rg_keys
         self.N, self.L = seq.shape if seq.ndim == 2 else (0, 0)
         self.R = max(1, len(rg_keys))
+        self.source = source
+
+    @property
+    def names(self):
+        if self._names is None:
+            self._names = [self.source.name(i) for i in range(self.N)]
+        return self._names
 
     @classmethod
     def from_fastq(cls, fastq, infer_rg_flag=False, need_corrected=True):
-        names, seq, qual = fastx.read_packed(fastq[0])
+        reads = fastx.NativeFastq(fastq[0])
+        n = reads.N
         corr = None
         if need_corrected:
-            cnames, corr, _ = fastx.read_packed(fastq[1])
-            n = min(len(names), len(cnames))  # zip() in the reference stops at the shorter file
-            names, seq, qual, cnames, corr = names[:n], seq[:n], qual[:n], cnames[:n], corr[:n]
-            for a, b in zip(names, cnames):
-                assert b.startswith(a)  # find_corrected_sites, kbbq/recalibrate.py:17
-            if n and corr.shape != seq.shape:
+            fixed = fastx.NativeFastq(fastq[1])
+            n = min(n, fixed.N)  # zip() in the reference stops at the shorter file
+            reads.check_names(fixed, n)  # find_corrected_sites, kbbq/recalibrate.py:17
+        if n == 0:
+            z = np.zeros((0, 0), np.uint8)
+            return cls([], z, z.copy(), z.copy() if need_corrected else None, np.zeros(0, np.uint16),
+                       np.zeros(0, np.uint8), [0], reads)
+        rg, second, keys = reads.infer(infer_rg_flag)
+        seq, qual = reads.pack(0, n)
+        if need_corrected:
+            if fixed.L != reads.L:
                 raise ValueError("operands could not be broadcast together: corrected reads differ in length")
-        rg, keys = infer_rg(names, infer_rg_flag)
-        return cls(names, seq, qual, corr, rg, infer_second(names), keys)
+            corr, _ = fixed.pack(0, n)
+            fixed.close()
+        return cls(None, seq, qual, corr, rg[:n], second[:n], keys, reads)

@@ -55,8 +55,18 @@ def recalibrate_fastq(fastq, infer_rg=False):
         return
     out = _native.recalibrate_host(batch.seq, batch.qual, batch.corr, batch.rg, batch.second,
                                    batch.L, batch.R, 6)
-    qual_txt = (out + np.uint8(33)).astype(np.uint8)
+    # native formatter straight to the stdout descriptor when there is one; text fallback otherwise
+    # (e.g. sys.stdout replaced by an in-memory stream)
     w = sys.stdout
+    try:
+        fd = w.fileno()
+    except (AttributeError, OSError, ValueError):
+        fd = None
+    if fd is not None and batch.source is not None:
+        w.flush()
+        batch.source.write(fd, out, 0, batch.N)
+        return
+    qual_txt = (out + np.uint8(33)).astype(np.uint8)
     seq = batch.seq
     chunks = []
     for i, name in enumerate(batch.names):
