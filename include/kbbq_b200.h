@@ -94,6 +94,26 @@ int kbbq_delta_q(const int64_t *prior_q_dev, const int64_t *numerrs_dev,
                  const int64_t *numtotal_dev, int64_t n, int64_t *delta_dev, void *stream);
 
 /*
+ * The MAP quality itself for a REAL-valued prior: argmax over q' of prior_dist[|trunc(q' - prior)|] +
+ * binom.logpmf, i.e. gatk_delta_q(prior, ...) + prior as the reference's report writer uses it for
+ * the EmpiricalQuality column of the read-group table, where the prior is EstimatedQReported rounded
+ * to 5 decimals (kbbq/gatk/bqsr.py:293-297; truncation at kbbq/compare_reads.py:245).
+ */
+int kbbq_posterior_q_real(const double *prior_q_dev, const int64_t *numerrs_dev,
+                          const int64_t *numtotal_dev, int64_t n, int64_t *posterior_dev, void *stream);
+
+/*
+ * Calibration benchmark counts: the two np.bincount calls of
+ * benchmark.calculate_q (kbbq/benchmark.py:76-91), total[q] += 1 and errs[q] += error, over n bases,
+ * skipping bases whose skip byte is non-zero (errors[~skips], quals[~skips], kbbq/benchmark.py:102-104).
+ * error = err[i] != 0 when `err` is given, else seq[i] != corr[i] (find_corrected_sites,
+ * kbbq/recalibrate.py:13-20).  `skip` may be NULL.  total / errs are int64[256] and ACCUMULATE.
+ */
+int kbbq_calibration_counts(const uint8_t *qual_dev, const uint8_t *err_dev, const uint8_t *seq_dev,
+                            const uint8_t *corr_dev, const uint8_t *skip_dev, int64_t n,
+                            int64_t *total_dev, int64_t *errs_dev, void *stream);
+
+/*
  * get_delta_qs (kbbq/gatk/applybqsr.py:80-103) for arbitrary axis lengths: q_* is [R][nq],
  * pos_* [R][nq][ncyc], din_* [R][nq][ndin].  Outputs rgdq[R], qdq[R][nq], posdq[R][nq][ncyc],
  * dindq[R][nq][ndin+1] (last dinuc column is the zero pad, :98-101).
@@ -156,6 +176,11 @@ int kbbq_get_delta_qs_host(const int64_t *meanq, const int64_t *rg_errs, const i
                            int64_t *rgdq, int64_t *qdq, int64_t *posdq, int64_t *dindq, int device);
 int kbbq_delta_q_host(const int64_t *prior_q, const int64_t *numerrs, const int64_t *numtotal,
                       int64_t n, int64_t *delta, int device);
+int kbbq_posterior_q_real_host(const double *prior_q, const int64_t *numerrs, const int64_t *numtotal,
+                               int64_t n, int64_t *posterior, int device);
+int kbbq_calibration_counts_host(const uint8_t *qual, const uint8_t *err, const uint8_t *seq,
+                                 const uint8_t *corr, const uint8_t *skip, int64_t n, int64_t *total,
+                                 int64_t *errs, int device);
 int kbbq_marginals_host(const int64_t *pos_errs, const int64_t *pos_total, int L, int R,
                         int64_t *q_errs, int64_t *q_total, int64_t *rg_errs, int64_t *rg_total,
                         int64_t *meanq, int device);

@@ -9,6 +9,7 @@
 
 #include "apply.cuh"
 #include "build.cuh"
+#include "calib.cuh"
 #include "common.cuh"
 #include "model.cuh"
 #include "prepare.cuh"
@@ -269,6 +270,57 @@ int kbbq_delta_q(const int64_t *prior_q, const int64_t *numerrs, const int64_t *
     delta_q_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         (const long long *)prior_q, (const long long *)numerrs, (const long long *)numtotal, n, (long long *)delta);
     KBBQ_LAUNCHED();
+    return KBBQ_OK;
+}
+
+int kbbq_posterior_q_real(const double *prior_q, const int64_t *numerrs, const int64_t *numtotal, int64_t n,
+                          int64_t *posterior, void *stream) {
+    if (n < 0 || (n > 0 && (!prior_q || !numerrs || !numtotal || !posterior))) return KBBQ_E_ARG;
+    if (n == 0) return KBBQ_OK;
+    int device;
+    KBBQ_CUDA(cudaGetDevice(&device));
+    int rc = upload_constants(device);
+    if (rc) return rc;
+    posterior_q_real_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        prior_q, (const long long *)numerrs, (const long long *)numtotal, n, (long long *)posterior);
+    KBBQ_LAUNCHED();
+    return KBBQ_OK;
+}
+
+int kbbq_calibration_counts(const uint8_t *qual, const uint8_t *err, const uint8_t *seq, const uint8_t *corr,
+                            const uint8_t *skip, int64_t n, int64_t *total, int64_t *errs, void *stream) {
+    if (n < 0 || !total || !errs) return KBBQ_E_ARG;
+    if (n == 0) return KBBQ_OK;
+    if (!qual || (!err && (!seq || !corr))) return KBBQ_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    int device, sms = KBBQ_SM_COUNT_FALLBACK;
+    KBBQ_CUDA(cudaGetDevice(&device));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    auto misaligned = [](const void *p) { return p && ((uintptr_t)p & 15u); };
+    CalibArgs a = {qual, err, seq, corr, skip, n, (unsigned long long *)total, (unsigned long long *)errs};
+    if (misaligned(qual) || misaligned(err) || misaligned(skip) || (!err && (misaligned(seq) || misaligned(corr)))) {
+        const long long chunk = 1ll << 31;  // a CTA counter is u32
+        for (long long o = 0; o < n; o += chunk) {
+            CalibArgs c = a;
+            c.qual += o; if (err) c.err += o; else { c.seq += o; c.corr += o; } if (skip) c.skip += o;
+            c.n = std::min<long long>(chunk, n - o);
+            calibration_scalar_kernel<<<sms * 8, CAL_THREADS, 0, st>>>(c);
+            KBBQ_LAUNCHED();
+        }
+        return KBBQ_OK;
+    }
+    const int grid = sms * 3;  // 3 CTAs of 64 KB shared memory per SM
+    const long long chunk = (long long)grid * CAL_THREADS * CAL_MAX_ITERS * 32;  // multiple of 16
+    auto kern = err ? (skip ? calibration_kernel<true, true> : calibration_kernel<true, false>)
+                    : (skip ? calibration_kernel<false, true> : calibration_kernel<false, false>);
+    KBBQ_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, CAL_SMEM));
+    for (long long o = 0; o < n; o += chunk) {
+        CalibArgs c = a;
+        c.qual += o; if (err) c.err += o; else { c.seq += o; c.corr += o; } if (skip) c.skip += o;
+        c.n = std::min<long long>(chunk, n - o);
+        kern<<<grid, CAL_THREADS, CAL_SMEM, st>>>(c);
+        KBBQ_LAUNCHED();
+    }
     return KBBQ_OK;
 }
 
@@ -729,6 +781,50 @@ int kbbq_delta_q_host(const int64_t *prior_q, const int64_t *numerrs, const int6
     KBBQ_CUDA(cudaMemcpy(p + 2 * n, numtotal, (size_t)n * 8, cudaMemcpyHostToDevice));
     KBBQ_TRY(kbbq_delta_q(p, p + n, p + 2 * n, n, p + 3 * n, nullptr));
     KBBQ_CUDA(cudaMemcpy(delta, p + 3 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return KBBQ_OK;
+}
+
+int kbbq_posterior_q_real_host(const double *prior_q, const int64_t *numerrs, const int64_t *numtotal, int64_t n,
+                               int64_t *posterior, int device) {
+    if (n < 0) return KBBQ_E_ARG;
+    if (n == 0) return KBBQ_OK;
+    KBBQ_CUDA(cudaSetDevice(device));
+    DevBuf d;
+    KBBQ_TRY(d.alloc((size_t)n * 4 * 8));
+    int64_t *p = d.as<int64_t>();
+    KBBQ_CUDA(cudaMemcpy(p, prior_q, (size_t)n * 8, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemcpy(p + n, numerrs, (size_t)n * 8, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemcpy(p + 2 * n, numtotal, (size_t)n * 8, cudaMemcpyHostToDevice));
+    KBBQ_TRY(kbbq_posterior_q_real(reinterpret_cast<const double *>(p), p + n, p + 2 * n, n, p + 3 * n, nullptr));
+    KBBQ_CUDA(cudaMemcpy(posterior, p + 3 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    return KBBQ_OK;
+}
+
+int kbbq_calibration_counts_host(const uint8_t *qual, const uint8_t *err, const uint8_t *seq, const uint8_t *corr,
+                                 const uint8_t *skip, int64_t n, int64_t *total, int64_t *errs, int device) {
+    if (n < 0 || !total || !errs) return KBBQ_E_ARG;
+    KBBQ_CUDA(cudaSetDevice(device));
+    const size_t nb = ((size_t)n + 15) / 16 * 16;
+    const int narr = 1 + (err ? 1 : 2) + (skip ? 1 : 0);
+    DevBuf d;
+    KBBQ_TRY(d.alloc(nb * narr + 2 * 256 * 8));
+    uint8_t *p = d.as<uint8_t>();
+    int64_t *cnt = reinterpret_cast<int64_t *>(p + nb * narr);
+    KBBQ_CUDA(cudaMemset(cnt, 0, 2 * 256 * 8));
+    uint8_t *dq = p, *de = nullptr, *ds = nullptr, *dc = nullptr, *dk = nullptr;
+    size_t o = nb;
+    KBBQ_CUDA(cudaMemcpy(dq, qual, (size_t)n, cudaMemcpyHostToDevice));
+    if (err) { de = p + o; o += nb; KBBQ_CUDA(cudaMemcpy(de, err, (size_t)n, cudaMemcpyHostToDevice)); }
+    else {
+        if (!seq || !corr) return KBBQ_E_ARG;
+        ds = p + o; o += nb; dc = p + o; o += nb;
+        KBBQ_CUDA(cudaMemcpy(ds, seq, (size_t)n, cudaMemcpyHostToDevice));
+        KBBQ_CUDA(cudaMemcpy(dc, corr, (size_t)n, cudaMemcpyHostToDevice));
+    }
+    if (skip) { dk = p + o; KBBQ_CUDA(cudaMemcpy(dk, skip, (size_t)n, cudaMemcpyHostToDevice)); }
+    KBBQ_TRY(kbbq_calibration_counts(dq, de, ds, dc, dk, n, cnt, cnt + 256, nullptr));
+    KBBQ_CUDA(cudaMemcpy(total, cnt, 256 * 8, cudaMemcpyDeviceToHost));
+    KBBQ_CUDA(cudaMemcpy(errs, cnt + 256, 256 * 8, cudaMemcpyDeviceToHost));
     return KBBQ_OK;
 }
 

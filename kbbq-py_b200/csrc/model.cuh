@@ -101,13 +101,17 @@ __global__ void marginals_rg_kernel(const long long *q_errs, const long long *q_
 // reference adds the fp64 log-likelihood to an x87 long-double prior, i.e. the sum is rounded to
 // 64 bits; here the sum is kept exact as (hi, lo) and compared lexicographically.  First maximum
 // wins (np.argmax).
-__device__ __forceinline__ int delta_q_cell(int prior, long long errs, long long tot) {
+// `prior` is an integer quality, or (PRIOR = double: the read-group row of a recalibration report,
+// kbbq/gatk/bqsr.py:293-297) a real one: the reference truncates candidate - prior towards zero
+// before taking the absolute value (kbbq/compare_reads.py:245).  Returns the MAP candidate.
+template <typename PRIOR>
+__device__ __forceinline__ int posterior_q_cell(PRIOR prior, long long errs, long long tot) {
     const double k = (double)(errs + 1), mm = (double)((tot + 2) - (errs + 1));
     int best = 0;
     double bh = 0.0, bl = 0.0;
     bool have = false;
     for (int c = 0; c < NQ; ++c) {
-        int d = c - prior;
+        int d = (int)((PRIOR)c - prior);
         d = d < 0 ? -d : d;
         const double pr = d < NQ ? c_prior[d] : -KBBQ_INF;  // prior outside 0..42: IndexError in the reference
         const double a = __dmul_rn(k, c_lnp[c]);
@@ -118,13 +122,22 @@ __device__ __forceinline__ int delta_q_cell(int prior, long long errs, long long
         else { dd s = two_sum(pr, ll); h = s.hi; l = s.lo; }
         if (!have || h > bh || (h == bh && l > bl)) { best = c; bh = h; bl = l; have = true; }
     }
-    return best - prior;
+    return best;
+}
+__device__ __forceinline__ int delta_q_cell(int prior, long long errs, long long tot) {
+    return posterior_q_cell<int>(prior, errs, tot) - prior;
 }
 
 __global__ void delta_q_kernel(const long long *prior, const long long *errs, const long long *tot,
                                long long n, long long *out) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = delta_q_cell((int)prior[i], errs[i], tot[i]);
+}
+
+__global__ void posterior_q_real_kernel(const double *prior, const long long *errs, const long long *tot,
+                                        long long n, long long *out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = posterior_q_cell<double>(prior[i], errs[i], tot[i]);
 }
 
 struct DeltaArgs {

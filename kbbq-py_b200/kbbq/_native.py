@@ -38,6 +38,10 @@ SIGNATURES = {
     "kbbq_apply_host": (_i, [_vp] * 4 + [_i64, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, C.POINTER(_i), _i]),
     "kbbq_get_delta_qs_host": (_i, [_vp] * 9 + [_i, _i, _i, _i] + [_vp] * 4 + [_i]),
     "kbbq_delta_q_host": (_i, [_vp, _vp, _vp, _i64, _vp, _i]),
+    "kbbq_posterior_q_real": (_i, [_vp, _vp, _vp, _i64, _vp, _vp]),
+    "kbbq_posterior_q_real_host": (_i, [_vp, _vp, _vp, _i64, _vp, _i]),
+    "kbbq_calibration_counts": (_i, [_vp] * 5 + [_i64, _vp, _vp, _vp]),
+    "kbbq_calibration_counts_host": (_i, [_vp] * 5 + [_i64, _vp, _vp, _i]),
     "kbbq_marginals_host": (_i, [_vp, _vp, _i, _i] + [_vp] * 5 + [_i]),
     "kbbq_synth_reads": (_i, [C.c_uint64, _i64, _i64, _i, _i] + [_vp] * 5 + [_vp]),
     "kbbq_launch_count": (_i64, []),
@@ -164,6 +168,28 @@ def delta_q_host(prior_q, numerrs, numtotal, device=None):
     check(lib().kbbq_delta_q_host(ptr(prior_q), ptr(numerrs), ptr(numtotal), prior_q.size, ptr(out),
                                   DEVICE if device is None else device))
     return out
+
+
+def posterior_q_real_host(prior_q, numerrs, numtotal, device=None):
+    """MAP quality for real-valued priors (the read-group table of a recalibration report)."""
+    prior_q = np.ascontiguousarray(prior_q, dtype=np.float64)
+    numerrs, numtotal = i64(numerrs), i64(numtotal)
+    out = np.zeros(prior_q.shape, np.int64)
+    check(lib().kbbq_posterior_q_real_host(ptr(prior_q), ptr(numerrs), ptr(numtotal), prior_q.size, ptr(out),
+                                           DEVICE if device is None else device))
+    return out
+
+
+def calibration_counts_host(qual, err=None, seq=None, corr=None, skip=None, device=None):
+    """-> (total int64[256], errs int64[256]): bases and errors per quality, skipped bases left out."""
+    qual = u8(qual).ravel()
+    arrs = [None if a is None else u8(a).ravel() for a in (err, seq, corr, skip)]
+    for a in arrs:
+        assert a is None or a.size == qual.size
+    total, errs = np.zeros(256, np.int64), np.zeros(256, np.int64)
+    check(lib().kbbq_calibration_counts_host(ptr(qual), *[ptr(a) for a in arrs], qual.size, ptr(total), ptr(errs),
+                                             DEVICE if device is None else device))
+    return total, errs
 
 
 def get_delta_qs_host(meanq, rg_errs, rg_total, q_errs, q_total, pos_errs, pos_total, din_errs, din_total,

@@ -123,6 +123,23 @@ class DeviceRecalibrator:
         return tuple(t.cpu().numpy().copy() for t in (self.rgdq, self.qdq, self.posdq, self.dindq))
 
 
+def calibration_counts(qual, err=None, seq=None, corr=None, skip=None, total=None, errs=None):
+    """Bases and errors per quality of device-resident reads (kbbq_calibration_counts, the counting
+    step of kbbq/benchmark.py:76-91).  error = err != 0, or seq != corr when `err` is None; bases with
+    a non-zero `skip` byte are left out.  Accumulates into int64[256] tensors `total` / `errs`
+    (allocated when None) and returns them, so batches -- and, after an all-reduce, ranks -- add up."""
+    lib = _native.lib()
+    dev = qual.device
+    if total is None:
+        total = torch.zeros(256, dtype=torch.int64, device=dev)
+    if errs is None:
+        errs = torch.zeros(256, dtype=torch.int64, device=dev)
+    rc = lib.kbbq_calibration_counts(_p(qual), _p(err), _p(seq), _p(corr), _p(skip), qual.numel(), _p(total),
+                                     _p(errs), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+    _native.check(rc)
+    return total, errs
+
+
 def synth_reads(seed, first_read, n, L, R, device=None, want_corr=True):
     """Counter-based synthetic reads generated on the GPU (kbbq_synth_reads): bench / test input."""
     lib = _native.lib()

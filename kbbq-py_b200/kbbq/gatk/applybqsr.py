@@ -1,11 +1,85 @@
-"""Mirror of the hot-path part of the reference's kbbq/gatk/applybqsr.py: get_delta_qs (:80-103).
+"""Mirror of the hot-path part of the reference's kbbq/gatk/applybqsr.py: get_delta_qs (:80-103)
+and the report reader table_to_vectors (:14-44).
 
-Out of scope (BAM input / GATK report): table_to_vectors, bamread_cycle_covariates,
-bamread_dinuc_covariates, recalibrate_bamread.
+Out of scope (BAM input, needs pysam): bamread_cycle_covariates, bamread_dinuc_covariates,
+recalibrate_bamread.
 """
 import numpy as np
 
 from .. import _native
+from .. import compare_reads as utils
+
+
+def table_to_vectors(table, rg_order, maxscore=42):
+    """The nine recalibration vectors of a RecalibrationReport (kbbq/gatk/applybqsr.py:14-44).
+
+    -> (meanq float64 [rg] = EstimatedQReported, global_errs, global_total [rg], q_errs, q_total
+    [rg, maxscore + 1], pos_errs, pos_total [rg, maxscore + 1, 2 * seqlen], dinuc_errs, dinuc_total
+    [rg, maxscore + 1, 16]), counts int64, cells the report does not list are 0.  seqlen is the
+    largest cycle in the report; cycle c > 0 sits at c - 1 and cycle -c at 2 * seqlen - c, the layout
+    of the table build.  Rows of read groups outside `rg_order` or qualities above maxscore are
+    ignored.  The reference does this with pandas reindex / fillna over the full index product;
+    here the listed rows are scattered into zero arrays.
+    """
+    rg_order = list(rg_order)
+    R, nq = len(rg_order), maxscore + 1
+    rg_index = {str(rg): i for i, rg in enumerate(rg_order)}
+
+    def rg_codes(values):
+        return np.array([rg_index.get(str(v), -1) for v in values], dtype=np.int64)
+
+    t2 = table.tables[2].data.reset_index()
+    meanq = np.full(R, np.nan, dtype=np.float64)
+    global_errs, global_total = np.zeros(R, np.int64), np.zeros(R, np.int64)
+    g = rg_codes(t2['ReadGroup'].to_numpy())
+    missing = sorted(set(range(R)) - set(g[g >= 0].tolist()))
+    if missing:
+        # the reference fails converting the NaN of a missing row to int64 (:19)
+        raise ValueError("read group %r is not in the report" % (rg_order[missing[0]],))
+    ok = g >= 0
+    meanq[g[ok]] = t2['EstimatedQReported'].to_numpy(dtype=np.float64)[ok]
+    global_errs[g[ok]] = t2['Errors'].to_numpy(dtype=np.float64)[ok].astype(np.int64)
+    global_total[g[ok]] = t2['Observations'].to_numpy(dtype=np.int64)[ok]
+
+    t3 = table.tables[3].data.reset_index()
+    q_errs, q_total = np.zeros((R, nq), np.int64), np.zeros((R, nq), np.int64)
+    g, q = rg_codes(t3['ReadGroup'].to_numpy()), t3['QualityScore'].to_numpy(dtype=np.int64)
+    ok = (g >= 0) & (q >= 0) & (q < nq)
+    q_errs[g[ok], q[ok]] = t3['Errors'].to_numpy(dtype=np.float64)[ok].astype(np.int64)
+    q_total[g[ok], q[ok]] = t3['Observations'].to_numpy(dtype=np.int64)[ok]
+
+    t4 = table.tables[4].data.reset_index()
+    g, q = rg_codes(t4['ReadGroup'].to_numpy()), t4['QualityScore'].to_numpy(dtype=np.int64)
+    name = np.asarray(t4['CovariateName'].to_numpy(), dtype=str)
+    value = np.asarray(t4['CovariateValue'].to_numpy(), dtype=str)
+    errs = t4['Errors'].to_numpy(dtype=np.float64).astype(np.int64)
+    obs = t4['Observations'].to_numpy(dtype=np.int64)
+    ok = (g >= 0) & (q >= 0) & (q < nq)
+
+    cyc = ok & (name == 'Cycle')
+    if not np.any(cyc):
+        raise KeyError('Cycle')  # .loc[..., 'Cycle'] in the reference (:28)
+    c = value[cyc].astype(np.int64)
+    # the reference takes the largest cycle (:30), which only works when read-1 cycles reach the full
+    # length; the largest magnitude is the same number there and also right for read-2-only reports
+    seqlen = int(np.abs(c).max())
+    if np.any(c == 0):
+        raise ValueError("malformed cycle values in the report")
+    pos_errs, pos_total = np.zeros((R, nq, 2 * seqlen), np.int64), np.zeros((R, nq, 2 * seqlen), np.int64)
+    slot = np.where(c > 0, c - 1, 2 * seqlen + c)
+    pos_errs[g[cyc], q[cyc], slot] = errs[cyc]
+    pos_total[g[cyc], q[cyc], slot] = obs[cyc]
+
+    dinuc_to_int = utils.Dinucleotide.dinuc_to_int
+    ndin = len(dinuc_to_int)
+    dinuc_errs, dinuc_total = np.zeros((R, nq, ndin), np.int64), np.zeros((R, nq, ndin), np.int64)
+    ctx = ok & (name == 'Context')
+    d = np.array([dinuc_to_int.get(v, -1) for v in value[ctx]], dtype=np.int64)
+    known = d >= 0  # contexts with an N are not part of the index product the reference reindexes to (:38)
+    dinuc_errs[g[ctx][known], q[ctx][known], d[known]] = errs[ctx][known]
+    dinuc_total[g[ctx][known], q[ctx][known], d[known]] = obs[ctx][known]
+
+    return meanq, global_errs, global_total, q_errs, q_total, pos_errs, pos_total, dinuc_errs, dinuc_total
 
 
 def get_delta_qs(meanq, rg_errs, rg_total, q_errs, q_total, pos_errs, pos_total, dinuc_errs, dinuc_total):

@@ -12,6 +12,29 @@ import sys
 REFERENCE_ROOT = os.environ.get("KBBQ_REFERENCE_ROOT", "/root/reference")
 
 
+def _pandas_aliases(pd):
+    """pandas API the reference's report code (kbbq/gatk/bqsr.py:227-366, kbbq/recaltable.py) relies on
+    and pandas >= 2 removed: DataFrame.append, object-dtype strings, fillna(downcast='infer')."""
+    import numpy as np
+    if not hasattr(pd.DataFrame, "append"):
+        pd.DataFrame.append = lambda self, other: pd.concat([self, other])
+    try:
+        pd.set_option("future.infer_string", False)
+    except Exception:
+        pass
+    if not getattr(pd.Series.fillna, "_kbbq_shim", False):
+        orig = pd.Series.fillna
+
+        def fillna(self, value=None, downcast=None, **kw):
+            out = orig(self, value, **kw)
+            if downcast == "infer" and out.dtype.kind == "f" and len(out) and \
+                    np.all(np.isfinite(out.values)) and np.all(out.values == np.floor(out.values)):
+                out = out.astype(np.int64)
+            return out
+        fillna._kbbq_shim = True
+        pd.Series.fillna = fillna
+
+
 def load():
     """Return (recalibrate, compare_reads, applybqsr) modules of the reference."""
     if not os.path.isdir(os.path.join(REFERENCE_ROOT, "kbbq")):
@@ -26,6 +49,7 @@ def load():
                           ("NINF", -np.inf), ("object", object)):
         if not hasattr(np, alias):
             setattr(np, alias, target)
+    _pandas_aliases(pandas)
     here = os.path.dirname(os.path.abspath(__file__))
     # a product package named `kbbq` may already be imported; the reference must win here
     for name in [m for m in sys.modules if m == "kbbq" or m.startswith("kbbq.")]:
