@@ -80,7 +80,7 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
     const uint32_t hdr0 = pin(smem_u32(smem_raw + sl.hdr_off) + m.grp * 16);
     const uint32_t stage_bytes = pin(sl.narr * sl.abytes), abytes = pin(sl.abytes), hdr_stride = sl.ngs * 16, krec = g.ng * 16;
     const uint32_t nstages = pin(sl.stages), ngs = pin(sl.ngs);
-    const uint32_t mp = t.mp, md = t.md, revoff = t.revoff, addq = t.addq, gbytes = g.gbytes;
+    const uint32_t revoff = t.revoff, addq = t.addq, gbytes = g.gbytes;
     const uint32_t addnq = (uint32_t)(128 - a.nq) * ONE4;  // q + this has bit 7 set iff q >= nq (q < 128)
     uint32_t stage = 0, phase = 0;
     uint32_t qgood = 0xFFFFFFFFu;
@@ -159,19 +159,18 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
                 const uint32_t vraw = w5 & nu & ~qw;
                 const uint32_t vm8 = prmt(vraw, 0u, selv);  // 0xFF for owned bytes with minscore - 1 <= q < nq
                 const uint32_t qrow4 = w5 & vm8 & 0x3F3F3F3Fu;
-                const uint32_t q4p = qrow4 * mp;
                 const uint32_t pw = prmt(pb, sw, 0x6540u);
                 const uint32_t d4 = (pw & 0x06060606u) * 4u + (sw & 0x06060606u);
                 const uint32_t nm8 = prmt((sw | pw) * 16u, 0xFFFFFFFFu, seln);
-                const uint32_t q4d = (qrow4 & ~nm8) * md;
+                const uint32_t qd = qrow4 & ~nm8;
+                const uint32_t x01 = prmt(d4, qd, 0x5140u), x23 = prmt(d4, qd, 0x7362u);  // see build.cuh
 
                 uint32_t v[4];
 #pragma unroll
                 for (int b = 0; b < 4; ++b) {
-                    const uint32_t pa = __dp4a(q4p, t.ohp[b], aeff[b]);
-                    uint32_t da = __dp4a(d4, t.ohd[b], din_base);
-                    da = __dp4a(q4d, t.ohq[b], da);
-                    da = __dp4a(q4d, t.ohq[b], da);
+                    const uint32_t pa = (b & 2) ? __dp2a_hi(t.cyc16[b & 1], qrow4, aeff[b]) : __dp2a_lo(t.cyc16[b & 1], qrow4, aeff[b]);
+                    const uint32_t xb = (b & 2) ? x23 : x01;
+                    const uint32_t da = (b & 1) ? __dp2a_hi(t.din16, xb, din_base) : __dp2a_lo(t.din16, xb, din_base);
                     uint32_t x, y;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(x) : "r"(pa));
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(y) : "r"(da));

@@ -13,9 +13,11 @@
 //   * one thread owns one (row, 32-bit word) position of a group of G reads (common.cuh), i.e.
 //     four fixed cycles of one read; lanes of a warp own consecutive words, so at every byte
 //     position they hit consecutive banks of the cycle table whatever the qualities are;
-//   * table addresses come from dot products: IDP.4A of the byte-parallel row index with a
-//     one-hot byte constant extracts byte b AND scales it by the row stride in one FMA-pipe
-//     instruction -- no per-byte extract, select or multiply on the ALU pipe;
+//   * table addresses come from dot products: IDP.2A (16-bit x 8-bit, same rate as IDP.4A) of a
+//     16-bit stride constant with the byte-parallel row-index word extracts byte b AND scales it
+//     by the row stride in one FMA-pipe instruction; for the dinucleotide table the (slot, row)
+//     bytes of a base are interleaved by one PRMT per two bases, so slot * slot stride + row * row
+//     stride is ONE instruction per base -- no per-byte extract, select or multiply on the ALU pipe;
 //   * bases that must not be tallied (q < minscore, bytes of a neighbouring read, invalid dinuc)
 //     get row index 0 (a trash row) through byte masks made by sign-replicating PRMTs whose
 //     selectors are per-thread constants (they also encode which bytes of the word the thread owns
@@ -46,40 +48,33 @@ constexpr int MAX_WARPS = MAX_THREADS / 32;
 // Row index of a base: qrow = q - (minscore - 1) for minscore <= q <= 42, 0 (trash) otherwise.
 struct TableCfg {
     int nrows;        // 44 - minscore (row 0 = trash)
-    int mp, kp;       // cycle table: byte-parallel qrow * mp, then * kp (both <= 255); row stride rs = mp * kp
-    int rs;           // bytes, multiple of 128
+    int rs;           // cycle table: row stride in bytes, multiple of 128
     int sj;           // plane stride in words: cell of cycle c at word (c & 3) * sj + (c >> 2)
     int revoff;       // bytes from the read-1 table to the read-2 table = nrows * rs
-    int md, k1, k2;   // dinuc table: qrow * md, then * (k1 + k2); row stride dq = md * (k1 + k2)
-    int dq;           // bytes, multiple of 128, >= 16 * drep * 4
+    int dq;           // dinuc table: row stride in bytes = 16 slots x drep replicas x 4
     int drep;         // replicas of the dinuc table (32: bank == lane; 16: lanes l and l + 16 share one)
     int pos_off, din_off;            // byte offsets from the start of dynamic shared memory
     int table_bytes;  // zeroed at the start of every segment
     int flush_pos;    // iterations between flushes of the cycle table
     int fold_din;     // iterations between folds of the dinuc replicas
     uint32_t addq;    // 0x81 - minscore in every byte: (q + addq) has bit 7 set iff q >= minscore - 1
-    // one-hot byte constants, k << 8b: IDP.4A with one of them = (byte b of the other operand) * k.
-    // Kept in the kernel parameters so that the instruction reads them straight from the constant bank.
-    uint32_t ohp[4];  // kp: cycle-table row
-    uint32_t ohq[4];  // k1 (= k2): dinuc-table row, applied twice
-    uint32_t ohd[4];  // drep * 2: the slot byte holds 2 * slot, a slot is drep x 4 B
-    uint32_t ohe[4];  // 255: mismatch byte 0xFF -> 65025
+    // 16-bit constants of the IDP.2A address arithmetic (dp2a: a.h0 * b.b0 + a.h1 * b.b1 for .lo, bytes 2, 3 for
+    // .hi).  Kept in the kernel parameters so that the instruction reads them straight from the constant bank.
+    uint32_t cyc16[2];  // {rs, rs << 16}: with the row-index word as b this is (byte 0 or 2) * rs, (byte 1 or 3) * rs
+    uint32_t din16;     // (2 * drep) | dq << 16: b = (2 * slot, row) byte pairs -> slot * drep * 4 + row * dq
+    uint32_t ohe[4];    // 255 << 8b: IDP.4A with the mismatch byte mask 0xFF -> 65025
 };
 
 inline bool make_table_cfg(const Geom &g, int kps, int drep, TableCfg *t) {
-    if (g.minscore < 1) return false;  // row index * 6 must fit a byte
+    if (g.minscore < 1) return false;  // row 0 is the trash row
+    if (drep != 32 && drep != 16) return false;
     t->nrows = NQ + 1 - g.minscore;
     t->sj = (g.L + 3) / 4;
-    const int need = 16 * t->sj;                       // bytes of one row: 4 planes x sj words
-    const int rs = (need + 127) / 128 * 128;
-    if (rs <= 896) { t->mp = 4; t->kp = rs / 4; t->rs = rs; }
-    else if (rs <= 1152) { t->mp = 6; t->kp = 192; t->rs = 1152; }
-    else return false;
+    t->rs = (16 * t->sj + 127) / 128 * 128;            // 4 planes x sj words, rounded to whole bank rows
+    if (t->rs > 1152) return false;                      // L <= 288: longer reads take the generic kernels
     t->revoff = t->nrows * t->rs;
     t->drep = drep;
-    if (drep == 32) { t->md = 6; t->k1 = 192; t->k2 = 192; t->dq = 6 * 384; }   // 2304 B >= 2048, multiple of 128
-    else if (drep == 16) { t->md = 4; t->k1 = 128; t->k2 = 128; t->dq = 1024; }
-    else return false;
+    t->dq = DIN_SLOTS * drep * 4;
     t->pos_off = 0;
     t->din_off = 2 * t->revoff;
     t->table_bytes = t->din_off + t->nrows * t->dq;
@@ -88,12 +83,10 @@ inline bool make_table_cfg(const Geom &g, int kps, int drep, TableCfg *t) {
     t->flush_pos = (int)((ERR_UNIT - 1) / (uint32_t)(kps * g.ng * g.G));
     t->fold_din = (int)((ERR_UNIT - 1) / (uint32_t)(kps * 4 * (g.threads / drep)));
     t->addq = (uint32_t)(0x81 - g.minscore) * ONE4;
-    for (int b = 0; b < 4; ++b) {
-        t->ohp[b] = (uint32_t)t->kp << (8 * b);
-        t->ohq[b] = (uint32_t)t->k1 << (8 * b);
-        t->ohd[b] = (uint32_t)(drep * 4 / 2) << (8 * b);
-        t->ohe[b] = 255u << (8 * b);
-    }
+    t->cyc16[0] = (uint32_t)t->rs;
+    t->cyc16[1] = (uint32_t)t->rs << 16;
+    t->din16 = (uint32_t)(drep * 2) | ((uint32_t)t->dq << 16);
+    for (int b = 0; b < 4; ++b) t->ohe[b] = 255u << (8 * b);
     return true;
 }
 
@@ -263,7 +256,7 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
     const uint32_t kgrp = g.ng * g.gbytes;
     const uint32_t stage_bytes = pin(sl.narr * sl.abytes), abytes = pin(sl.abytes), hdr_stride = sl.ngs * 16, krec = g.ng * 16;
     const uint32_t nstages = pin(sl.stages), ngs = pin(sl.ngs);
-    const uint32_t mp = t.mp, md = t.md, revoff = t.revoff, addq = t.addq;
+    const uint32_t revoff = t.revoff, addq = t.addq;
     const uint32_t one = pin(1u), lut_acgt = pin(0x47544341u);  // 'A' 'C' 'T' 'G' by 2-bit code
     uint32_t stage = 0, phase = 0;
     uint32_t qgood = 0xFFFFFFFFu, bbad = 0;
@@ -333,14 +326,15 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
                     const uint32_t vraw = w5 & nu & ~qw;        // bit 7 <=> minscore - 1 <= q <= 42
                     const uint32_t vm8 = prmt(vraw, 0u, selv);  // 0xFF for owned bytes in range
                     const uint32_t qrow4 = w5 & vm8 & 0x3F3F3F3Fu;  // 0 = trash row
-                    const uint32_t q4p = qrow4 * mp;
 
                     // ---- dinucleotide slot, byte-parallel: 2 * (4 * code(prev) + code(cur)), code = (b >> 1) & 3 ----
                     const uint32_t pw = prmt(pb, sw, 0x6540u);  // previous base of every byte
                     const uint32_t d4 = (pw & 0x06060606u) * 4u + (sw & 0x06060606u);
                     // 'N' is the only accepted base with bit 3 set; cycle 0 and foreign bytes take 0xFF from the selector
                     const uint32_t nm8 = prmt((sw | pw) * 16u, 0xFFFFFFFFu, seln);
-                    const uint32_t q4d = (qrow4 & ~nm8) * md;
+                    // (2 * slot, dinuc row) byte pairs of bases 0, 1 and 2, 3: one IDP.2A per base gives the address
+                    const uint32_t qd = qrow4 & ~nm8;
+                    const uint32_t x01 = prmt(d4, qd, 0x5140u), x23 = prmt(d4, qd, 0x7362u);
 
                     // ---- mismatch: 0xFF where the corrected base differs (bases are 7-bit) ----
                     const uint32_t e8 = prmt((sw ^ cw) + 0x7F7F7F7Fu, 0u, 0xBA98u);
@@ -357,10 +351,9 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
 #pragma unroll
                     for (int b = 0; b < 4; ++b) {
                         const uint32_t inc = __dp4a(e8, t.ohe[b], one);
-                        const uint32_t pa = __dp4a(q4p, t.ohp[b], aeff[b]);
-                        uint32_t da = __dp4a(d4, t.ohd[b], din_base);
-                        da = __dp4a(q4d, t.ohq[b], da);
-                        da = __dp4a(q4d, t.ohq[b], da);
+                        const uint32_t pa = (b & 2) ? __dp2a_hi(t.cyc16[b & 1], qrow4, aeff[b]) : __dp2a_lo(t.cyc16[b & 1], qrow4, aeff[b]);
+                        const uint32_t xb = (b & 2) ? x23 : x01;
+                        const uint32_t da = (b & 1) ? __dp2a_hi(t.din16, xb, din_base) : __dp2a_lo(t.din16, xb, din_base);
                         red_shared_add(pa, inc);
                         red_shared_add(da, inc);
                     }
