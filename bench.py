@@ -262,10 +262,16 @@ def run_b200(args):
         dt = parallel.max_over_ranks(dt, dev)
         if not torch.equal(h_out.to(dev), out):
             raise SystemExit("bench.py: host-buffer path and device path disagree")
+        # bytes that cross PCIe per step: kbbq_recalibrate_host sends the corrected reads as a 1-bit-per-base
+        # mismatch map made by the host cores inside the call (csrc/host_pack.cpp) unless KBBQ_HOST_NO_BITMAP=1;
+        # the device-API path of the multi-rank step copies all three arrays
+        bitmap = world == 1 and os.environ.get("KBBQ_HOST_NO_BITMAP", "0") in ("", "0")
+        corr_bytes = (N * L + 31) // 32 * 4 if bitmap else N * L
         e2e = {"value": world * N * L * ke / dt, "unit": UNIT,
-               "h2d_bytes_per_step": 3 * N * L + N + (2 * N if R > 1 else 0), "d2h_bytes_per_step": N * L,
+               "h2d_bytes_per_step": 2 * N * L + corr_bytes + N + (2 * N if R > 1 else 0), "d2h_bytes_per_step": N * L,
+               "host_input_bytes_per_step": 3 * N * L + N + (2 * N if R > 1 else 0),
                "ms_per_step": 1e3 * dt / ke, "steps": ke,
-               "api": api}
+               "api": api + ("; corrected reads cross PCIe as a mismatch bit map" if bitmap else "")}
 
     if world > 1:
         dist.barrier()

@@ -231,6 +231,14 @@ int kbbq_fastq_check_names(const kbbq_fastq *uncorr, const kbbq_fastq *corr, int
 /* '@' name '\n' seq '\n+\n' (out_qual + 33) '\n' for reads [first, first + n); out_qual u8[n*L] */
 int kbbq_fastq_write(int fd, const kbbq_fastq *f, int64_t first, int64_t n, const uint8_t *out_qual, int threads);
 
+/*
+ * Host helper of the host-buffer entry points: bit (i mod 32) of bits[i / 32] = (seq[i] != corr[i]),
+ * i.e. find_corrected_sites (kbbq/recalibrate.py:13-20) over n packed bases, multithreaded (threads
+ * <= 0: all hardware threads).  bits holds ceil(n / 32) words.  kbbq_recalibrate_host sends this map
+ * over PCIe instead of the corrected reads (1/8 of the bytes) unless KBBQ_HOST_NO_BITMAP=1.
+ */
+int kbbq_host_mismatch_bits(const uint8_t *seq, const uint8_t *corr, int64_t n, uint32_t *bits, int threads);
+
 /* Number of kernel launches this library has issued since load (bench.py's gpu_launches). */
 int64_t kbbq_launch_count(void);
 

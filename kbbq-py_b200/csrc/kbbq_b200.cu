@@ -431,6 +431,26 @@ struct DevBuf {
     template <class T> T *as() { return (T *)p; }
 };
 
+// corr[i] = seq[i] ^ bit i of the mismatch map: a byte array that differs from seq exactly where the
+// corrected read did (host_pack.cpp), which is all the build kernel looks at.  16 bases per thread.
+__global__ void expand_corr_kernel(const uint8_t *seq, const uint32_t *bits, uint8_t *corr, long long n) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i = t * 16;
+    if (i >= n) return;
+    const uint32_t m = (bits[t >> 1] >> ((t & 1) * 16)) & 0xFFFFu;
+    if (i + 16 <= n) {
+        uint4 v = *reinterpret_cast<const uint4 *>(seq + i);
+        // bits 0..3 of a nibble -> bit 0 of bytes 0..3
+        v.x ^= ((m & 0xFu) * 0x00204081u) & 0x01010101u;
+        v.y ^= (((m >> 4) & 0xFu) * 0x00204081u) & 0x01010101u;
+        v.z ^= (((m >> 8) & 0xFu) * 0x00204081u) & 0x01010101u;
+        v.w ^= (((m >> 12) & 0xFu) * 0x00204081u) & 0x01010101u;
+        *reinterpret_cast<uint4 *>(corr + i) = v;
+    } else {
+        for (int j = 0; i + j < n; ++j) corr[i + j] = seq[i + j] ^ (uint8_t)((m >> j) & 1u);
+    }
+}
+
 // Device memory and streams kbbq_recalibrate_host keeps between calls (per device): allocating
 // and freeing several GB per call costs from tens of milliseconds to a second (driver page
 // scrubbing), far more than the kernels.  Grown on demand, released by kbbq_host_release().
@@ -439,6 +459,15 @@ struct HostArena {
     void *base = nullptr;
     size_t cap = 0;
     cudaStream_t copy = nullptr, comp = nullptr;
+    void *pinned = nullptr;   // page-locked staging for the mismatch bit map
+    size_t pinned_cap = 0;
+    int ensure_pinned(size_t bytes) {
+        if (bytes <= pinned_cap) return KBBQ_OK;
+        if (pinned) { KBBQ_CUDA(cudaFreeHost(pinned)); pinned = nullptr; pinned_cap = 0; }
+        KBBQ_CUDA(cudaHostAlloc(&pinned, bytes, cudaHostAllocDefault));
+        pinned_cap = bytes;
+        return KBBQ_OK;
+    }
     int ensure(size_t bytes) {
         if (bytes <= cap) return KBBQ_OK;
         if (base) { KBBQ_CUDA(cudaFree(base)); base = nullptr; cap = 0; }
@@ -453,6 +482,8 @@ struct HostArena {
     }
     void release() {
         if (base) cudaFree(base);
+        if (pinned) cudaFreeHost(pinned);
+        pinned = nullptr; pinned_cap = 0;
         if (copy) cudaStreamDestroy(copy);
         if (comp) cudaStreamDestroy(comp);
         base = nullptr; cap = 0; copy = comp = nullptr;
@@ -514,7 +545,7 @@ int kbbq_host_release(int device) {
     if (device < 0 || device >= 64) return KBBQ_E_ARG;
     HostArena &A = g_arena[device];
     std::lock_guard<std::mutex> lock(A.mu);
-    if (A.base || A.copy || A.comp) {
+    if (A.base || A.copy || A.comp || A.pinned) {
         KBBQ_CUDA(cudaSetDevice(device));
         A.release();
     }
@@ -554,12 +585,22 @@ int kbbq_recalibrate_host(const uint8_t *seq, const uint8_t *qual, const uint8_t
     const int64_t buf_reads = resident ? N : chunk;
     size_t ws_bytes = 0;
     KBBQ_TRY(kbbq_workspace_bytes(chunk, L, R, &ws_bytes));
+    // the corrected reads cross PCIe as a mismatch bit map made by the host cores (host_pack.cpp)
+    bool use_bits = true;
+    if (const char *e = getenv("KBBQ_HOST_NO_BITMAP")) use_bits = atoi(e) == 0;
+    const size_t bits_words = ((size_t)chunk * L + 31) / 32 + 4;   // per chunk
+    uint32_t *h_bits = nullptr;
+    if (use_bits && N > 0) {
+        KBBQ_TRY(A.ensure_pinned((size_t)nchunks * bits_words * 4));
+        h_bits = (uint32_t *)A.pinned;
+    }
 
     // carve everything out of the arena: measure, grow if needed, carve for real
     int64_t *d_tab = nullptr, *d_model = nullptr;
     int *d_status = nullptr;
     uint8_t *d_seq[2] = {}, *d_qual[2] = {}, *d_corr[2] = {}, *d_out[2] = {}, *d_sec[2] = {};
     uint16_t *d_rg[2] = {};
+    uint32_t *d_bits[2] = {};
     void *d_ws = nullptr;
     for (int pass = 0; pass < 2; ++pass) {
         Carver c(pass ? A.base : nullptr);
@@ -575,6 +616,7 @@ int kbbq_recalibrate_host(const uint8_t *seq, const uint8_t *qual, const uint8_t
         for (int b = 0; b < 2; ++b) {  // corrected reads and outputs always rotate through two chunk buffers
             d_corr[b] = c.take<uint8_t>((size_t)chunk * L + 16);
             d_out[b] = c.take<uint8_t>((size_t)chunk * L + 16);
+            d_bits[b] = use_bits ? c.take<uint32_t>(bits_words) : nullptr;
         }
         d_ws = c.take<uint8_t>(ws_bytes);
         if (!pass) KBBQ_TRY(A.ensure(c.off));
@@ -596,11 +638,24 @@ int kbbq_recalibrate_host(const uint8_t *seq, const uint8_t *qual, const uint8_t
         if (k >= 2) KBBQ_CUDA(cudaStreamWaitEvent(s_copy, consumed[k - 2], 0));
         KBBQ_CUDA(cudaMemcpyAsync(d_seq[b] + doff, seq + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, s_copy));
         KBBQ_CUDA(cudaMemcpyAsync(d_qual[b] + doff, qual + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, s_copy));
-        KBBQ_CUDA(cudaMemcpyAsync(d_corr[cb], corr + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, s_copy));
         if (rg) KBBQ_CUDA(cudaMemcpyAsync(d_rg[b] + roff, rg + r0, (size_t)n * 2, cudaMemcpyHostToDevice, s_copy));
         if (second) KBBQ_CUDA(cudaMemcpyAsync(d_sec[b] + roff, second + r0, (size_t)n, cudaMemcpyHostToDevice, s_copy));
+        if (use_bits) {
+            // the host cores compare while the copy engine is busy with seq and qual of this chunk
+            uint32_t *hb = h_bits + (size_t)k * bits_words;
+            KBBQ_TRY(kbbq_host_mismatch_bits(seq + (size_t)r0 * L, corr + (size_t)r0 * L, n * L, hb, 0));
+            KBBQ_CUDA(cudaMemcpyAsync(d_bits[cb], hb, (((size_t)n * L + 31) / 32) * 4, cudaMemcpyHostToDevice, s_copy));
+        } else {
+            KBBQ_CUDA(cudaMemcpyAsync(d_corr[cb], corr + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, s_copy));
+        }
         KBBQ_CUDA(cudaEventRecord(copied[k], s_copy));
         KBBQ_CUDA(cudaStreamWaitEvent(s_comp, copied[k], 0));
+        if (use_bits) {
+            const long long nb = (long long)n * L;
+            expand_corr_kernel<<<(unsigned)((nb + 16 * 256 - 1) / (16 * 256)), 256, 0, s_comp>>>(
+                d_seq[b] + doff, d_bits[cb], d_corr[cb], nb);
+            KBBQ_LAUNCHED();
+        }
         KBBQ_TRY(kbbq_build(d_seq[b] + doff, d_qual[b] + doff, d_corr[cb], rg ? d_rg[b] + roff : nullptr,
                             second ? d_sec[b] + roff : nullptr, n, L, R, minscore, pe, pt, de, dt, d_ws, ws_bytes,
                             d_status, 0, s_comp));

@@ -56,6 +56,7 @@ SIGNATURES = {
     "kbbq_fastq_rg_key": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_i)]),
     "kbbq_fastq_check_names": (_i, [_vp, _vp, _i64, _i, C.POINTER(_i64)]),
     "kbbq_fastq_write": (_i, [_i, _vp, _i64, _i64, _vp, _i]),
+    "kbbq_host_mismatch_bits": (_i, [_vp, _vp, _i64, _vp, _i]),
     "kbbq_plan_info": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i)]),
 }
 

@@ -154,14 +154,18 @@ def test_synthetic_configs_vs_oracle(torch_cuda, oracle_mod, case):
         assert np.array_equal(out.astype(np.int16), want_o), (path, splits)
 
 
+@pytest.mark.parametrize("bitmap", ["1", "0"])
 @pytest.mark.parametrize("streaming", ["0", "1"])
-def test_host_buffer_entry_point_chunked(oracle_mod, monkeypatch, streaming):
-    """kbbq_recalibrate_host with several chunks, resident and two-pass streaming modes."""
+def test_host_buffer_entry_point_chunked(oracle_mod, monkeypatch, streaming, bitmap):
+    """kbbq_recalibrate_host with several chunks, resident and two-pass streaming modes, the corrected
+    reads crossing PCIe as a mismatch bit map (default) or as they are."""
     from kbbq import _native, synth
-    N, L, R = 50_000, 150, 4
+    N, L, R = 50_003, 151, 4   # odd sizes: the last chunk's bit map ends inside a word
     seq, qual, corr, rg, second = synth.synth_reads(11, 0, N, L, R)
+    corr[::7, 3] = ord("N")    # corrected bases outside ACGT only have to differ
     monkeypatch.setenv("KBBQ_HOST_CHUNK_READS", "7000")
     monkeypatch.setenv("KBBQ_HOST_FORCE_STREAMING", streaming)
+    monkeypatch.setenv("KBBQ_HOST_NO_BITMAP", "0" if bitmap == "1" else "1")
     out, tabs, dqs = _native.recalibrate_host(seq, qual, corr, rg, second, L, R, want_tables=True)
     want_t = oracle_mod.covariate_arrays(seq, qual, corr, rg, second, L, R)
     want_d = oracle_mod.get_delta_qs(*want_t)

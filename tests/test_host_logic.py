@@ -145,3 +145,22 @@ def test_shard_ranges_cover_and_align():
             for (a, b), (c, d) in zip(spans, spans[1:]):
                 assert b == c and a <= b
             assert all(lo % 16 == 0 for lo, _ in spans if lo < n)
+
+
+def test_host_mismatch_bits_matches_numpy():
+    """kbbq_host_mismatch_bits (csrc/host_pack.cpp): bit i = seq[i] != corr[i], little-endian in u32 words."""
+    from kbbq import _native
+    lib = _native.lib()
+    rng = np.random.default_rng(3)
+    for n in (0, 1, 31, 32, 33, 4096 * 32 * 3 + 17, 1_000_003):
+        seq = rng.integers(65, 85, size=n, dtype=np.uint8)
+        corr = seq.copy()
+        flip = rng.random(n) < 0.05
+        corr[flip] ^= rng.integers(1, 64, size=int(flip.sum()), dtype=np.uint8)
+        bits = np.full((n + 31) // 32 + 1, 0xDEADBEEF, np.uint32)
+        for threads in (1, 0):
+            assert lib.kbbq_host_mismatch_bits(_native.ptr(seq), _native.ptr(corr), n, _native.ptr(bits), threads) == 0
+            want = np.packbits(seq != corr, bitorder="little")
+            got = bits[:(n + 31) // 32].view(np.uint8)[:want.size]
+            assert np.array_equal(got, want), (n, threads)
+            assert bits[(n + 31) // 32] == 0xDEADBEEF  # nothing written past the map
