@@ -103,6 +103,30 @@ int kbbq_posterior_q_real(const double *prior_q_dev, const int64_t *numerrs_dev,
                           const int64_t *numtotal_dev, int64_t n, int64_t *posterior_dev, void *stream);
 
 /*
+ * BAM side.  kbbq_build_bam is the tally of bqsr.bam_to_bqsr_covariates
+ * (kbbq/gatk/bqsr.py:52-123) for N reads of length L already unpacked from their BAM records:
+ *   seq, qual (the OQ qualities), err, skip: u8[N*L]; err / skip = what compare_reads.find_read_errors
+ *   (kbbq/compare_reads.py:84-135) and bqsr.trim_bamread (kbbq/gatk/bqsr.py:158-212) return, merged;
+ *   rg u16[N]; flags u8[N] (bit 0 = read 2, bit 1 = reverse strand); aln_start / aln_end u16[N] =
+ *   query_alignment_start / _end (soft clips lie outside).  skip, rg, flags, aln_* may be NULL.
+ * The kernel adds the q < minscore and N skips (:94-96), counts cycles inside the aligned part,
+ * backwards on the reverse strand (bamread_bqsr_cycle, :23-31), and takes dinucleotides from the
+ * reverse complement there (bamread_bqsr_dinuc, :33-50).  Tables as kbbq_build's, accumulating.
+ * kbbq_apply_bam is applybqsr.recalibrate_bamread (kbbq/gatk/applybqsr.py:65-78): whole-read cycles
+ * flipped on the reverse strand, reverse-complement dinucleotides, same delta tables as kbbq_apply.
+ */
+int kbbq_build_bam(const uint8_t *seq_dev, const uint8_t *qual_dev, const uint8_t *err_dev,
+                   const uint8_t *skip_dev, const uint16_t *rg_dev, const uint8_t *flags_dev,
+                   const uint16_t *aln_start_dev, const uint16_t *aln_end_dev, int64_t N, int L, int R,
+                   int minscore, int64_t *pos_errs_dev, int64_t *pos_total_dev, int64_t *din_errs_dev,
+                   int64_t *din_total_dev, int *status_dev, void *stream);
+int kbbq_apply_bam(const uint8_t *seq_dev, const uint8_t *qual_dev, const uint16_t *rg_dev,
+                   const uint8_t *flags_dev, int64_t N, int L, int R, int minscore,
+                   const int64_t *meanq_dev, const int64_t *rgdq_dev, const int64_t *qdq_dev,
+                   const int64_t *posdq_dev, const int64_t *dindq_dev, int nq, int ndin1,
+                   uint8_t *out_qual_dev, int *status_dev, void *stream);
+
+/*
  * Calibration benchmark counts: the two np.bincount calls of
  * benchmark.calculate_q (kbbq/benchmark.py:76-91), total[q] += 1 and errs[q] += error, over n bases,
  * skipping bases whose skip byte is non-zero (errors[~skips], quals[~skips], kbbq/benchmark.py:102-104).
@@ -178,6 +202,15 @@ int kbbq_delta_q_host(const int64_t *prior_q, const int64_t *numerrs, const int6
                       int64_t n, int64_t *delta, int device);
 int kbbq_posterior_q_real_host(const double *prior_q, const int64_t *numerrs, const int64_t *numtotal,
                                int64_t n, int64_t *posterior, int device);
+int kbbq_build_bam_host(const uint8_t *seq, const uint8_t *qual, const uint8_t *err, const uint8_t *skip,
+                        const uint16_t *rg, const uint8_t *flags, const uint16_t *aln_start,
+                        const uint16_t *aln_end, int64_t N, int L, int R, int minscore, int64_t *pos_errs,
+                        int64_t *pos_total, int64_t *din_errs, int64_t *din_total, int *status_out,
+                        int device);
+int kbbq_apply_bam_host(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, const uint8_t *flags,
+                        int64_t N, int L, int R, int minscore, const int64_t *meanq, const int64_t *rgdq,
+                        const int64_t *qdq, const int64_t *posdq, const int64_t *dindq, int nq, int ndin1,
+                        uint8_t *out_qual, int *status_out, int device);
 int kbbq_calibration_counts_host(const uint8_t *qual, const uint8_t *err, const uint8_t *seq,
                                  const uint8_t *corr, const uint8_t *skip, int64_t n, int64_t *total,
                                  int64_t *errs, int device);

@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "apply.cuh"
+#include "bam.cuh"
 #include "build.cuh"
 #include "calib.cuh"
 #include "common.cuh"
@@ -283,6 +284,46 @@ int kbbq_posterior_q_real(const double *prior_q, const int64_t *numerrs, const i
     if (rc) return rc;
     posterior_q_real_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         prior_q, (const long long *)numerrs, (const long long *)numtotal, n, (long long *)posterior);
+    KBBQ_LAUNCHED();
+    return KBBQ_OK;
+}
+
+int kbbq_build_bam(const uint8_t *seq, const uint8_t *qual, const uint8_t *err, const uint8_t *skip, const uint16_t *rg,
+                   const uint8_t *flags, const uint16_t *aln_start, const uint16_t *aln_end, int64_t N, int L, int R,
+                   int minscore, int64_t *pos_errs, int64_t *pos_total, int64_t *din_errs, int64_t *din_total,
+                   int *status, void *stream) {
+    if (N < 0 || L < 1 || L > 32767 || R < 1 || R > 65535 || minscore < 0 || minscore > NQ) return KBBQ_E_ARG;
+    if (!pos_errs || !pos_total || !din_errs || !din_total || !status) return KBBQ_E_ARG;
+    if (N == 0) return KBBQ_OK;
+    if (!seq || !qual || !err) return KBBQ_E_ARG;
+    int device, sms = KBBQ_SM_COUNT_FALLBACK;
+    KBBQ_CUDA(cudaGetDevice(&device));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    BuildBamArgs a = {seq, qual, err, skip, rg, flags, aln_start, aln_end, N, L, R, minscore,
+                      (unsigned long long *)pos_errs, (unsigned long long *)pos_total,
+                      (unsigned long long *)din_errs, (unsigned long long *)din_total, status};
+    const long long blocks = std::min<long long>(((long long)N * L + 255) / 256, (long long)sms * 16);
+    build_bam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    KBBQ_LAUNCHED();
+    return KBBQ_OK;
+}
+
+int kbbq_apply_bam(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, const uint8_t *flags, int64_t N, int L,
+                   int R, int minscore, const int64_t *meanq, const int64_t *rgdq, const int64_t *qdq,
+                   const int64_t *posdq, const int64_t *dindq, int nq, int ndin1, uint8_t *out_qual, int *status,
+                   void *stream) {
+    if (N < 0 || L < 1 || L > 32767 || R < 1 || R > 65535 || nq < 1 || nq > 256 || ndin1 != 17) return KBBQ_E_ARG;
+    if (!meanq || !rgdq || !qdq || !posdq || !dindq || !status) return KBBQ_E_ARG;
+    if (N == 0) return KBBQ_OK;
+    if (!seq || !qual || !out_qual) return KBBQ_E_ARG;
+    int device, sms = KBBQ_SM_COUNT_FALLBACK;
+    KBBQ_CUDA(cudaGetDevice(&device));
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    ApplyBamArgs a = {seq, qual, rg, flags, out_qual, N, L, R, minscore, nq, ndin1, (const long long *)meanq,
+                      (const long long *)rgdq, (const long long *)qdq, (const long long *)posdq,
+                      (const long long *)dindq, status};
+    const long long blocks = std::min<long long>(((long long)N * L + 255) / 256, (long long)sms * 16);
+    apply_bam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
     KBBQ_LAUNCHED();
     return KBBQ_OK;
 }
@@ -853,6 +894,85 @@ int kbbq_posterior_q_real_host(const double *prior_q, const int64_t *numerrs, co
     KBBQ_TRY(kbbq_posterior_q_real(reinterpret_cast<const double *>(p), p + n, p + 2 * n, n, p + 3 * n, nullptr));
     KBBQ_CUDA(cudaMemcpy(posterior, p + 3 * n, (size_t)n * 8, cudaMemcpyDeviceToHost));
     return KBBQ_OK;
+}
+
+// Host-buffer forms of the BAM-side entry points: copy, run, copy back (a BAM batch is small next to
+// what the host spends parsing it).
+int kbbq_build_bam_host(const uint8_t *seq, const uint8_t *qual, const uint8_t *err, const uint8_t *skip,
+                        const uint16_t *rg, const uint8_t *flags, const uint16_t *aln_start, const uint16_t *aln_end,
+                        int64_t N, int L, int R, int minscore, int64_t *pos_errs, int64_t *pos_total,
+                        int64_t *din_errs, int64_t *din_total, int *status_out, int device) {
+    if (N < 0 || L < 1 || R < 1 || R > 65535) return KBBQ_E_ARG;
+    if (!pos_errs || !pos_total || !din_errs || !din_total) return KBBQ_E_ARG;
+    KBBQ_CUDA(cudaSetDevice(device));
+    const size_t npos = (size_t)R * NQ * 2 * L, ndin = (size_t)R * NQ * 16, nb = (size_t)N * L;
+    Carver c(nullptr);
+    auto carve = [&](Carver &cv, uint8_t **ds, uint8_t **dq, uint8_t **de, uint8_t **dk, uint16_t **dr, uint8_t **df,
+                     uint16_t **d0, uint16_t **d1, int64_t **dt, int **dst) {
+        *ds = cv.take<uint8_t>(nb); *dq = cv.take<uint8_t>(nb); *de = cv.take<uint8_t>(nb); *dk = cv.take<uint8_t>(nb);
+        *dr = cv.take<uint16_t>((size_t)N); *df = cv.take<uint8_t>((size_t)N);
+        *d0 = cv.take<uint16_t>((size_t)N); *d1 = cv.take<uint16_t>((size_t)N);
+        *dt = cv.take<int64_t>(2 * npos + 2 * ndin); *dst = cv.take<int>(64);
+    };
+    uint8_t *ds, *dq, *de, *dk, *df; uint16_t *dr, *d0, *d1; int64_t *dt; int *dst;
+    carve(c, &ds, &dq, &de, &dk, &dr, &df, &d0, &d1, &dt, &dst);
+    DevBuf buf;
+    KBBQ_TRY(buf.alloc(c.off));
+    Carver c2(buf.p);
+    carve(c2, &ds, &dq, &de, &dk, &dr, &df, &d0, &d1, &dt, &dst);
+    auto up = [&](void *d, const void *h, size_t n) { return h && n ? cudaMemcpy(d, h, n, cudaMemcpyHostToDevice) : cudaSuccess; };
+    KBBQ_CUDA(up(ds, seq, nb)); KBBQ_CUDA(up(dq, qual, nb)); KBBQ_CUDA(up(de, err, nb)); KBBQ_CUDA(up(dk, skip, nb));
+    KBBQ_CUDA(up(dr, rg, (size_t)N * 2)); KBBQ_CUDA(up(df, flags, (size_t)N));
+    KBBQ_CUDA(up(d0, aln_start, (size_t)N * 2)); KBBQ_CUDA(up(d1, aln_end, (size_t)N * 2));
+    KBBQ_CUDA(cudaMemcpy(dt, pos_errs, npos * 8, cudaMemcpyHostToDevice));   // the tables accumulate
+    KBBQ_CUDA(cudaMemcpy(dt + npos, pos_total, npos * 8, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemcpy(dt + 2 * npos, din_errs, ndin * 8, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemcpy(dt + 2 * npos + ndin, din_total, ndin * 8, cudaMemcpyHostToDevice));
+    KBBQ_CUDA(cudaMemset(dst, 0, sizeof(int)));
+    KBBQ_TRY(kbbq_build_bam(ds, dq, de, skip ? dk : nullptr, rg ? dr : nullptr, flags ? df : nullptr,
+                            aln_start ? d0 : nullptr, aln_end ? d1 : nullptr, N, L, R, minscore, dt, dt + npos,
+                            dt + 2 * npos, dt + 2 * npos + ndin, dst, nullptr));
+    KBBQ_CUDA(cudaMemcpy(pos_errs, dt, npos * 8, cudaMemcpyDeviceToHost));
+    KBBQ_CUDA(cudaMemcpy(pos_total, dt + npos, npos * 8, cudaMemcpyDeviceToHost));
+    KBBQ_CUDA(cudaMemcpy(din_errs, dt + 2 * npos, ndin * 8, cudaMemcpyDeviceToHost));
+    KBBQ_CUDA(cudaMemcpy(din_total, dt + 2 * npos + ndin, ndin * 8, cudaMemcpyDeviceToHost));
+    int st = 0;
+    KBBQ_CUDA(cudaMemcpy(&st, dst, sizeof(int), cudaMemcpyDeviceToHost));
+    if (status_out) *status_out = st;
+    return st ? KBBQ_E_DATA : KBBQ_OK;
+}
+
+int kbbq_apply_bam_host(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, const uint8_t *flags, int64_t N,
+                        int L, int R, int minscore, const int64_t *meanq, const int64_t *rgdq, const int64_t *qdq,
+                        const int64_t *posdq, const int64_t *dindq, int nq, int ndin1, uint8_t *out_qual,
+                        int *status_out, int device) {
+    if (N < 0 || L < 1 || R < 1 || R > 65535 || nq < 1 || ndin1 != 17) return KBBQ_E_ARG;
+    KBBQ_CUDA(cudaSetDevice(device));
+    const size_t nb = (size_t)N * L, n_q = (size_t)R * nq;
+    uint8_t *ds, *dq, *dout, *df; uint16_t *dr; int64_t *dm; int *dst;
+    DevBuf buf;
+    for (int pass = 0; pass < 2; ++pass) {
+        Carver cv(pass ? buf.p : nullptr);
+        ds = cv.take<uint8_t>(nb); dq = cv.take<uint8_t>(nb); dout = cv.take<uint8_t>(nb);
+        dr = cv.take<uint16_t>((size_t)N); df = cv.take<uint8_t>((size_t)N);
+        dm = cv.take<int64_t>(2 * (size_t)R + n_q * (1 + 2 * (size_t)L + ndin1)); dst = cv.take<int>(64);
+        if (!pass) KBBQ_TRY(buf.alloc(cv.off));
+    }
+    int64_t *d_meanq = dm, *d_rgdq = dm + R, *d_qdq = d_rgdq + R, *d_posdq = d_qdq + n_q, *d_dindq = d_posdq + n_q * 2 * L;
+    auto up = [&](void *d, const void *h, size_t n) { return h && n ? cudaMemcpy(d, h, n, cudaMemcpyHostToDevice) : cudaSuccess; };
+    KBBQ_CUDA(up(ds, seq, nb)); KBBQ_CUDA(up(dq, qual, nb));
+    KBBQ_CUDA(up(dr, rg, (size_t)N * 2)); KBBQ_CUDA(up(df, flags, (size_t)N));
+    KBBQ_CUDA(up(d_meanq, meanq, (size_t)R * 8)); KBBQ_CUDA(up(d_rgdq, rgdq, (size_t)R * 8));
+    KBBQ_CUDA(up(d_qdq, qdq, n_q * 8)); KBBQ_CUDA(up(d_posdq, posdq, n_q * 2 * L * 8));
+    KBBQ_CUDA(up(d_dindq, dindq, n_q * ndin1 * 8));
+    KBBQ_CUDA(cudaMemset(dst, 0, sizeof(int)));
+    KBBQ_TRY(kbbq_apply_bam(ds, dq, rg ? dr : nullptr, flags ? df : nullptr, N, L, R, minscore, d_meanq, d_rgdq, d_qdq,
+                            d_posdq, d_dindq, nq, ndin1, dout, dst, nullptr));
+    if (nb) KBBQ_CUDA(cudaMemcpy(out_qual, dout, nb, cudaMemcpyDeviceToHost));
+    int st = 0;
+    KBBQ_CUDA(cudaMemcpy(&st, dst, sizeof(int), cudaMemcpyDeviceToHost));
+    if (status_out) *status_out = st;
+    return st ? KBBQ_E_DATA : KBBQ_OK;
 }
 
 int kbbq_calibration_counts_host(const uint8_t *qual, const uint8_t *err, const uint8_t *seq, const uint8_t *corr,

@@ -42,6 +42,10 @@ SIGNATURES = {
     "kbbq_posterior_q_real_host": (_i, [_vp, _vp, _vp, _i64, _vp, _i]),
     "kbbq_calibration_counts": (_i, [_vp] * 5 + [_i64, _vp, _vp, _vp]),
     "kbbq_calibration_counts_host": (_i, [_vp] * 5 + [_i64, _vp, _vp, _i]),
+    "kbbq_build_bam": (_i, [_vp] * 8 + [_i64, _i, _i, _i] + [_vp] * 4 + [_vp, _vp]),
+    "kbbq_apply_bam": (_i, [_vp] * 4 + [_i64, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, _vp, _vp]),
+    "kbbq_build_bam_host": (_i, [_vp] * 8 + [_i64, _i, _i, _i] + [_vp] * 4 + [_vp, _i]),
+    "kbbq_apply_bam_host": (_i, [_vp] * 4 + [_i64, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, _vp, _i]),
     "kbbq_marginals_host": (_i, [_vp, _vp, _i, _i] + [_vp] * 5 + [_i]),
     "kbbq_synth_reads": (_i, [C.c_uint64, _i64, _i64, _i, _i] + [_vp] * 5 + [_vp]),
     "kbbq_launch_count": (_i64, []),
@@ -191,6 +195,47 @@ def calibration_counts_host(qual, err=None, seq=None, corr=None, skip=None, devi
     check(lib().kbbq_calibration_counts_host(ptr(qual), *[ptr(a) for a in arrs], qual.size, ptr(total), ptr(errs),
                                              DEVICE if device is None else device))
     return total, errs
+
+
+def _u16(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.uint16)
+
+
+def build_bam_host(seq, qual, err, skip, rg, flags, aln_start, aln_end, L, R, minscore=6, tables=None, device=None):
+    """BAM-side tally on packed host arrays (kbbq_build_bam_host); `tables` = (pe, pt, de, dt) to add to."""
+    seq, qual, err = u8(seq).ravel(), u8(qual).ravel(), u8(err).ravel()
+    skip = None if skip is None else u8(skip).ravel()
+    N = seq.size // L
+    assert seq.size == qual.size == err.size == N * L
+    flags = None if flags is None else u8(flags)
+    rg, aln_start, aln_end = _u16(rg), _u16(aln_start), _u16(aln_end)
+    if tables is None:
+        tables = (np.zeros((R, NQ, 2 * L), np.int64), np.zeros((R, NQ, 2 * L), np.int64),
+                  np.zeros((R, NQ, 16), np.int64), np.zeros((R, NQ, 16), np.int64))
+    pe, pt, de, dt = tables
+    st = C.c_int(0)
+    rc = lib().kbbq_build_bam_host(ptr(seq), ptr(qual), ptr(err), ptr(skip), ptr(rg), ptr(flags), ptr(aln_start),
+                                   ptr(aln_end), N, L, R, minscore, ptr(pe), ptr(pt), ptr(de), ptr(dt), C.byref(st),
+                                   DEVICE if device is None else device)
+    check(rc, st.value)
+    return pe, pt, de, dt
+
+
+def apply_bam_host(seq, qual, rg, flags, L, R, meanq, rgdq, qdq, posdq, dindq, minscore=6, device=None):
+    seq, qual = u8(seq).ravel(), u8(qual).ravel()
+    N = seq.size // L
+    flags = None if flags is None else u8(flags)
+    rg = _u16(rg)
+    meanq, rgdq, qdq, posdq, dindq = [i64(a) for a in (meanq, rgdq, qdq, posdq, dindq)]
+    nq, ndin1 = qdq.shape[1], dindq.shape[2]
+    assert posdq.shape == (R, nq, 2 * L) and dindq.shape[:2] == (R, nq)
+    out = np.zeros((N, L), np.uint8)
+    st = C.c_int(0)
+    rc = lib().kbbq_apply_bam_host(ptr(seq), ptr(qual), ptr(rg), ptr(flags), N, L, R, minscore, ptr(meanq), ptr(rgdq),
+                                   ptr(qdq), ptr(posdq), ptr(dindq), nq, ndin1, ptr(out), C.byref(st),
+                                   DEVICE if device is None else device)
+    check(rc, st.value)
+    return out
 
 
 def get_delta_qs_host(meanq, rg_errs, rg_total, q_errs, q_total, pos_errs, pos_total, din_errs, din_total,

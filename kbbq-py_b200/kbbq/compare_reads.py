@@ -4,8 +4,11 @@ Same names, argument meaning and error behaviour.  The arithmetic of the model
 (:func:`gatk_delta_q`) and of the apply (:func:`recalibrate_fastq`) runs on the GPU through
 the C ABI; the small covariate helpers that only produce index arrays for a single read stay
 numpy on the host (they are API surface, the batched kernels fuse the same index arithmetic).
-Out of scope (BAM / regression experiments): load_positions, get_var_sites, train_regression,
-regression_recalibrate, find_read_errors, bamread_get_oq, get_rg_to_pu.
+The BAM-side helpers find_read_errors, bamread_get_oq and get_rg_to_pu (host work on one pysam
+record: CIGAR walk, tag decoding) are here for kbbq.gatk.bqsr / kbbq.gatk.applybqsr; they take any
+object with pysam's AlignedSegment attributes and never import pysam themselves.
+Out of scope (regression experiments, file readers): load_positions, get_var_sites,
+train_regression, regression_recalibrate.
 """
 import numpy as np
 
@@ -172,3 +175,55 @@ def recalibrate_fastq(read, meanq, globaldeltaq, qscoredeltaq, positiondeltaq, d
                              positiondeltaq[g:g + 1], dinucdeltaq[g:g + 1], minscore=minscore)
     out = out.reshape(L).astype(np.int8).astype(int)  # the device keeps the low 8 bits of the sum
     return out
+
+
+# ---- BAM reads (host side of SURVEY.md section 8 row f3) -----------------------------------------
+
+def find_read_errors(read, ref, variable):
+    """Errors and sites to skip of one aligned read (reference: kbbq/compare_reads.py:84-135).
+
+    Walks the CIGAR: aligned bases (M, =, X) are errors where they differ from `ref` and skipped
+    where `variable` marks the reference position; an insertion is skipped when the positions on
+    both sides are; a deletion or N skips the base in front of it if it spans a variable position;
+    soft clips are skipped; hard clips and pads consume nothing.  `ref` / `variable` map contig ->
+    array over the contig.  Returns (errors, skips), boolean arrays over the read.
+    """
+    seq = np.frombuffer(read.query_sequence.encode(), dtype=np.uint8)
+    errors = np.zeros(seq.shape, dtype=bool)
+    skips = np.zeros(seq.shape, dtype=bool)
+    lo, hi = read.reference_start, read.reference_end
+    var = np.asarray(variable[read.reference_name][lo:hi], dtype=bool)
+    refseq = ref[read.reference_name][lo:hi]
+    if not (isinstance(refseq, np.ndarray) and refseq.dtype == np.uint8):
+        refseq = np.frombuffer(''.join(refseq).encode(), dtype=np.uint8)
+    q = r = 0
+    for op, n in read.cigartuples:
+        if op in (0, 7, 8):
+            errors[q:q + n] = refseq[r:r + n] != seq[q:q + n]
+            skips[q:q + n] = var[r:r + n]
+            q += n
+            r += n
+        elif op == 1:
+            skips[q:q + n] = var[r - 1] and var[r]
+            q += n
+        elif op in (2, 3):
+            skips[q - 1] = skips[q - 1] or bool(np.any(var[r:r + n]))
+            r += n
+        elif op == 4:
+            skips[q:q + n] = True
+            q += n
+        elif op in (5, 6):
+            pass
+        else:
+            raise ValueError("Unrecognized Cigar Operation " + str(op) + " In Read\n" + str(read))
+    return errors, skips
+
+
+def bamread_get_oq(read):
+    """Original qualities from the OQ tag (reference: kbbq/compare_reads.py:332-336)."""
+    return np.frombuffer(read.get_tag('OQ').encode(), dtype=np.uint8).astype(int) - 33
+
+
+def get_rg_to_pu(bamfileobj):
+    """{read group ID: platform unit} from the header (reference: kbbq/compare_reads.py:338-340)."""
+    return {rg['ID']: rg['PU'] for rg in bamfileobj.header.as_dict()['RG']}

@@ -106,6 +106,24 @@ class DeviceRecalibrator:
                                  self._stream())
         _native.check(rc)
 
+    def build_bam(self, seq, qual, err, skip=None, rg=None, flags=None, aln_start=None, aln_end=None):
+        """Accumulate a batch of aligned reads (kbbq_build_bam): err / skip u8 [N, L] from the host's CIGAR
+        walk, flags u8 [N] (bit 0 read 2, bit 1 reverse strand), aln_start / aln_end int16 [N]."""
+        N = seq.numel() // self.L
+        rc = self.lib.kbbq_build_bam(_p(seq), _p(qual), _p(err), _p(skip), _p(rg), _p(flags), _p(aln_start),
+                                     _p(aln_end), N, self.L, self.R, self.minscore, _p(self.pos_errs),
+                                     _p(self.pos_total), _p(self.din_errs), _p(self.din_total), _p(self.status),
+                                     self._stream())
+        _native.check(rc)
+
+    def apply_bam(self, seq, qual, out, rg=None, flags=None):
+        """Recalibrated qualities of a batch of aligned reads (kbbq_apply_bam)."""
+        N = seq.numel() // self.L
+        rc = self.lib.kbbq_apply_bam(_p(seq), _p(qual), _p(rg), _p(flags), N, self.L, self.R, self.minscore,
+                                     _p(self.meanq), _p(self.rgdq), _p(self.qdq), _p(self.posdq), _p(self.dindq),
+                                     NQ, 17, _p(out), _p(self.status), self._stream())
+        _native.check(rc)
+
     def check_status(self):
         """Synchronise and raise the reference's exception for any data error seen on the device."""
         st = int(self.status.item())

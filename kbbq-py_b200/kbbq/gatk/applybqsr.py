@@ -1,8 +1,9 @@
 """Mirror of the hot-path part of the reference's kbbq/gatk/applybqsr.py: get_delta_qs (:80-103)
 and the report reader table_to_vectors (:14-44).
 
-Out of scope (BAM input, needs pysam): bamread_cycle_covariates, bamread_dinuc_covariates,
-recalibrate_bamread.
+BAM side: bamread_cycle_covariates, bamread_dinuc_covariates,
+recalibrate_bamread (:46-78) for one read, recalibrate_bam_arrays for a packed batch; the gather
+runs on the GPU (kbbq_apply_bam).
 """
 import numpy as np
 
@@ -96,3 +97,64 @@ def get_delta_qs(meanq, rg_errs, rg_total, q_errs, q_total, pos_errs, pos_total,
     assert pos_total.shape[:2] == q_total.shape and dinuc_total.shape[:2] == q_total.shape
     return _native.get_delta_qs_host(meanq, rg_errs, rg_total, q_errs, q_total, pos_errs, pos_total,
                                      dinuc_errs, dinuc_total)
+
+
+# ---- BAM side ------------------------------------------------------------------------------------
+
+def bamread_cycle_covariates(read):
+    """Whole-read cycles, flipped on the reverse strand (reference: kbbq/gatk/applybqsr.py:46-50)."""
+    cycle = utils.generic_cycle_covariate(read.query_length, read.is_read2)
+    return cycle[::-1].copy() if read.is_reverse else cycle
+
+
+def bamread_dinuc_covariates(read, use_oq=True, minscore=6):
+    """Whole-read dinucleotides, from the reverse complement on the reverse strand
+    (reference: kbbq/gatk/applybqsr.py:52-63)."""
+    from . import bqsr
+    quals = utils.bamread_get_oq(read) if use_oq else np.array(read.query_qualities, dtype=int)
+    return bqsr._strand_dinuc(read.query_sequence, quals, read.is_reverse, minscore)
+
+
+def recalibrate_bam_arrays(seq, qual, rg, is_read2, is_reverse, meanq, globaldeltaq, qscoredeltaq, positiondeltaq,
+                           dinucdeltaq, minscore=6):
+    """recalibrate_bamread over a packed batch: seq (bytes), qual [N, L]; rg, is_read2, is_reverse [N].
+    -> int array [N, L].  Runs on the GPU (kbbq_apply_bam)."""
+    seq = np.ascontiguousarray(seq, dtype=np.uint8)
+    N, L = seq.shape
+    flags = (np.asarray(is_read2).astype(np.uint8) & 1) | ((np.asarray(is_reverse).astype(np.uint8) & 1) << 1)
+    R = np.asarray(meanq).shape[0]
+    out = _native.apply_bam_host(seq, qual, rg, flags, L, R, meanq, globaldeltaq, qscoredeltaq, positiondeltaq,
+                                 dinucdeltaq, minscore=minscore)
+    return out.astype(np.int8).astype(int)  # the device keeps the low 8 bits of the sum
+
+
+def recalibrate_bamread(read, meanq, globaldeltaq, qscoredeltaq, positiondeltaq, dinucdeltaq, rg_to_int,
+                        use_oq=True, minscore=6):
+    """Recalibrated qualities of ONE aligned read (reference: kbbq/gatk/applybqsr.py:65-78).
+
+    Like the reference, the dinucleotide covariate is gated by the OQ qualities whatever `use_oq` says
+    (:74 calls bamread_dinuc_covariates with its default); with use_oq = False the two quality arrays
+    differ and the rare sites where they disagree about minscore are patched on the host.
+    """
+    original = utils.bamread_get_oq(read) if use_oq else np.array(read.query_qualities, dtype=int)
+    if np.any(original < 0) or np.any(original > 255):
+        raise IndexError("quality out of range")
+    seq = np.frombuffer(read.query_sequence.encode(), dtype=np.uint8).reshape(1, -1)
+    rg = rg_to_int[read.get_tag('RG')]
+    meanq, globaldeltaq = np.atleast_1d(np.asarray(meanq)), np.atleast_1d(np.asarray(globaldeltaq))
+    qscoredeltaq, positiondeltaq, dinucdeltaq = (np.asarray(a) for a in (qscoredeltaq, positiondeltaq, dinucdeltaq))
+    if positiondeltaq.shape[2] != 2 * seq.shape[1]:
+        raise IndexError("positiondeltaq cycle axis must have length 2 * len(read)")
+    out = recalibrate_bam_arrays(seq, original.reshape(1, -1), np.zeros(1, np.uint16), [read.is_read2], [read.is_reverse],
+                                 meanq[rg:rg + 1], globaldeltaq[rg:rg + 1], qscoredeltaq[rg:rg + 1],
+                                 positiondeltaq[rg:rg + 1], dinucdeltaq[rg:rg + 1], minscore=minscore)[0]
+    if not use_oq:
+        # dinucleotides gated by OQ, everything else by the BAM qualities: redo the (few) affected sites
+        din_oq = bamread_dinuc_covariates(read, True, minscore)
+        din_q = bamread_dinuc_covariates(read, False, minscore)
+        cyc = bamread_cycle_covariates(read)
+        for i in np.flatnonzero((din_oq != din_q) & (original >= minscore)):
+            q = original[i]
+            out[i] = (meanq[rg] + globaldeltaq[rg] + qscoredeltaq[rg, q] + dinucdeltaq[rg, q, din_oq[i]] +
+                      positiondeltaq[rg, q, cyc[i]])
+    return out

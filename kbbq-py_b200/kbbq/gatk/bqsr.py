@@ -8,8 +8,9 @@ from the delta-Q kernels of the C ABI (kbbq_delta_q, kbbq_posterior_q_real), one
 over every cell at once; rows are then selected and ordered with NumPy (the reference builds
 pandas frames over all cells, concatenates and re-sorts them through a MultiIndex).
 
-The BAM half of the reference module (bam_to_bqsr_covariates, bamread_bqsr_*, trim_bamread,
-bam_to_report) needs pysam and is out of scope.
+The BAM half keeps the reference's function names: the host walks the
+records (it needs nothing from pysam but the objects the caller hands in; only reading the FASTA
+imports pysam), the tally runs on the GPU (kbbq_build_bam).
 """
 import numpy as np
 import pandas as pd
@@ -143,14 +144,165 @@ def vectors_to_report(meanq, global_errs, global_total, q_errs, q_total, pos_err
     return recaltable.RecalibrationReport(tables)
 
 
-def _needs_pysam(name):
-    def f(*args, **kwargs):
-        raise NotImplementedError("kbbq.gatk.bqsr.%s reads BAM files through pysam; out of scope of the B200 path" % name)
-    f.__name__ = name
-    return f
+# ---- BAM side -------------------------------------------------------
+# Per-read covariate helpers keep the reference's names and results (they are API surface; the
+# batched kernel kbbq_build_bam fuses the same index arithmetic).  Reads are anything with pysam's
+# AlignedSegment attributes.
+
+def bamread_bqsr_cycle(read):
+    """Cycle of every base, 0 outside the aligned part (reference: kbbq/gatk/bqsr.py:23-31)."""
+    full = np.zeros(read.query_length, dtype=int)
+    lo, hi = read.query_alignment_start, read.query_alignment_end
+    c = np.arange(hi - lo)
+    if read.is_reverse:
+        c = c[::-1]
+    full[lo:hi] = np.negative(c + 1) if read.is_read2 else c
+    return full
 
 
-for _n in ("bam_to_bqsr_covariates", "bamread_bqsr_cycle", "bamread_bqsr_dinuc", "bamread_adaptor_boundary",
-           "trim_bamread", "bam_to_report"):
-    globals()[_n] = _needs_pysam(_n)
-del _n
+def _strand_dinuc(seq, quals, reverse, minscore):
+    """generic_dinuc_covariate of a window; on the reverse strand of its reverse complement, flipped
+    back to stored order (reference: kbbq/gatk/bqsr.py:38-49, kbbq/gatk/applybqsr.py:55-62)."""
+    if not reverse:
+        return utils.generic_dinuc_covariate(np.array(list(seq), dtype='U1'), quals, minscore).copy()
+    rc = [utils.Dinucleotide.complement.get(x, 'N') for x in reversed(seq)]
+    return utils.generic_dinuc_covariate(np.array(rc, dtype='U1').reshape(len(rc)), quals[::-1], minscore)[::-1].copy()
+
+
+def bamread_bqsr_dinuc(read, use_oq=True, minscore=6):
+    """Dinucleotide of every base inside the aligned part, 0 outside (reference: kbbq/gatk/bqsr.py:33-50)."""
+    lo, hi = read.query_alignment_start, read.query_alignment_end
+    quals = utils.bamread_get_oq(read) if use_oq else np.array(read.query_qualities, dtype=int)
+    full = np.zeros(read.query_length, dtype=int)
+    if hi > lo:
+        full[lo:hi] = _strand_dinuc(read.query_sequence[lo:hi], quals[lo:hi], read.is_reverse, minscore)
+    return full
+
+
+def bamread_adaptor_boundary(read):
+    """Reference position where the adaptor starts, or None (reference: kbbq/gatk/bqsr.py:131-156)."""
+    if (read.tlen == 0 or not read.is_paired or read.is_unmapped or read.mate_is_unmapped or
+            read.is_reverse == read.mate_is_reverse):
+        return None
+    if read.is_reverse:
+        return read.next_reference_start - 1 if (read.reference_end - 1) > read.next_reference_start else None
+    return read.reference_start + abs(read.tlen) if read.reference_start <= (read.next_reference_start + read.tlen) else None
+
+
+def trim_bamread(read):
+    """Bases past the adaptor boundary, to be skipped (reference: kbbq/gatk/bqsr.py:158-212)."""
+    skips = np.zeros(len(read.query_qualities), dtype=bool)
+    boundary = bamread_adaptor_boundary(read)
+    if boundary is None:
+        return skips
+    pairs = read.get_aligned_pairs()
+    if read.is_reverse:
+        if boundary >= read.reference_start:
+            cut, reached = 0, False
+            for readidx, refidx in reversed(pairs):  # first read base at or left of the boundary, from the right
+                reached = reached or (refidx is not None and refidx <= boundary)
+                if reached and readidx is not None:
+                    cut = readidx + 1
+                    break
+            skips[:cut] = True
+    elif boundary <= read.reference_end - 1:
+        cut, reached = len(skips), False
+        for readidx, refidx in pairs:
+            reached = reached or (refidx is not None and refidx >= boundary)
+            if reached and readidx is not None:
+                cut = readidx
+                break
+        skips[cut:] = True
+    return skips
+
+
+def bam_arrays_to_bqsr_covariates(seq, qual, errors, skips, rg, is_read2, is_reverse, aln_start, aln_end, nrgs,
+                                  minscore=6):
+    """The tally of bam_to_bqsr_covariates (kbbq/gatk/bqsr.py:86-123) on reads already unpacked into
+    arrays: seq (bytes), qual (OQ), errors, skips [N, L]; rg, is_read2, is_reverse, aln_start, aln_end [N].
+    Runs on the GPU (kbbq_build_bam + kbbq_marginals).  -> the nine vectors, as fastq_to_covariate_arrays."""
+    seq = np.asarray(seq)
+    if seq.dtype.kind in 'US':
+        seq = np.frombuffer(np.ascontiguousarray(seq).astype('S1').tobytes(), np.uint8).reshape(seq.shape)
+    N, L = seq.shape
+    flags = (np.asarray(is_read2).astype(np.uint8) & 1) | ((np.asarray(is_reverse).astype(np.uint8) & 1) << 1)
+    pe, pt, de, dt = _native.build_bam_host(seq, qual, np.asarray(errors).astype(bool), np.asarray(skips).astype(bool),
+                                            rg, flags, aln_start, aln_end, L, nrgs, minscore)
+    meanq, rg_e, rg_t, q_e, q_t = _native.marginals_host(pe, pt)
+    return meanq, rg_e, rg_t, q_e, q_t, pe, pt, de, dt
+
+
+def _load_reference(fastafilename):
+    try:
+        import pysam
+    except ImportError:
+        raise NotImplementedError("reading %s needs pysam.FastaFile; pass arrays to bam_arrays_to_bqsr_covariates "
+                                  "instead" % fastafilename)
+    fasta = pysam.FastaFile(fastafilename)
+    return {chrom: np.frombuffer(fasta.fetch(reference=chrom).encode(), dtype=np.uint8) for chrom in fasta.references}
+
+
+def bam_to_bqsr_covariates(bamfileobj, fastafilename, var_pos, minscore=6, maxscore=42, batch_reads=1 << 20):
+    """Covariate arrays of a BAM file (reference: kbbq/gatk/bqsr.py:52-123).
+
+    The host walks the records (CIGAR against the reference, known variant sites, adaptor trimming:
+    compare_reads.find_read_errors, trim_bamread) and packs them; every `batch_reads` reads the tally
+    runs on the GPU and adds into the tables.  As in the reference the tables are sized by the first
+    read; shorter reads are padded with skipped bases, a longer one is an IndexError.
+    """
+    if maxscore != 42:
+        raise NotImplementedError("only maxscore = 42 is supported")
+    rg_to_pu = utils.get_rg_to_pu(bamfileobj)
+    rg_to_int = dict(zip(rg_to_pu, range(len(rg_to_pu))))
+    nrgs = len(rg_to_pu)
+    ref = _load_reference(fastafilename)
+    fullskips = {chrom: np.zeros(len(ref[chrom]), dtype=bool) for chrom in ref}
+    for chrom in fullskips:
+        fullskips[chrom][np.array(var_pos[chrom], dtype=int)] = True
+    tables, L, rows = None, None, []
+
+    def flush():
+        nonlocal tables
+        if not rows:
+            return
+        n = len(rows)
+        seq, qual = np.full((n, L), ord('N'), np.uint8), np.zeros((n, L), np.uint8)
+        err, skip = np.zeros((n, L), np.uint8), np.ones((n, L), np.uint8)
+        rg, flags = np.zeros(n, np.uint16), np.zeros(n, np.uint8)
+        a0, a1 = np.zeros(n, np.uint16), np.zeros(n, np.uint16)
+        for i, (s, q, e, k, g, f, lo, hi) in enumerate(rows):
+            m = s.size
+            seq[i, :m], qual[i, :m], err[i, :m], skip[i, :m] = s, q, e, k
+            rg[i], flags[i], a0[i], a1[i] = g, f, lo, hi
+        tables = _native.build_bam_host(seq, qual, err, skip, rg, flags, a0, a1, L, nrgs, minscore, tables=tables)
+        rows.clear()
+
+    for read in bamfileobj:
+        s = np.frombuffer(read.query_sequence.encode(), dtype=np.uint8)
+        if L is None:
+            L = len(read.query_qualities)
+        if s.size > L:
+            raise IndexError("read %s is longer than the first read (%d > %d)" % (read.query_name, s.size, L))
+        e, k = utils.find_read_errors(read, ref, fullskips)
+        k = np.logical_or(k, trim_bamread(read))
+        q = utils.bamread_get_oq(read)
+        if np.any(q > 255) or np.any(q < 0):
+            raise IndexError("quality out of range")
+        rows.append((s, q.astype(np.uint8), e, k, rg_to_int[read.get_tag('RG')],
+                     (1 if read.is_read2 else 0) | (2 if read.is_reverse else 0),
+                     read.query_alignment_start, read.query_alignment_end))
+        if len(rows) >= batch_reads:
+            flush()
+    flush()
+    if tables is None:
+        raise StopIteration  # the reference's next(bamfileobj) on an empty file (:70)
+    pe, pt, de, dt = tables
+    meanq, rg_e, rg_t, q_e, q_t = _native.marginals_host(pe, pt)
+    return meanq, rg_e, rg_t, q_e, q_t, pe, pt, de, dt
+
+
+def bam_to_report(bamfileobj, fastafilename, var_pos):
+    """reference: kbbq/gatk/bqsr.py:368-371."""
+    rgs = list(utils.get_rg_to_pu(bamfileobj).values())
+    vectors = bam_to_bqsr_covariates(bamfileobj, fastafilename, var_pos)
+    return vectors_to_report(*vectors, rgs)

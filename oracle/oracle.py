@@ -136,6 +136,36 @@ def apply(seq, qual, rg, second, L, R, meanq, rgdq, qdq, posdq, dindq, minscore=
     return out
 
 
+def build_tables_bam(seq, qual, err, skip, rg, flags, aln_start, aln_end, L, R, minscore=6):
+    """BAM-side tally (kbbq/gatk/bqsr.py:86-118) -> pos_errs, pos_total, din_errs, din_total."""
+    seq, qual, err = _u8(seq).ravel(), _u8(qual).ravel(), _u8(err).ravel()
+    skip = None if skip is None else _u8(skip).ravel()
+    N = seq.size // L if L else 0
+    u16 = lambda a: None if a is None else np.ascontiguousarray(a, dtype=np.uint16)
+    rg, aln_start, aln_end = u16(rg), u16(aln_start), u16(aln_end)
+    flags = None if flags is None else _u8(flags)
+    tabs = [np.zeros((R, NQ, 2 * L), np.int64), np.zeros((R, NQ, 2 * L), np.int64),
+            np.zeros((R, NQ, 16), np.int64), np.zeros((R, NQ, 16), np.int64)]
+    st = lib().oracle_build_bam(_p(seq), _p(qual), _p(err), _p(skip), _p(rg), _p(flags), _p(aln_start), _p(aln_end),
+                                C.c_int64(N), C.c_int(L), C.c_int(R), C.c_int(minscore), *[_p(t) for t in tabs])
+    _check(st)
+    return tabs
+
+
+def apply_bam(seq, qual, rg, flags, L, R, meanq, rgdq, qdq, posdq, dindq, minscore=6):
+    """recalibrate_bamread (kbbq/gatk/applybqsr.py:65-78) -> int16 [N, L]."""
+    seq, qual = _u8(seq).ravel(), _u8(qual).ravel()
+    N = seq.size // L if L else 0
+    rg = None if rg is None else np.ascontiguousarray(rg, dtype=np.uint16)
+    flags = None if flags is None else _u8(flags)
+    out = np.zeros((N, L), np.int16)
+    ins = [_i64(a) for a in (meanq, rgdq, qdq, posdq, dindq)]
+    st = lib().oracle_apply_bam(_p(seq), _p(qual), _p(rg), _p(flags), C.c_int64(N), C.c_int(L), C.c_int(R),
+                                C.c_int(minscore), *[_p(a) for a in ins], _p(out))
+    _check(st)
+    return out
+
+
 def recalibrate(seq, qual, corr, rg, second, L, R, minscore=6, threads=0):
     """Whole path on host buffers -> int16 [N, L]."""
     seq, qual, corr = _u8(seq).ravel(), _u8(qual).ravel(), _u8(corr).ravel()
