@@ -226,17 +226,28 @@ int kbbq_fastq_pack(const kbbq_fastq *f, int64_t first, int64_t n, uint8_t *seq,
     std::vector<int> bad(T, 0);
     parallel_for(T, [&](int t) {
         const int64_t a = n * t / T, b = n * (t + 1) / T;
+        unsigned low = 0;  // thread-local: a shared flag array would bounce its cache line on every base
         for (int64_t i = a; i < b; ++i) {
             const size_t ri = (size_t)(first + i);
-            const Rec r = parse_record(f->data + f->rec[ri], f->data + f->rec[ri + 1]);
-            memcpy(seq + (size_t)i * L, r.s0, (size_t)L);
-            const uint8_t *q = (const uint8_t *)r.q0;
-            uint8_t *o = qual + (size_t)i * L;
+            // the index already checked the record: '@' line, sequence, '+' line, quality of L bytes each
+            const char *s0 = (const char *)memchr(f->data + f->rec[ri], '\n', (size_t)(f->rec[ri + 1] - f->rec[ri])) + 1;
+            const char *q0 = f->data + f->rec[ri + 1] - L - 1;
+            if (q0[L] != '\n' || q0[-1] != '\n') {  // no final newline, or CRLF line ends: take the slow path
+                const Rec r = parse_record(f->data + f->rec[ri], f->data + f->rec[ri + 1]);
+                s0 = r.s0;
+                q0 = r.q0;
+            }
+            memcpy(seq + (size_t)i * L, s0, (size_t)L);
+            const uint8_t *__restrict q = (const uint8_t *)q0;
+            uint8_t *__restrict o = qual + (size_t)i * L;
+            unsigned m = 0xFF;
             for (int c = 0; c < L; ++c) {
-                bad[t] |= q[c] < 33;
+                m = q[c] < m ? q[c] : m;
                 o[c] = (uint8_t)(q[c] - 33);
             }
+            low |= m < 33;
         }
+        bad[t] = (int)low;
     });
     for (int v : bad) if (v) return KBBQ_E_FORMAT;
     return KBBQ_OK;
