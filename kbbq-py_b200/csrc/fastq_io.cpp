@@ -365,6 +365,62 @@ int kbbq_fastq_write(int fd, const kbbq_fastq *f, int64_t first, int64_t n, cons
     const int T = n_threads(threads, (n >> 12) + 1);
     const int64_t wave = 1 << 15;  // reads per thread and wave: bounds the formatting buffers
     std::vector<std::vector<char>> buf(T);
+
+    // A seekable descriptor (a file, not a pipe, not O_APPEND): every thread formats its own contiguous
+    // share of the reads and writes it at its own offset, so the copy into the page cache is parallel too.
+    const off_t pos0 = lseek(fd, 0, SEEK_CUR);
+    const int fl = fcntl(fd, F_GETFL);
+    if (pos0 >= 0 && fl >= 0 && !(fl & O_APPEND) && T > 1) {
+        std::vector<int64_t> bytes(T + 1, 0);
+        parallel_for(T, [&](int t) {  // size of every share: names vary, the rest is 2 L + 6 per record
+            const int64_t a = n * t / T, b = n * (t + 1) / T;
+            int64_t sum = 0;
+            for (int64_t i = a; i < b; ++i) {
+                const char *h0 = f->data + f->rec[(size_t)(first + i)] + 1;
+                const char *h1 = line_end(h0, f->data + f->rec[(size_t)(first + i) + 1]);
+                sum += (int64_t)(name_end(h0, h1) - h0) + 2 * (int64_t)L + 6;
+            }
+            bytes[t + 1] = sum;
+        });
+        for (int t = 0; t < T; ++t) bytes[t + 1] += bytes[t];
+        std::vector<int> failed(T, 0);
+        parallel_for(T, [&](int t) {
+            const int64_t a = n * t / T, b = n * (t + 1) / T;
+            off_t at = pos0 + (off_t)bytes[t];
+            std::vector<char> &o = buf[t];
+            for (int64_t c0 = a; c0 < b; c0 += 4096) {
+                const int64_t c1 = std::min(b, c0 + 4096);
+                o.clear();
+                for (int64_t i = c0; i < c1; ++i) {
+                    const size_t ri = (size_t)(first + i);
+                    const Rec r = parse_record(f->data + f->rec[ri], f->data + f->rec[ri + 1]);
+                    const size_t nl = (size_t)(name_end(r.h0, r.h1) - r.h0);
+                    const size_t used = o.size();
+                    o.resize(used + nl + 2 * (size_t)L + 6);
+                    char *w = o.data() + used;
+                    *w++ = '@';
+                    memcpy(w, r.h0, nl); w += nl;
+                    *w++ = '\n';
+                    memcpy(w, r.s0, (size_t)L); w += L;
+                    *w++ = '\n'; *w++ = '+'; *w++ = '\n';
+                    const uint8_t *__restrict q = out_qual + (size_t)i * L;
+                    for (int c = 0; c < L; ++c) w[c] = (char)(q[c] + 33);
+                    w[L] = '\n';
+                }
+                const char *p = o.data();
+                size_t left = o.size();
+                while (left) {
+                    const ssize_t k = pwrite(fd, p, left, at);
+                    if (k < 0) { failed[t] = 1; return; }
+                    p += k; at += k; left -= (size_t)k;
+                }
+            }
+        });
+        for (int v : failed) if (v) return KBBQ_E_IO;
+        if (lseek(fd, pos0 + (off_t)bytes[T], SEEK_SET) < 0) return KBBQ_E_IO;
+        return KBBQ_OK;
+    }
+
     for (int64_t base = 0; base < n; base += wave * T) {
         parallel_for(T, [&](int t) {
             const int64_t a = std::min(n, base + wave * t), b = std::min(n, a + wave);

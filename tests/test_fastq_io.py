@@ -122,3 +122,38 @@ def test_write_round_trip(tmp_path):
     with open(dst) as fh:  # header without the comment, '+' line bare (kbbq/recalibrate.py:152-156)
         head = [fh.readline() for _ in range(4)]
     assert head[0] == "@" + recs[0][0] + "\n" and head[2] == "+\n"
+
+
+def test_write_to_pipe_append_and_offset_agree(tmp_path):
+    """The formatter writes at per-thread offsets into seekable files and serially into pipes and
+    O_APPEND files; the bytes must be the same, and a seekable descriptor continues where it stood."""
+    import threading
+    rng = np.random.default_rng(9)
+    recs = _random_records(rng, 20_003, 31)
+    src = tmp_path / "in.fq"
+    _write(src, recs)
+    f = fastx.NativeFastq(src, threads=4)
+    newq = rng.integers(0, 60, size=(f.N, f.L)).astype(np.uint8)
+    plain = tmp_path / "plain.fq"
+    fd = os.open(plain, os.O_WRONLY | os.O_CREAT | os.O_TRUNC)
+    os.write(fd, b"# kept\n")          # the descriptor does not start at 0
+    f.write(fd, newq)
+    os.write(fd, b"# after\n")         # ... and is left behind the records
+    os.close(fd)
+    want = plain.read_bytes()
+    assert want.startswith(b"# kept\n@") and want.endswith(b"\n# after\n")
+    body = want[len(b"# kept\n"):-len(b"# after\n")]
+    app = tmp_path / "append.fq"
+    fd = os.open(app, os.O_WRONLY | os.O_CREAT | os.O_APPEND)
+    f.write(fd, newq)
+    os.close(fd)
+    assert app.read_bytes() == body
+    r, w = os.pipe()
+    got = []
+    t = threading.Thread(target=lambda: got.append(b"".join(iter(lambda: os.read(r, 1 << 20), b""))))
+    t.start()
+    f.write(w, newq)
+    os.close(w)
+    t.join()
+    os.close(r)
+    assert got[0] == body
