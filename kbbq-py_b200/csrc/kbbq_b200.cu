@@ -68,10 +68,16 @@ static bool plan_smem(const Geom &g, int narr, int max_smem, TableCfg *tc, Stage
     const char *d = getenv("KBBQ_DREP");
     const int dmax = d ? atoi(d) : 32;
     const char *w = getenv("KBBQ_MIN_STAGES");
-    const int want0 = w ? std::max(2, std::min(8, atoi(w))) : 3;
-    for (int want = want0; want >= 2; --want) {
-        for (int kmin = 2; kmin >= 1; --kmin) {       // two groups per barrier round are worth more ...
-            for (int drep = 32; drep >= 16; drep >>= 1) {  // ... than conflict-free dinuc replicas
+    const int want = w ? std::max(2, std::min(8, atoi(w))) : 2;
+    // Measured (tools/kps_sweep.sh and the shape runs in DESIGN.md): more groups per barrier round win
+    // -- four groups x two stages beats two x four by 5 % in the 150 bp build -- as long as the stages
+    // behind the one being consumed hold the bandwidth-delay product of an SM (~30 B/clk x ~1400 clk);
+    // below that a deeper ring of smaller stages is faster (250 bp).  Both matter more than
+    // conflict-free dinuc replicas.
+    const int in_flight_min = 40000;
+    for (int pass = 0; pass < 2; ++pass) {          // pass 1: nothing holds the product; take what fits
+        for (int kmin = 2; kmin >= 1; --kmin) {
+            for (int drep = 32; drep >= 16; drep >>= 1) {
                 if (drep > dmax) continue;
                 for (int k = kmax; k >= kmin; --k) {
                     if (g.nprod > 1 && g.ng * k > 32) continue;  // one producer lane per group of a stage
@@ -82,7 +88,9 @@ static bool plan_smem(const Geom &g, int narr, int max_smem, TableCfg *tc, Stage
                         // depth has to be a multiple of their number
                         if (s % g.nprod) continue;
                         *sl = make_stage_layout(g, narr, s, k, tc->table_bytes);
-                        if (sl->total <= max_smem) return true;
+                        if (sl->total > max_smem) continue;
+                        if (pass == 0 && (s - 1) * narr * sl->abytes < in_flight_min) break;  // deepest ring that fits is too shallow
+                        return true;
                     }
                 }
             }
