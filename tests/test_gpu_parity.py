@@ -202,14 +202,26 @@ def test_input_errors_raise_like_the_reference(torch_cuda):
     assert pt.sum() == 0
 
 
-def test_full_size_properties_config2(torch_cuda):
-    """BASELINE config 2 at full size (10 M x 150 bp, 1 read group): size-independent properties."""
+FULL_SIZE = [
+    # BASELINE.json configs at full per-GPU size: (id, seed, reads, read length, read groups)
+    ("config2_10M_x150_r1", 1002, 10_000_000, 150, 1),
+    ("config3_shard_25M_x150_r8", 1003, 25_000_000, 150, 8),   # 200 M reads over 8 GPUs
+    ("config4_20M_x250_r32", 1004, 20_000_000, 250, 32),
+]
+
+
+@pytest.mark.parametrize("case", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_full_size_properties(torch_cuda, case):
+    """BASELINE configs at full size: size-independent properties (checksums of checksums, marginals,
+    linearity, the generic kernels as an independent second implementation)."""
     torch = torch_cuda
     from kbbq.device import DeviceRecalibrator, synth_reads
-    N, L, R = 10_000_000, 150, 1
-    seq, qual, corr, rg, second = synth_reads(1002, 0, N, L, R)
+    _, seed, N, L, R = case
+    seq, qual, corr, rg, second = synth_reads(seed, 0, N, L, R)
+    if R == 1:
+        rg = None
     rec = DeviceRecalibrator(L, R, max_reads=N)
-    rec.build(seq, qual, corr, None, second)
+    rec.build(seq, qual, corr, rg, second)
     whole = rec.tables.clone()
     valid = qual >= 6
     err = (seq != corr) & valid
@@ -221,27 +233,32 @@ def test_full_size_properties_config2(torch_cuda):
     per_cycle = rec.pos_total.sum((0, 1))
     assert torch.equal(per_cycle[:L], col[0]) and torch.equal(per_cycle[L:].flip(0), col[1])
     # per-quality marginal == histogram of the quality bytes
-    hist = torch.bincount(qual.view(-1).to(torch.int64), minlength=43)
+    hist = sum(torch.bincount(qual[lo:lo + 2_000_000].reshape(-1).to(torch.int64), minlength=43)
+               for lo in range(0, N, 2_000_000))
     hist[:6] = 0
     assert torch.equal(rec.pos_total.sum((0, 2)), hist)
+    if rg is not None:  # per-read-group marginal == valid bases of the reads of that group
+        per_rg = torch.zeros(R, dtype=torch.int64, device=qual.device)
+        per_rg.index_add_(0, rg.to(torch.int64), valid.sum(1))
+        assert torch.equal(rec.pos_total.sum((1, 2)), per_rg)
     assert int(rec.din_total.sum()) <= int(valid.sum()) - int(valid[:, 0].sum())
     assert bool((rec.din_errs <= rec.din_total).all()) and bool((rec.pos_errs <= rec.pos_total).all())
     # linearity: two half batches add up to the whole; the generic kernel agrees with the smem kernel
     rec.reset()
     h = N // 2
-    rec.build(seq[:h], qual[:h], corr[:h], None, second[:h])
-    rec.build(seq[h:], qual[h:], corr[h:], None, second[h:])
+    rec.build(seq[:h], qual[:h], corr[:h], None if rg is None else rg[:h], second[:h])
+    rec.build(seq[h:], qual[h:], corr[h:], None if rg is None else rg[h:], second[h:])
     assert torch.equal(rec.tables, whole)
     rec.reset()
-    rec.build(seq, qual, corr, None, second, path=2)
+    rec.build(seq, qual, corr, rg, second, path=2)
     assert torch.equal(rec.tables, whole)
     # apply: untouched below minscore, bounded otherwise, smem == generic
     rec.model()
     out = torch.empty_like(qual)
-    rec.apply(seq, qual, out, None, second)
+    rec.apply(seq, qual, out, rg, second)
     assert torch.equal(out[~valid], qual[~valid])
     assert int(out[valid].max()) <= 60
     out2 = torch.empty_like(qual)
-    rec.apply(seq, qual, out2, None, second, path=2)
+    rec.apply(seq, qual, out2, rg, second, path=2)
     assert torch.equal(out, out2)
     rec.check_status()
