@@ -8,7 +8,7 @@
 // Roofline: HBM, 2 B/base (qual + error mask) or 3 B/base (qual + seq + corrected), + 1 with a skip
 // mask.  128-bit loads, two vectors in flight per thread; histograms privatised per LANE in shared
 // memory ([warp][quality < 64][lane]: bank == lane, so the reduction is conflict free however
-// skewed the qualities are), total and errors packed in one u32 counter (1 + 65536 * error), folded
+// skewed the qualities are), total and errors packed in one u32 counter (1 + 65025 * error), folded
 // into the global int64 counts before a total field could overflow.  Qualities >= 64 (legal for
 // bincount, absent from real data) go straight to global atomics.
 #pragma once
@@ -19,7 +19,7 @@ namespace kbbq {
 constexpr int CAL_BINS = 64;
 constexpr int CAL_THREADS = 256;
 constexpr int CAL_SMEM = (CAL_THREADS / 32) * CAL_BINS * 32 * 4;  // 64 KB
-constexpr long long CAL_MAX_ITERS = 2000;  // x 32 bases per thread and iteration: a lane counter stays < 65536
+constexpr long long CAL_MAX_ITERS = 2000;  // x 32 bases per thread and iteration: a lane counter's total stays < 65025
 
 struct CalibArgs {
     const uint8_t *qual, *err, *seq, *corr, *skip;
@@ -38,15 +38,34 @@ __device__ __forceinline__ uint32_t nonzero_bytes(uint32_t x) {
     return (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & H4;
 }
 
+constexpr uint32_t CAL_ERR_UNIT = 65025u;  // 255 * 255: what an error adds on top of the 1 (as in build.cuh)
+
+// Four bases.  Branch free on the common path (every quality < 64): the increment of base b is
+// keep_b + 65025 * (error_b & keep_b), two IDP.4A with one-hot byte constants on byte masks, and its
+// address q_b * 128 + lane column is a third; a skipped base adds 0.
+template <bool HAS_SKIP>
 __device__ __forceinline__ void cal_word(uint32_t qw, uint32_t ew, uint32_t kw, uint32_t base, const CalibArgs &a) {
-    const uint32_t e = nonzero_bytes(ew), k = nonzero_bytes(kw);
+    const uint32_t e = nonzero_bytes(ew);                                    // bit 7 per byte
+    const uint32_t keep1 = HAS_SKIP ? ((~nonzero_bytes(kw)) >> 7) & ONE4 : ONE4;   // 1 per kept byte
+    uint32_t errff;  // 0xFF per kept error: PTX prmt replicates the sign of byte b for selector nibble 8 | b
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(errff) : "r"(e), "r"(0u), "r"(0xBA98u));
+    if (HAS_SKIP) errff &= keep1 * 255u;
+    if ((qw & 0xC0C0C0C0u) == 0u) {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
+        for (int b = 0; b < 4; ++b) {
+            const uint32_t inc = __dp4a(errff, 255u << (8 * b), __dp4a(keep1, 1u << (8 * b), 0u));
+            const uint32_t addr = __dp4a(qw, 128u << (8 * b), base);
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(addr), "r"(inc) : "memory");
+        }
+        return;
+    }
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {  // a quality >= 64 somewhere in the word: legal for bincount, never seen in real data
         const uint32_t q = (qw >> (8 * b)) & 0xFFu;
-        const uint32_t er = (e >> (8 * b + 7)) & 1u;
-        if ((k >> (8 * b + 7)) & 1u) continue;
+        if (!((keep1 >> (8 * b)) & 1u)) continue;
+        const uint32_t er = (errff >> (8 * b)) & 1u;
         if (q < CAL_BINS) {
-            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(base + q * 128u), "r"(1u + (er << 16)) : "memory");
+            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(base + q * 128u), "r"(1u + er * CAL_ERR_UNIT) : "memory");
         } else {
             atomicAdd(a.total + q, 1ull);
             if (er) atomicAdd(a.errs + q, 1ull);
@@ -64,8 +83,8 @@ __device__ __forceinline__ void cal_fold(unsigned int *hist, const CalibArgs &a)
             unsigned int *p = hist + (w * CAL_BINS + q) * 32 + lane;
             const unsigned int v = *p;
             *p = 0;
-            tot += v & 0xFFFFu;
-            er += v >> 16;
+            tot += v % CAL_ERR_UNIT;
+            er += v / CAL_ERR_UNIT;
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) {
@@ -113,15 +132,15 @@ __global__ void __launch_bounds__(CAL_THREADS) calibration_kernel(const __grid_c
             k0 = ldg_stream16(a.skip + 16 * v);
             if (two) k1 = ldg_stream16(a.skip + 16 * v2);
         }
-        cal_word(q0.x, e0.x, k0.x, base, a);
-        cal_word(q0.y, e0.y, k0.y, base, a);
-        cal_word(q0.z, e0.z, k0.z, base, a);
-        cal_word(q0.w, e0.w, k0.w, base, a);
+        cal_word<HAS_SKIP>(q0.x, e0.x, k0.x, base, a);
+        cal_word<HAS_SKIP>(q0.y, e0.y, k0.y, base, a);
+        cal_word<HAS_SKIP>(q0.z, e0.z, k0.z, base, a);
+        cal_word<HAS_SKIP>(q0.w, e0.w, k0.w, base, a);
         if (two) {
-            cal_word(q1.x, e1.x, k1.x, base, a);
-            cal_word(q1.y, e1.y, k1.y, base, a);
-            cal_word(q1.z, e1.z, k1.z, base, a);
-            cal_word(q1.w, e1.w, k1.w, base, a);
+            cal_word<HAS_SKIP>(q1.x, e1.x, k1.x, base, a);
+            cal_word<HAS_SKIP>(q1.y, e1.y, k1.y, base, a);
+            cal_word<HAS_SKIP>(q1.z, e1.z, k1.z, base, a);
+            cal_word<HAS_SKIP>(q1.w, e1.w, k1.w, base, a);
         }
     }
     // tail: the last n % 16 bases, one thread each
