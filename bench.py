@@ -45,22 +45,67 @@ def measured_peak_gbs():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock and throttle reasons sampled DURING the timed region: NVML from a background thread (one
+    sample per millisecond: the timed region is tens of milliseconds long), nvidia-smi -lms as fallback."""
     QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, gpu_index):
-        self.proc = None
-        self.gpu_index = gpu_index
+        import threading
+        self.proc, self.thread, self.stop_flag = None, None, threading.Event()
+        self.sm, self.bits, self.smax, self.how = [], 0, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            uuid = None
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+            except Exception:
+                pass
+            handle = None
+            if uuid:
+                try:
+                    handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+                except Exception:
+                    handle = None
+            if handle is None:
+                handle = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(handle, pynvml.NVML_CLOCK_SM))
+            reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+                pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+
+            def loop():
+                while not self.stop_flag.is_set():
+                    try:
+                        self.sm.append(float(pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)))
+                        self.bits |= int(reasons(handle))
+                    except Exception:
+                        pass
+                    time.sleep(0.001)
+            self.thread = threading.Thread(target=loop, daemon=True)
+            self.thread.start()
+            self.how = "nvml"
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.QUERY, "--format=csv,noheader,nounits",
                  "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.how = "nvidia-smi"
         except Exception:
             self.proc = None
 
     def stop(self):
+        if self.thread is not None:
+            self.stop_flag.set()
+            self.thread.join(timeout=2)
+            reasons = sorted(k for k, bit in self.REASONS.items() if self.bits & bit)
+            return {"sm_mhz": statistics.median(self.sm) if self.sm else None, "sm_max_mhz": self.smax,
+                    "samples": len(self.sm), "reasons": reasons, "source": "nvml, 1 ms period, timed region only"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -85,7 +130,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 100"}
 
 
 def cpu_port_throughput(n_reads, L, R, seed, target_s, threads=0):
