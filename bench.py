@@ -139,7 +139,9 @@ def cpu_port_throughput(n_reads, L, R, seed, target_s, threads=0):
     import oracle
     from kbbq import synth
     oracle.build()
-    threads = threads or oracle.max_threads()
+    # every hardware thread this process may run on; torchrun exports OMP_NUM_THREADS=1 to its workers, which
+    # omp_get_max_threads() would obey, so the count is passed explicitly (omp_set_num_threads in the oracle)
+    threads = threads or len(os.sched_getaffinity(0)) or oracle.max_threads()
     probe = min(n_reads, 100_000)
     data = synth.synth_reads(seed, 0, probe, L, R)
     t0 = time.perf_counter()
