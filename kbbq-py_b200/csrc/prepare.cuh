@@ -93,17 +93,22 @@ __device__ __forceinline__ void identity_rows(const PrepArgs &a, long long grp, 
 // Single read group, pass 1: do all groups look like group 0, with every row tallied?  Then the
 // kernels need no work list at all (uni[0] stays 0) and pass 2 returns at once.  Reads 1-3 B/read.
 __global__ void prep_uniform_kernel(PrepArgs a) {
-    const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (grp == 0) {
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    if (t0 == 0) {
         a.seg[0] = 0;
         a.seg[1] = (unsigned int)a.ngroups;
     }
-    if (grp >= a.ngroups) return;
-    unsigned int exist, sec, exist0, sec0;
-    identity_rows(a, grp, exist, sec, true);
+    unsigned int exist0, sec0;
     identity_rows(a, 0, exist0, sec0, false);
-    if (exist != exist0 || sec != sec0 || exist0 != (1u << a.G) - 1u) a.uni[0] = 1u;
-    if (grp == 0) {
+    bool differs = exist0 != (1u << a.G) - 1u;
+    for (long long grp = t0; grp < a.ngroups; grp += stride) {  // a few thousand threads, coalesced byte loads
+        unsigned int exist, sec;
+        identity_rows(a, grp, exist, sec, true);
+        differs |= exist != exist0 || sec != sec0;
+    }
+    if (differs) a.uni[0] = 1u;
+    if (t0 == 0) {
         const entry_t p0 = make_entry(0u, 0, exist0, sec0);
         a.uni[1] = p0.z;
         a.uni[2] = p0.w;
@@ -113,17 +118,18 @@ __global__ void prep_uniform_kernel(PrepArgs a) {
 // Single read group, pass 2 (only when the groups differ): the list is the identity.
 __global__ void prep_identity_kernel(PrepArgs a) {
     if (a.uni[0] == 0u) return;
-    const long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (grp >= a.ngroups) return;
-    unsigned int exist, sec;
-    identity_rows(a, grp, exist, sec, false);
-    // a stage is one contiguous span: ng consecutive groups from the start of the CTA's slice, the
-    // first one 16-byte aligned down
     const unsigned long long E = (unsigned long long)a.ngroups;
-    const unsigned long long lo = slice_lo(E, slice_of(E, (unsigned long long)grp, a.grid), a.grid);
-    const unsigned int j = (unsigned int)(((unsigned long long)grp - lo) % (unsigned int)a.ng);
-    const unsigned int mis0 = (unsigned int)((((unsigned long long)grp - j) * a.gbytes) & 15ull);
-    a.entries[grp] = make_entry(mis0 + j * a.gbytes, grp, exist, sec);
+    for (long long grp = (long long)blockIdx.x * blockDim.x + threadIdx.x; grp < a.ngroups;
+         grp += (long long)gridDim.x * blockDim.x) {
+        unsigned int exist, sec;
+        identity_rows(a, grp, exist, sec, false);
+        // a stage is one contiguous span: ng consecutive groups from the start of the CTA's slice, the
+        // first one 16-byte aligned down
+        const unsigned long long lo = slice_lo(E, slice_of(E, (unsigned long long)grp, a.grid), a.grid);
+        const unsigned int j = (unsigned int)(((unsigned long long)grp - lo) % (unsigned int)a.ng);
+        const unsigned int mis0 = (unsigned int)((((unsigned long long)grp - j) * a.gbytes) & 15ull);
+        a.entries[grp] = make_entry(mis0 + j * a.gbytes, grp, exist, sec);
+    }
 }
 
 // mode 0: count list entries per read group into a.cursor; mode 1: scatter entries.
@@ -266,9 +272,10 @@ inline int run_prepare(const uint16_t *rg, const uint8_t *second, long long N, i
     }
     const unsigned int blocks = (unsigned int)((a.ngroups + PREP_THREADS - 1) / PREP_THREADS);
     if (R == 1) {
-        prep_uniform_kernel<<<blocks, PREP_THREADS, 0, st>>>(a);
+        const unsigned int few = std::min<unsigned int>(blocks, (unsigned int)std::max(grid, 1) * 8u);
+        prep_uniform_kernel<<<few, PREP_THREADS, 0, st>>>(a);
         KBBQ_LAUNCHED();
-        prep_identity_kernel<<<blocks, PREP_THREADS, 0, st>>>(a);
+        prep_identity_kernel<<<few, PREP_THREADS, 0, st>>>(a);
         KBBQ_LAUNCHED();
         return KBBQ_OK;
     }
