@@ -114,17 +114,24 @@ int kbbq_posterior_q_real(const double *prior_q_dev, const int64_t *numerrs_dev,
  * reverse complement there (bamread_bqsr_dinuc, :33-50).  Tables as kbbq_build's, accumulating.
  * kbbq_apply_bam is applybqsr.recalibrate_bamread (kbbq/gatk/applybqsr.py:65-78): whole-read cycles
  * flipped on the reverse strand, reverse-complement dinucleotides, same delta tables as kbbq_apply.
+ * With a workspace of kbbq_bam_workspace_bytes(N, L, R) device bytes the batch is first rewritten
+ * into canonical reads (position = cycle, reverse strand complemented, skipped and N bases at quality
+ * 0) and goes through the shared-memory kernels of kbbq_build / kbbq_apply; with workspace == NULL the
+ * direct one-thread-per-base kernels run (global atomics: correct, two orders of magnitude slower).
  */
+int kbbq_bam_workspace_bytes(int64_t N, int L, int R, size_t *bytes);
 int kbbq_build_bam(const uint8_t *seq_dev, const uint8_t *qual_dev, const uint8_t *err_dev,
                    const uint8_t *skip_dev, const uint16_t *rg_dev, const uint8_t *flags_dev,
                    const uint16_t *aln_start_dev, const uint16_t *aln_end_dev, int64_t N, int L, int R,
                    int minscore, int64_t *pos_errs_dev, int64_t *pos_total_dev, int64_t *din_errs_dev,
-                   int64_t *din_total_dev, int *status_dev, void *stream);
+                   int64_t *din_total_dev, void *workspace_dev, size_t workspace_bytes, int *status_dev,
+                   void *stream);
 int kbbq_apply_bam(const uint8_t *seq_dev, const uint8_t *qual_dev, const uint16_t *rg_dev,
                    const uint8_t *flags_dev, int64_t N, int L, int R, int minscore,
                    const int64_t *meanq_dev, const int64_t *rgdq_dev, const int64_t *qdq_dev,
                    const int64_t *posdq_dev, const int64_t *dindq_dev, int nq, int ndin1,
-                   uint8_t *out_qual_dev, int *status_dev, void *stream);
+                   uint8_t *out_qual_dev, void *workspace_dev, size_t workspace_bytes, int *status_dev,
+                   void *stream);
 
 /*
  * Calibration benchmark counts: the two np.bincount calls of

@@ -134,4 +134,108 @@ __global__ void apply_bam_kernel(ApplyBamArgs a) {
     }
 }
 
+// ---- canonical form: the BAM side on the FASTQ kernels --------------------------------------------
+// The direct kernels above hit a few thousand hot cells of the global tables with atomics from every
+// SM (215 ms for 10 M x 150 bp with one read group).  Everything that distinguishes an aligned read
+// from a FASTQ read is a permutation and a mask, so one streaming pass rewrites a batch into reads the
+// shared-memory kernels (build.cuh / apply.cuh) tally and recalibrate as they are:
+//   position p of the rewritten read = cycle p: base lo + p of the aligned window, or hi - 1 - p and
+//   complemented (anything but ACGT -> N) on the reverse strand; the rest of the row is N with quality 0;
+//   quality 0 (below every minscore >= 1) for skipped bases and N bases, which the BAM tally leaves out
+//   of BOTH tables while the FASTQ tally would count an N in the cycle table; corrected base = base ^ 1
+//   where the host flagged an error; second = read 2.
+// The previous base in read direction is then simply the previous byte, for either strand.  Bases
+// outside the window that the host did NOT mark as skipped are tallied at cycle 0 / dinucleotide 0 as
+// the reference does (kbbq/gatk/bqsr.py:24,43: the "full" arrays start as zeros); they are rare
+// (find_read_errors skips every soft clip), so they take global atomics here.
+struct BamCanonArgs {
+    const uint8_t *seq, *qual, *err, *skip;
+    const uint16_t *rg;
+    const uint8_t *flags;
+    const uint16_t *aln_start, *aln_end;
+    long long N;
+    int L, R, minscore;
+    bool build;               // false: apply (whole read, qualities untouched, no corrected array)
+    uint8_t *cseq, *cqual, *ccorr, *csecond;
+    unsigned long long *pos_errs, *pos_total, *din_errs, *din_total;
+    int *status;
+};
+
+__device__ __forceinline__ uint8_t bam_complement(uint8_t b) {
+    return b == 'A' ? 'T' : b == 'T' ? 'A' : b == 'G' ? 'C' : b == 'C' ? 'G' : 'N';
+}
+
+// One warp per read at a time (no index division), lanes over the positions of the read, byte
+// accesses: 6.4 ms for 10 M x 150 bp, instruction bound (a shared-memory staged variant with 32-bit
+// global accesses executed more instructions per read and took 11 ms; the next step would be the
+// 4-bases-per-thread SWAR form of build.cuh).
+constexpr int BAM_WARPS = 8;  // warps per block of the canonical-form kernels
+
+__global__ void __launch_bounds__(BAM_WARPS * 32) bam_canon_kernel(BamCanonArgs a) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long nwarps = (long long)gridDim.x * BAM_WARPS;
+    const uint8_t *__restrict__ seq = a.seq, *__restrict__ qual = a.qual, *__restrict__ errp = a.err,
+                  *__restrict__ skipp = a.skip;
+    for (long long r = (long long)blockIdx.x * BAM_WARPS + warp; r < a.N; r += nwarps) {
+        const int fl = a.flags ? a.flags[r] : 0;
+        const bool reverse = fl & BAM_FLAG_REVERSE;
+        int lo = 0, hi = a.L;
+        if (a.build) {
+            lo = a.aln_start ? a.aln_start[r] : 0;
+            hi = a.aln_end ? a.aln_end[r] : a.L;
+            if (lo > a.L) lo = a.L;
+            if (hi > a.L) hi = a.L;
+            if (hi < lo) hi = lo;
+        }
+        const int alen = hi - lo;
+        const long long row = r * a.L;
+#pragma unroll 2
+        for (int p = lane; p < a.L; p += 32) {
+            // every position reads exactly one source base -- inside the window the one that lands here,
+            // outside it one clipped base ([0, lo) then [hi, L)) -- so the loads are unconditional and
+            // independent of each other (a load behind a data-dependent branch costs a full round trip)
+            const bool inside = p < alen;
+            const int k = p - alen;
+            const long long i = row + (inside ? (reverse ? hi - 1 - p : lo + p) : (k < lo ? k : hi + (k - lo)));
+            const uint8_t s = seq[i];
+            const unsigned int qq = qual[i];
+            const bool e = a.build && errp[i] != 0;
+            const bool sk = a.build && skipp && skipp[i] != 0;
+            uint8_t b = 'N', q = 0, c = 'N';
+            if (inside) {
+                b = reverse ? bam_complement(s) : s;
+                q = (a.build && (sk || s == 'N')) ? (uint8_t)0 : (uint8_t)qq;
+                c = e ? (uint8_t)(b ^ 1) : b;
+            } else if (a.build && !sk && (int)qq >= a.minscore && s != 'N') {
+                const unsigned int g = a.rg ? a.rg[r] : 0;
+                if (qq > NQ - 1) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
+                else if (g >= (unsigned int)a.R) atomicOr(a.status, KBBQ_FLAG_RG_RANGE);
+                else {
+                    const size_t po = ((size_t)g * NQ + qq) * (2 * a.L), d = ((size_t)g * NQ + qq) * 16;
+                    atomicAdd(a.pos_total + po, 1ull);
+                    atomicAdd(a.din_total + d, 1ull);
+                    if (e) { atomicAdd(a.pos_errs + po, 1ull); atomicAdd(a.din_errs + d, 1ull); }
+                }
+            }
+            a.cseq[row + p] = b;
+            a.cqual[row + p] = q;
+            if (a.build) a.ccorr[row + p] = c;
+        }
+        if (lane == 0) a.csecond[r] = (uint8_t)(fl & BAM_FLAG_READ2);
+    }
+}
+
+// out[r][i] = canonical out[r][p(i)]: flips the reverse-strand reads back (apply only)
+__global__ void __launch_bounds__(BAM_WARPS * 32) bam_uncanon_kernel(const uint8_t *__restrict__ cout, const uint8_t *flags,
+                                                                    long long N, int L, uint8_t *__restrict__ out) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long nwarps = (long long)gridDim.x * BAM_WARPS;
+    for (long long r = (long long)blockIdx.x * BAM_WARPS + warp; r < N; r += nwarps) {
+        const bool reverse = flags && (flags[r] & BAM_FLAG_REVERSE);
+        const long long row = r * L;
+#pragma unroll 2
+        for (int i = lane; i < L; i += 32) out[row + i] = cout[row + (reverse ? L - 1 - i : i)];
+    }
+}
+
 }  // namespace kbbq

@@ -296,10 +296,38 @@ int kbbq_posterior_q_real(const double *prior_q, const int64_t *numerrs, const i
     return KBBQ_OK;
 }
 
+// Workspace of the BAM-side entry points: the canonical copies of the batch (bam.cuh) followed by the
+// workspace of kbbq_build / kbbq_apply.
+struct BamWorkspace {
+    uint8_t *cseq, *cqual, *cthird, *csecond;  // third array: corrected reads (build) / canonical output (apply)
+    void *inner;
+    size_t inner_bytes, bytes;
+};
+static BamWorkspace carve_bam_workspace(void *base, long long N, int L, int R) {
+    BamWorkspace w = {};
+    char *p = (char *)base;
+    size_t off = 0;
+    const size_t nb = align_up((size_t)N * L + 16, 256);
+    w.cseq = (uint8_t *)(p + off); off += nb;
+    w.cqual = (uint8_t *)(p + off); off += nb;
+    w.cthird = (uint8_t *)(p + off); off += nb;
+    w.csecond = (uint8_t *)(p + off); off += align_up((size_t)N + 16, 256);
+    w.inner = p + off;
+    w.inner_bytes = carve_workspace(nullptr, N, L, R).bytes;
+    w.bytes = off + w.inner_bytes;
+    return w;
+}
+
+int kbbq_bam_workspace_bytes(int64_t N, int L, int R, size_t *bytes) {
+    if (N < 0 || L < 1 || R < 1 || R > 65535 || !bytes) return KBBQ_E_ARG;
+    *bytes = carve_bam_workspace(nullptr, N, L, R).bytes;
+    return KBBQ_OK;
+}
+
 int kbbq_build_bam(const uint8_t *seq, const uint8_t *qual, const uint8_t *err, const uint8_t *skip, const uint16_t *rg,
                    const uint8_t *flags, const uint16_t *aln_start, const uint16_t *aln_end, int64_t N, int L, int R,
                    int minscore, int64_t *pos_errs, int64_t *pos_total, int64_t *din_errs, int64_t *din_total,
-                   int *status, void *stream) {
+                   void *workspace, size_t workspace_bytes, int *status, void *stream) {
     if (N < 0 || L < 1 || L > 32767 || R < 1 || R > 65535 || minscore < 0 || minscore > NQ) return KBBQ_E_ARG;
     if (!pos_errs || !pos_total || !din_errs || !din_total || !status) return KBBQ_E_ARG;
     if (N == 0) return KBBQ_OK;
@@ -307,19 +335,33 @@ int kbbq_build_bam(const uint8_t *seq, const uint8_t *qual, const uint8_t *err, 
     int device, sms = KBBQ_SM_COUNT_FALLBACK;
     KBBQ_CUDA(cudaGetDevice(&device));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long blocks = std::min<long long>(((long long)N * L + 255) / 256, (long long)sms * 16);
+    if (workspace && minscore >= 1) {  // canonical form + the shared-memory build kernel
+        BamWorkspace w = carve_bam_workspace(workspace, N, L, R);
+        if (workspace_bytes < w.bytes) return KBBQ_E_WORKSPACE;
+        BamCanonArgs c = {seq, qual, err, skip, rg, flags, aln_start, aln_end, N, L, R, minscore, true,
+                          w.cseq, w.cqual, w.cthird, w.csecond,
+                          (unsigned long long *)pos_errs, (unsigned long long *)pos_total,
+                          (unsigned long long *)din_errs, (unsigned long long *)din_total, status};
+        bam_canon_kernel<<<(unsigned)std::min<long long>((N + BAM_WARPS - 1) / BAM_WARPS, (long long)sms * 8), BAM_WARPS * 32, 0, st>>>(c);
+        KBBQ_LAUNCHED();
+        return kbbq_build(w.cseq, w.cqual, w.cthird, rg, w.csecond, N, L, R, minscore, pos_errs, pos_total, din_errs,
+                          din_total, w.inner, w.inner_bytes, status, 0, stream);
+    }
+    // no workspace (or minscore 0, where no quality can mean "skip"): direct kernel, global atomics
     BuildBamArgs a = {seq, qual, err, skip, rg, flags, aln_start, aln_end, N, L, R, minscore,
                       (unsigned long long *)pos_errs, (unsigned long long *)pos_total,
                       (unsigned long long *)din_errs, (unsigned long long *)din_total, status};
-    const long long blocks = std::min<long long>(((long long)N * L + 255) / 256, (long long)sms * 16);
-    build_bam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    build_bam_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
     KBBQ_LAUNCHED();
     return KBBQ_OK;
 }
 
 int kbbq_apply_bam(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, const uint8_t *flags, int64_t N, int L,
                    int R, int minscore, const int64_t *meanq, const int64_t *rgdq, const int64_t *qdq,
-                   const int64_t *posdq, const int64_t *dindq, int nq, int ndin1, uint8_t *out_qual, int *status,
-                   void *stream) {
+                   const int64_t *posdq, const int64_t *dindq, int nq, int ndin1, uint8_t *out_qual, void *workspace,
+                   size_t workspace_bytes, int *status, void *stream) {
     if (N < 0 || L < 1 || L > 32767 || R < 1 || R > 65535 || nq < 1 || nq > 256 || ndin1 != 17) return KBBQ_E_ARG;
     if (!meanq || !rgdq || !qdq || !posdq || !dindq || !status) return KBBQ_E_ARG;
     if (N == 0) return KBBQ_OK;
@@ -327,11 +369,26 @@ int kbbq_apply_bam(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, 
     int device, sms = KBBQ_SM_COUNT_FALLBACK;
     KBBQ_CUDA(cudaGetDevice(&device));
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long blocks = std::min<long long>(((long long)N * L + 255) / 256, (long long)sms * 16);
+    if (workspace && minscore >= 1 && nq <= NQ) {  // canonical form + the shared-memory apply kernel + flip back
+        BamWorkspace w = carve_bam_workspace(workspace, N, L, R);
+        if (workspace_bytes < w.bytes) return KBBQ_E_WORKSPACE;
+        BamCanonArgs c = {seq, qual, nullptr, nullptr, rg, flags, nullptr, nullptr, N, L, R, minscore, false,
+                          w.cseq, w.cqual, nullptr, w.csecond, nullptr, nullptr, nullptr, nullptr, status};
+        bam_canon_kernel<<<(unsigned)std::min<long long>((N + BAM_WARPS - 1) / BAM_WARPS, (long long)sms * 8), BAM_WARPS * 32, 0, st>>>(c);
+        KBBQ_LAUNCHED();
+        int rc = kbbq_apply(w.cseq, w.cqual, rg, w.csecond, N, L, R, minscore, meanq, rgdq, qdq, posdq, dindq, nq, ndin1,
+                            w.cthird, w.inner, w.inner_bytes, status, 0, stream);
+        if (rc) return rc;
+        bam_uncanon_kernel<<<(unsigned)std::min<long long>((N + BAM_WARPS - 1) / BAM_WARPS, (long long)sms * 8), BAM_WARPS * 32, 0, st>>>(w.cthird, flags, N, L, out_qual);
+        KBBQ_LAUNCHED();
+        return KBBQ_OK;
+    }
     ApplyBamArgs a = {seq, qual, rg, flags, out_qual, N, L, R, minscore, nq, ndin1, (const long long *)meanq,
                       (const long long *)rgdq, (const long long *)qdq, (const long long *)posdq,
                       (const long long *)dindq, status};
-    const long long blocks = std::min<long long>(((long long)N * L + 255) / 256, (long long)sms * 16);
-    apply_bam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(a);
+    apply_bam_kernel<<<(unsigned)blocks, 256, 0, st>>>(a);
     KBBQ_LAUNCHED();
     return KBBQ_OK;
 }
@@ -937,9 +994,13 @@ int kbbq_build_bam_host(const uint8_t *seq, const uint8_t *qual, const uint8_t *
     KBBQ_CUDA(cudaMemcpy(dt + 2 * npos, din_errs, ndin * 8, cudaMemcpyHostToDevice));
     KBBQ_CUDA(cudaMemcpy(dt + 2 * npos + ndin, din_total, ndin * 8, cudaMemcpyHostToDevice));
     KBBQ_CUDA(cudaMemset(dst, 0, sizeof(int)));
+    size_t ws_bytes = 0;
+    KBBQ_TRY(kbbq_bam_workspace_bytes(N, L, R, &ws_bytes));
+    DevBuf ws;
+    KBBQ_TRY(ws.alloc(ws_bytes));
     KBBQ_TRY(kbbq_build_bam(ds, dq, de, skip ? dk : nullptr, rg ? dr : nullptr, flags ? df : nullptr,
                             aln_start ? d0 : nullptr, aln_end ? d1 : nullptr, N, L, R, minscore, dt, dt + npos,
-                            dt + 2 * npos, dt + 2 * npos + ndin, dst, nullptr));
+                            dt + 2 * npos, dt + 2 * npos + ndin, ws.p, ws_bytes, dst, nullptr));
     KBBQ_CUDA(cudaMemcpy(pos_errs, dt, npos * 8, cudaMemcpyDeviceToHost));
     KBBQ_CUDA(cudaMemcpy(pos_total, dt + npos, npos * 8, cudaMemcpyDeviceToHost));
     KBBQ_CUDA(cudaMemcpy(din_errs, dt + 2 * npos, ndin * 8, cudaMemcpyDeviceToHost));
@@ -974,8 +1035,12 @@ int kbbq_apply_bam_host(const uint8_t *seq, const uint8_t *qual, const uint16_t 
     KBBQ_CUDA(up(d_qdq, qdq, n_q * 8)); KBBQ_CUDA(up(d_posdq, posdq, n_q * 2 * L * 8));
     KBBQ_CUDA(up(d_dindq, dindq, n_q * ndin1 * 8));
     KBBQ_CUDA(cudaMemset(dst, 0, sizeof(int)));
+    size_t ws_bytes = 0;
+    KBBQ_TRY(kbbq_bam_workspace_bytes(N, L, R, &ws_bytes));
+    DevBuf ws;
+    KBBQ_TRY(ws.alloc(ws_bytes));
     KBBQ_TRY(kbbq_apply_bam(ds, dq, rg ? dr : nullptr, flags ? df : nullptr, N, L, R, minscore, d_meanq, d_rgdq, d_qdq,
-                            d_posdq, d_dindq, nq, ndin1, dout, dst, nullptr));
+                            d_posdq, d_dindq, nq, ndin1, dout, ws.p, ws_bytes, dst, nullptr));
     if (nb) KBBQ_CUDA(cudaMemcpy(out_qual, dout, nb, cudaMemcpyDeviceToHost));
     int st = 0;
     KBBQ_CUDA(cudaMemcpy(&st, dst, sizeof(int), cudaMemcpyDeviceToHost));

@@ -42,8 +42,9 @@ SIGNATURES = {
     "kbbq_posterior_q_real_host": (_i, [_vp, _vp, _vp, _i64, _vp, _i]),
     "kbbq_calibration_counts": (_i, [_vp] * 5 + [_i64, _vp, _vp, _vp]),
     "kbbq_calibration_counts_host": (_i, [_vp] * 5 + [_i64, _vp, _vp, _i]),
-    "kbbq_build_bam": (_i, [_vp] * 8 + [_i64, _i, _i, _i] + [_vp] * 4 + [_vp, _vp]),
-    "kbbq_apply_bam": (_i, [_vp] * 4 + [_i64, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, _vp, _vp]),
+    "kbbq_bam_workspace_bytes": (_i, [_i64, _i, _i, C.POINTER(_sz)]),
+    "kbbq_build_bam": (_i, [_vp] * 8 + [_i64, _i, _i, _i] + [_vp] * 4 + [_vp, _sz, _vp, _vp]),
+    "kbbq_apply_bam": (_i, [_vp] * 4 + [_i64, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, _vp, _sz, _vp, _vp]),
     "kbbq_build_bam_host": (_i, [_vp] * 8 + [_i64, _i, _i, _i] + [_vp] * 4 + [_vp, _i]),
     "kbbq_apply_bam_host": (_i, [_vp] * 4 + [_i64, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, _vp, _i]),
     "kbbq_marginals_host": (_i, [_vp, _vp, _i, _i] + [_vp] * 5 + [_i]),

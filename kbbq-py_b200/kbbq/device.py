@@ -106,22 +106,34 @@ class DeviceRecalibrator:
                                  self._stream())
         _native.check(rc)
 
-    def build_bam(self, seq, qual, err, skip=None, rg=None, flags=None, aln_start=None, aln_end=None):
+    def build_bam(self, seq, qual, err, skip=None, rg=None, flags=None, aln_start=None, aln_end=None, fast=True):
         """Accumulate a batch of aligned reads (kbbq_build_bam): err / skip u8 [N, L] from the host's CIGAR
         walk, flags u8 [N] (bit 0 read 2, bit 1 reverse strand), aln_start / aln_end int16 [N]."""
         N = seq.numel() // self.L
+        ws = self._bam_workspace(N) if fast else None
         rc = self.lib.kbbq_build_bam(_p(seq), _p(qual), _p(err), _p(skip), _p(rg), _p(flags), _p(aln_start),
                                      _p(aln_end), N, self.L, self.R, self.minscore, _p(self.pos_errs),
-                                     _p(self.pos_total), _p(self.din_errs), _p(self.din_total), _p(self.status),
-                                     self._stream())
+                                     _p(self.pos_total), _p(self.din_errs), _p(self.din_total), _p(ws),
+                                     0 if ws is None else ws.numel(), _p(self.status), self._stream())
         _native.check(rc)
 
-    def apply_bam(self, seq, qual, out, rg=None, flags=None):
+    def _bam_workspace(self, n_reads):
+        """Canonical copies of a BAM batch + the build / apply workspace (kbbq_bam_workspace_bytes)."""
+        if n_reads > getattr(self, "bam_ws_reads", -1):
+            nbytes = C.c_size_t(0)
+            _native.check(self.lib.kbbq_bam_workspace_bytes(n_reads, self.L, self.R, C.byref(nbytes)))
+            self.bam_ws = torch.empty(max(nbytes.value, 256), dtype=torch.uint8, device=self.device)
+            self.bam_ws_reads = n_reads
+        return self.bam_ws
+
+    def apply_bam(self, seq, qual, out, rg=None, flags=None, fast=True):
         """Recalibrated qualities of a batch of aligned reads (kbbq_apply_bam)."""
         N = seq.numel() // self.L
+        ws = self._bam_workspace(N) if fast else None
         rc = self.lib.kbbq_apply_bam(_p(seq), _p(qual), _p(rg), _p(flags), N, self.L, self.R, self.minscore,
                                      _p(self.meanq), _p(self.rgdq), _p(self.qdq), _p(self.posdq), _p(self.dindq),
-                                     NQ, 17, _p(out), _p(self.status), self._stream())
+                                     NQ, 17, _p(out), _p(ws), 0 if ws is None else ws.numel(), _p(self.status),
+                                     self._stream())
         _native.check(rc)
 
     def check_status(self):

@@ -156,20 +156,25 @@ def test_bam_device_entry_points_against_the_oracle(oracle_mod):
     a0 = rng.integers(0, 8, size=N).astype(np.uint16) * (rng.random(N) < 0.4)
     a1 = (L - rng.integers(0, 8, size=N) * (rng.random(N) < 0.4)).astype(np.uint16)
     a0 = a0.astype(np.uint16)
+    # a few bases outside the aligned window that the host did not mark: tallied at cycle 0 / dinuc AA (reference quirk)
+    skip[::97, -1] = 0
+    skip[::89, 0] = 0
     want = oracle_mod.build_tables_bam(seq, qual, err, skip, rg, flags, a0, a1, L, R)
-    rec = DeviceRecalibrator(L, R, max_reads=0)
     dev = lambda a: torch.from_numpy(a.view(np.int16) if a.dtype == np.uint16 else a).cuda()
-    for lo in range(0, N, 25_000):
-        sl = slice(lo, min(N, lo + 25_000))
-        rec.build_bam(dev(seq[sl]), dev(qual[sl]), dev(err[sl]), dev(skip[sl]), dev(rg[sl]), dev(flags[sl]),
-                      dev(a0[sl]), dev(a1[sl]))
-    tables = rec.covariate_arrays()
-    rec.check_status()
-    for key, a, b in zip(TABLE_KEYS[5:], tables[5:], want):
-        assert np.array_equal(a, b), key
-    deltas = rec.delta_qs()
-    out = torch.empty(N, L, dtype=torch.uint8, device="cuda")
-    rec.apply_bam(dev(seq), dev(qual), out, dev(rg), dev(flags))
-    rec.check_status()
-    want_o = oracle_mod.apply_bam(seq, qual, rg, flags, L, R, tables[0], *deltas)
-    assert np.array_equal(out.cpu().numpy().astype(np.int16), want_o)
+    # fast = canonical form + the shared-memory kernels; not fast = the direct kernels (global atomics)
+    for fast in (True, False):
+        rec = DeviceRecalibrator(L, R, max_reads=0)
+        for lo in range(0, N, 25_000):
+            sl = slice(lo, min(N, lo + 25_000))
+            rec.build_bam(dev(seq[sl]), dev(qual[sl]), dev(err[sl]), dev(skip[sl]), dev(rg[sl]), dev(flags[sl]),
+                          dev(a0[sl]), dev(a1[sl]), fast=fast)
+        tables = rec.covariate_arrays()
+        rec.check_status()
+        for key, a, b in zip(TABLE_KEYS[5:], tables[5:], want):
+            assert np.array_equal(a, b), (key, fast)
+        deltas = rec.delta_qs()
+        out = torch.empty(N, L, dtype=torch.uint8, device="cuda")
+        rec.apply_bam(dev(seq), dev(qual), out, dev(rg), dev(flags), fast=fast)
+        rec.check_status()
+        want_o = oracle_mod.apply_bam(seq, qual, rg, flags, L, R, tables[0], *deltas)
+        assert np.array_equal(out.cpu().numpy().astype(np.int16), want_o), fast
