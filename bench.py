@@ -346,12 +346,27 @@ def run_b200(args):
                                                          ("second", second), ("rg", rg))}
             d_out = torch.empty_like(qual)
             rec2 = DeviceRecalibrator(L, R, max_reads=N, device=dev)
+            # as kbbq_recalibrate_host does, the corrected reads cross PCIe as a mismatch bit map made by this
+            # rank's share of the host threads (KBBQ_HOST_NO_BITMAP=1: as they are)
+            use_bits = os.environ.get("KBBQ_HOST_NO_BITMAP", "0") in ("", "0")
+            nwords = (N * L + 31) // 32
+            h_bits = torch.empty(nwords, dtype=torch.int32, pin_memory=True)
+            d_bits = torch.empty(nwords, dtype=torch.int32, device=dev)
+            host_threads = max(1, len(os.sched_getaffinity(0)) // world)
 
             def e2e_step():
-                for k in ("seq", "qual", "corr", "second") + (("rg",) if R > 1 else ()):
+                for k in ("seq", "qual", "second") + (("rg",) if R > 1 else ()):
                     d_in[k].copy_(h[k], non_blocking=True)
                 rec2.tables.zero_()
-                rec2.build(d_in["seq"], d_in["qual"], d_in["corr"], d_in["rg"] if R > 1 else None, d_in["second"])
+                rg_d = d_in["rg"] if R > 1 else None
+                if use_bits:
+                    _native.check(lib.kbbq_host_mismatch_bits(_native.ptr(a["seq"].reshape(-1)), _native.ptr(a["corr"].reshape(-1)),
+                                                              N * L, C.c_void_p(h_bits.data_ptr()), host_threads))
+                    d_bits.copy_(h_bits, non_blocking=True)
+                    rec2.build_from_bits(d_in["seq"], d_in["qual"], d_bits, d_in["corr"], rg_d, d_in["second"])
+                else:
+                    d_in["corr"].copy_(h["corr"], non_blocking=True)
+                    rec2.build(d_in["seq"], d_in["qual"], d_in["corr"], rg_d, d_in["second"])
                 rec2.allreduce()
                 rec2.model()
                 rec2.apply(d_in["seq"], d_in["qual"], d_out, d_in["rg"] if R > 1 else None, d_in["second"])
@@ -374,7 +389,7 @@ def run_b200(args):
         # bytes that cross PCIe per step: kbbq_recalibrate_host sends the corrected reads as a 1-bit-per-base
         # mismatch map made by the host cores inside the call (csrc/host_pack.cpp) unless KBBQ_HOST_NO_BITMAP=1;
         # the device-API path of the multi-rank step copies all three arrays
-        bitmap = world == 1 and os.environ.get("KBBQ_HOST_NO_BITMAP", "0") in ("", "0")
+        bitmap = os.environ.get("KBBQ_HOST_NO_BITMAP", "0") in ("", "0")
         corr_bytes = (N * L + 31) // 32 * 4 if bitmap else N * L
         e2e = {"value": world * N * L * ke / dt, "unit": UNIT,
                "h2d_bytes_per_step": 2 * N * L + corr_bytes + N + (2 * N if R > 1 else 0), "d2h_bytes_per_step": N * L,

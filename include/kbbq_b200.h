@@ -278,6 +278,10 @@ int kbbq_fastq_write(int fd, const kbbq_fastq *f, int64_t first, int64_t n, cons
  * over PCIe instead of the corrected reads (1/8 of the bytes) unless KBBQ_HOST_NO_BITMAP=1.
  */
 int kbbq_host_mismatch_bits(const uint8_t *seq, const uint8_t *corr, int64_t n, uint32_t *bits, int threads);
+/* The device side of that: corr_dev[i] = seq_dev[i] ^ bit i, a byte array that differs from seq exactly
+ * where the corrected read did -- all kbbq_build looks at.  seq_dev / corr_dev 16-byte aligned. */
+int kbbq_expand_mismatch_bits(const uint8_t *seq_dev, const uint32_t *bits_dev, int64_t n, uint8_t *corr_dev,
+                              void *stream);
 
 /* Number of kernel launches this library has issued since load (bench.py's gpu_launches). */
 int64_t kbbq_launch_count(void);

@@ -647,6 +647,15 @@ ModelPtrs carve_model(int64_t *base, int L, int R) {
 
 extern "C" {
 
+int kbbq_expand_mismatch_bits(const uint8_t *seq, const uint32_t *bits, int64_t n, uint8_t *corr, void *stream) {
+    if (n < 0 || (n > 0 && (!seq || !bits || !corr))) return KBBQ_E_ARG;
+    if (n == 0) return KBBQ_OK;
+    if (((uintptr_t)seq | (uintptr_t)corr) & 15u) return KBBQ_E_ARG;
+    expand_corr_kernel<<<(unsigned)((n + 16 * 256 - 1) / (16 * 256)), 256, 0, (cudaStream_t)stream>>>(seq, bits, corr, n);
+    KBBQ_LAUNCHED();
+    return KBBQ_OK;
+}
+
 int kbbq_host_release(int device) {
     if (device < 0 || device >= 64) return KBBQ_E_ARG;
     HostArena &A = g_arena[device];

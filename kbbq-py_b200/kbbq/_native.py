@@ -62,6 +62,7 @@ SIGNATURES = {
     "kbbq_fastq_check_names": (_i, [_vp, _vp, _i64, _i, C.POINTER(_i64)]),
     "kbbq_fastq_write": (_i, [_i, _vp, _i64, _i64, _vp, _i]),
     "kbbq_host_mismatch_bits": (_i, [_vp, _vp, _i64, _vp, _i]),
+    "kbbq_expand_mismatch_bits": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "kbbq_plan_info": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i)]),
 }
 

@@ -80,6 +80,12 @@ class DeviceRecalibrator:
                                  _p(self.workspace), self.ws_bytes, _p(self.status), path, self._stream())
         _native.check(rc)
 
+    def build_from_bits(self, seq, qual, bits, corr_scratch, rg=None, second=None):
+        """build() when the corrected reads arrive as the 1-bit-per-base mismatch map of
+        kbbq_host_mismatch_bits (int32 tensor): it is expanded into `corr_scratch` (u8, like seq) first."""
+        _native.check(self.lib.kbbq_expand_mismatch_bits(_p(seq), _p(bits), seq.numel(), _p(corr_scratch), self._stream()))
+        self.build(seq, qual, corr_scratch, rg, second)
+
     def allreduce(self):
         """Sum the partial tables over all ranks: the one collective of the path."""
         parallel.allreduce_tables(self.tables, self.pg)
