@@ -165,76 +165,149 @@ __device__ __forceinline__ uint8_t bam_complement(uint8_t b) {
     return b == 'A' ? 'T' : b == 'T' ? 'A' : b == 'G' ? 'C' : b == 'C' ? 'G' : 'N';
 }
 
-// One warp per read at a time (no index division), lanes over the positions of the read, byte
-// accesses: 6.4 ms for 10 M x 150 bp, instruction bound (a shared-memory staged variant with 32-bit
-// global accesses executed more instructions per read and took 11 ms; the next step would be the
-// 4-bases-per-thread SWAR form of build.cuh).
+// ---- the rewrite pass -------------------------------------------------------------------------------
+// One thread produces one ALIGNED 32-bit word of every output array, i.e. four
+// positions, from four source bytes fetched as two aligned words and a funnel shift (the source
+// window starts at any byte, and runs backwards on the reverse strand: byte-reversed with one PRMT).
+// Masks are byte-parallel as in build.cuh.  Words that reach outside the aligned window or the read
+// (at most three per read) take the byte-wise path, which also does the reference's cycle-0 tally of
+// unskipped bases outside the window.  One base per thread with byte accesses took 6.4 ms for
+// 10 M x 150 bp (182 instructions per base); this form is bound by memory instead.
 constexpr int BAM_WARPS = 8;  // warps per block of the canonical-form kernels
 
-__global__ void __launch_bounds__(BAM_WARPS * 32) bam_canon_kernel(BamCanonArgs a) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long nwarps = (long long)gridDim.x * BAM_WARPS;
+__device__ __forceinline__ uint32_t load4_any(const uint8_t *__restrict__ p) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8u;
+    const uint32_t lo = w[0], hi = sh ? w[1] : 0u;  // nothing is read past the word that holds the last byte
+    return __funnelshift_r(lo, hi, sh);
+}
+// 0xFF in every byte of x that is not zero
+__device__ __forceinline__ uint32_t nonzero_mask(uint32_t x) {
+    uint32_t m = (((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & H4, r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(m), "r"(0u), "r"(0xBA98u));  // sign of byte b -> byte b
+    return r;
+}
+// complement.get(x, 'N') on four bases (kbbq/gatk/bqsr.py:40): A <-> T, C <-> G, anything else N
+__device__ __forceinline__ uint32_t complement4(uint32_t w) {
+    const uint32_t code3 = (w >> 1) & 0x07070707u;          // A 0, C 1, T 2, G 3, N 7
+    const uint32_t y = code3 | (code3 >> 4);
+    const uint32_t sel = __byte_perm(y, 0u, 0x4420u) & 0x7777u;
+    const uint32_t self = __byte_perm(0x47544341u /* A C T G */, 0x4E000000u /* . . . N */, sel);
+    const uint32_t comp = __byte_perm(0x43414754u /* T G A C */, 0x4E4E4E4Eu, sel);
+    const uint32_t bad = nonzero_mask(self ^ w);              // a byte that is not the base its code stands for
+    return (comp & ~bad) | (0x4E4E4E4Eu & bad);
+}
+
+// One thread per aligned output word (`wmax` word slots per read, r0 = first read of this launch), so
+// that nothing waits for anything: a warp-per-read loop was bound by its chain of round trips.
+__global__ void __launch_bounds__(BAM_WARPS * 32) bam_canon_kernel(BamCanonArgs a, long long r0, unsigned int wmax) {
+    const unsigned int t = blockIdx.x * (unsigned int)(BAM_WARPS * 32) + threadIdx.x;
+    const unsigned int rl = t / wmax;
+    const int k = (int)(t - rl * wmax);
+    const long long r = r0 + rl;
+    if (r >= a.N) return;
     const uint8_t *__restrict__ seq = a.seq, *__restrict__ qual = a.qual, *__restrict__ errp = a.err,
                   *__restrict__ skipp = a.skip;
-    for (long long r = (long long)blockIdx.x * BAM_WARPS + warp; r < a.N; r += nwarps) {
-        const int fl = a.flags ? a.flags[r] : 0;
-        const bool reverse = fl & BAM_FLAG_REVERSE;
-        int lo = 0, hi = a.L;
+    const int fl = a.flags ? a.flags[r] : 0;
+    const bool reverse = fl & BAM_FLAG_REVERSE;
+    int lo = 0, hi = a.L;
+    if (a.build) {
+        lo = a.aln_start ? a.aln_start[r] : 0;
+        hi = a.aln_end ? a.aln_end[r] : a.L;
+        if (lo > a.L) lo = a.L;
+        if (hi > a.L) hi = a.L;
+        if (hi < lo) hi = lo;
+    }
+    const int alen = hi - lo;
+    const long long row = r * a.L;
+    // output words are aligned in memory: word k holds positions 4 k - ao .. 4 k - ao + 3 (the three
+    // canonical arrays share their alignment: carve_bam_workspace)
+    const int ao = (int)((uintptr_t)(a.cseq + row) & 3);
+    if (k == 0) a.csecond[r] = (uint8_t)(fl & BAM_FLAG_READ2);
+    if (k >= ((ao + a.L + 3) >> 2)) return;
+    const int p0 = 4 * k - ao;
+    if (p0 >= 0 && p0 + 3 < alen) {  // four positions inside the window: word path
+        const long long s = row + (reverse ? hi - 4 - p0 : lo + p0);
+        uint32_t ws = load4_any(seq + s), wq = load4_any(qual + s), we = 0u, wk = 0u;
         if (a.build) {
-            lo = a.aln_start ? a.aln_start[r] : 0;
-            hi = a.aln_end ? a.aln_end[r] : a.L;
-            if (lo > a.L) lo = a.L;
-            if (hi > a.L) hi = a.L;
-            if (hi < lo) hi = lo;
+            we = load4_any(errp + s);
+            if (skipp) wk = load4_any(skipp + s);
         }
-        const int alen = hi - lo;
-        const long long row = r * a.L;
-#pragma unroll 2
-        for (int p = lane; p < a.L; p += 32) {
-            // every position reads exactly one source base -- inside the window the one that lands here,
-            // outside it one clipped base ([0, lo) then [hi, L)) -- so the loads are unconditional and
-            // independent of each other (a load behind a data-dependent branch costs a full round trip)
-            const bool inside = p < alen;
-            const int k = p - alen;
-            const long long i = row + (inside ? (reverse ? hi - 1 - p : lo + p) : (k < lo ? k : hi + (k - lo)));
-            const uint8_t s = seq[i];
-            const unsigned int qq = qual[i];
-            const bool e = a.build && errp[i] != 0;
-            const bool sk = a.build && skipp && skipp[i] != 0;
-            uint8_t b = 'N', q = 0, c = 'N';
-            if (inside) {
-                b = reverse ? bam_complement(s) : s;
-                q = (a.build && (sk || s == 'N')) ? (uint8_t)0 : (uint8_t)qq;
-                c = e ? (uint8_t)(b ^ 1) : b;
-            } else if (a.build && !sk && (int)qq >= a.minscore && s != 'N') {
-                const unsigned int g = a.rg ? a.rg[r] : 0;
-                if (qq > NQ - 1) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
-                else if (g >= (unsigned int)a.R) atomicOr(a.status, KBBQ_FLAG_RG_RANGE);
-                else {
-                    const size_t po = ((size_t)g * NQ + qq) * (2 * a.L), d = ((size_t)g * NQ + qq) * 16;
-                    atomicAdd(a.pos_total + po, 1ull);
-                    atomicAdd(a.din_total + d, 1ull);
-                    if (e) { atomicAdd(a.pos_errs + po, 1ull); atomicAdd(a.din_errs + d, 1ull); }
-                }
+        if (reverse) {
+            ws = __byte_perm(ws, 0u, 0x0123u);
+            wq = __byte_perm(wq, 0u, 0x0123u);
+            we = __byte_perm(we, 0u, 0x0123u);
+            wk = __byte_perm(wk, 0u, 0x0123u);
+        }
+        const uint32_t b4 = reverse ? complement4(ws) : ws;
+        uint32_t q4 = wq;
+        if (a.build) {
+            const uint32_t is_n = ~nonzero_mask(ws ^ 0x4E4E4E4Eu);      // the ORIGINAL base is N (:96)
+            q4 &= ~(is_n | nonzero_mask(wk));
+            *reinterpret_cast<uint32_t *>(a.ccorr + row + p0) = b4 ^ (nonzero_mask(we) & ONE4);
+        }
+        *reinterpret_cast<uint32_t *>(a.cseq + row + p0) = b4;
+        *reinterpret_cast<uint32_t *>(a.cqual + row + p0) = q4;
+        return;
+    }
+    for (int j = 0; j < 4; ++j) {  // a word at an edge of the window or of the read: byte by byte
+        const int p = p0 + j;
+        if (p < 0 || p >= a.L) continue;
+        // every position reads exactly one source base: inside the window the one that lands here,
+        // outside it one clipped base ([0, lo) then [hi, L))
+        const bool inside = p < alen;
+        const int kk = p - alen;
+        const long long i = row + (inside ? (reverse ? hi - 1 - p : lo + p) : (kk < lo ? kk : hi + (kk - lo)));
+        const uint8_t s = seq[i];
+        const unsigned int qq = qual[i];
+        const bool e = a.build && errp[i] != 0;
+        const bool sk = a.build && skipp && skipp[i] != 0;
+        uint8_t b = 'N', q = 0, c = 'N';
+        if (inside) {
+            b = reverse ? bam_complement(s) : s;
+            q = (a.build && (sk || s == 'N')) ? (uint8_t)0 : (uint8_t)qq;
+            c = e ? (uint8_t)(b ^ 1) : b;
+        } else if (a.build && !sk && (int)qq >= a.minscore && s != 'N') {
+            const unsigned int g = a.rg ? a.rg[r] : 0;
+            if (qq > NQ - 1) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
+            else if (g >= (unsigned int)a.R) atomicOr(a.status, KBBQ_FLAG_RG_RANGE);
+            else {
+                const size_t po = ((size_t)g * NQ + qq) * (2 * a.L), d = ((size_t)g * NQ + qq) * 16;
+                atomicAdd(a.pos_total + po, 1ull);
+                atomicAdd(a.din_total + d, 1ull);
+                if (e) { atomicAdd(a.pos_errs + po, 1ull); atomicAdd(a.din_errs + d, 1ull); }
             }
-            a.cseq[row + p] = b;
-            a.cqual[row + p] = q;
-            if (a.build) a.ccorr[row + p] = c;
         }
-        if (lane == 0) a.csecond[r] = (uint8_t)(fl & BAM_FLAG_READ2);
+        a.cseq[row + p] = b;
+        a.cqual[row + p] = q;
+        if (a.build) a.ccorr[row + p] = c;
     }
 }
 
-// out[r][i] = canonical out[r][p(i)]: flips the reverse-strand reads back (apply only)
+// out[r][i] = canonical out[r][p(i)]: flips the reverse-strand reads back (apply only); aligned output words
 __global__ void __launch_bounds__(BAM_WARPS * 32) bam_uncanon_kernel(const uint8_t *__restrict__ cout, const uint8_t *flags,
-                                                                    long long N, int L, uint8_t *__restrict__ out) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long nwarps = (long long)gridDim.x * BAM_WARPS;
-    for (long long r = (long long)blockIdx.x * BAM_WARPS + warp; r < N; r += nwarps) {
-        const bool reverse = flags && (flags[r] & BAM_FLAG_REVERSE);
-        const long long row = r * L;
-#pragma unroll 2
-        for (int i = lane; i < L; i += 32) out[row + i] = cout[row + (reverse ? L - 1 - i : i)];
+                                                                    long long N, int L, uint8_t *__restrict__ out,
+                                                                    long long r0, unsigned int wmax) {
+    const unsigned int t = blockIdx.x * (unsigned int)(BAM_WARPS * 32) + threadIdx.x;
+    const unsigned int rl = t / wmax;
+    const int k = (int)(t - rl * wmax);
+    const long long r = r0 + rl;
+    if (r >= N) return;
+    const bool reverse = flags && (flags[r] & BAM_FLAG_REVERSE);
+    const long long row = r * L;
+    const int ao = (int)((uintptr_t)(out + row) & 3);
+    if (k >= ((ao + L + 3) >> 2)) return;
+    const int i0 = 4 * k - ao;
+    if (i0 >= 0 && i0 + 3 < L) {
+        uint32_t w = load4_any(cout + row + (reverse ? L - 4 - i0 : i0));
+        if (reverse) w = __byte_perm(w, 0u, 0x0123u);
+        *reinterpret_cast<uint32_t *>(out + row + i0) = w;
+        return;
+    }
+    for (int j = 0; j < 4; ++j) {
+        const int i = i0 + j;
+        if (i >= 0 && i < L) out[row + i] = cout[row + (reverse ? L - 1 - i : i)];
     }
 }
 

@@ -318,6 +318,18 @@ static BamWorkspace carve_bam_workspace(void *base, long long N, int L, int R) {
     return w;
 }
 
+// one thread per output word; 32-bit thread indices, so very large batches take several launches
+static int launch_bam_canon(const BamCanonArgs &c, cudaStream_t st) {
+    const unsigned int wmax = (unsigned int)((3 + c.L + 3) >> 2);
+    const long long per = std::max<long long>(1, (long long)(0x7FFFFFFFu / wmax) / 256 * 256);
+    for (long long r0 = 0; r0 < c.N; r0 += per) {
+        const long long n = std::min<long long>(per, c.N - r0);
+        bam_canon_kernel<<<(unsigned)((n * wmax + BAM_WARPS * 32 - 1) / (BAM_WARPS * 32)), BAM_WARPS * 32, 0, st>>>(c, r0, wmax);
+        KBBQ_LAUNCHED();
+    }
+    return KBBQ_OK;
+}
+
 int kbbq_bam_workspace_bytes(int64_t N, int L, int R, size_t *bytes) {
     if (N < 0 || L < 1 || R < 1 || R > 65535 || !bytes) return KBBQ_E_ARG;
     *bytes = carve_bam_workspace(nullptr, N, L, R).bytes;
@@ -344,8 +356,7 @@ int kbbq_build_bam(const uint8_t *seq, const uint8_t *qual, const uint8_t *err, 
                           w.cseq, w.cqual, w.cthird, w.csecond,
                           (unsigned long long *)pos_errs, (unsigned long long *)pos_total,
                           (unsigned long long *)din_errs, (unsigned long long *)din_total, status};
-        bam_canon_kernel<<<(unsigned)std::min<long long>((N + BAM_WARPS - 1) / BAM_WARPS, (long long)sms * 8), BAM_WARPS * 32, 0, st>>>(c);
-        KBBQ_LAUNCHED();
+        { const int rc_ = launch_bam_canon(c, st); if (rc_) return rc_; }
         return kbbq_build(w.cseq, w.cqual, w.cthird, rg, w.csecond, N, L, R, minscore, pos_errs, pos_total, din_errs,
                           din_total, w.inner, w.inner_bytes, status, 0, stream);
     }
@@ -376,13 +387,20 @@ int kbbq_apply_bam(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, 
         if (workspace_bytes < w.bytes) return KBBQ_E_WORKSPACE;
         BamCanonArgs c = {seq, qual, nullptr, nullptr, rg, flags, nullptr, nullptr, N, L, R, minscore, false,
                           w.cseq, w.cqual, nullptr, w.csecond, nullptr, nullptr, nullptr, nullptr, status};
-        bam_canon_kernel<<<(unsigned)std::min<long long>((N + BAM_WARPS - 1) / BAM_WARPS, (long long)sms * 8), BAM_WARPS * 32, 0, st>>>(c);
-        KBBQ_LAUNCHED();
+        { const int rc_ = launch_bam_canon(c, st); if (rc_) return rc_; }
         int rc = kbbq_apply(w.cseq, w.cqual, rg, w.csecond, N, L, R, minscore, meanq, rgdq, qdq, posdq, dindq, nq, ndin1,
                             w.cthird, w.inner, w.inner_bytes, status, 0, stream);
         if (rc) return rc;
-        bam_uncanon_kernel<<<(unsigned)std::min<long long>((N + BAM_WARPS - 1) / BAM_WARPS, (long long)sms * 8), BAM_WARPS * 32, 0, st>>>(w.cthird, flags, N, L, out_qual);
-        KBBQ_LAUNCHED();
+        {
+            const unsigned int wmax = (unsigned int)((3 + L + 3) >> 2);
+            const long long per = std::max<long long>(1, (long long)(0x7FFFFFFFu / wmax) / 256 * 256);  // reads per launch
+            for (long long r0 = 0; r0 < N; r0 += per) {
+                const long long n = std::min<long long>(per, N - r0);
+                bam_uncanon_kernel<<<(unsigned)((n * wmax + BAM_WARPS * 32 - 1) / (BAM_WARPS * 32)), BAM_WARPS * 32, 0, st>>>(
+                    w.cthird, flags, N, L, out_qual, r0, wmax);
+                KBBQ_LAUNCHED();
+            }
+        }
         return KBBQ_OK;
     }
     ApplyBamArgs a = {seq, qual, rg, flags, out_qual, N, L, R, minscore, nq, ndin1, (const long long *)meanq,
