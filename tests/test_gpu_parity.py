@@ -262,3 +262,32 @@ def test_full_size_properties(torch_cuda, case):
     rec.apply(seq, qual, out2, rg, second, path=2)
     assert torch.equal(out, out2)
     rec.check_status()
+
+
+def test_random_shapes_vs_oracle(torch_cuda, oracle_mod):
+    """Seeded sweep over read lengths (every alignment class, the generic-kernel range L > 288 included),
+    read-group counts, batch sizes that leave partial groups, unpaired reads and N-rich data; path 0 is
+    what a caller gets (shared-memory kernels when the plan fits, generic otherwise)."""
+    from kbbq import synth
+    rng = np.random.default_rng(2026)
+    shapes = [(4, 1), (5, 2), (7, 3), (9, 1), (33, 4), (64, 2), (75, 1), (99, 3), (101, 1), (126, 6), (149, 2),
+              (152, 1), (200, 9), (251, 2), (287, 1), (288, 2), (289, 1), (300, 3), (400, 1)]
+    for L, R in shapes:
+        N = int(rng.integers(1, 9000))
+        seq, qual, corr, rg, second = synth.synth_reads(int(rng.integers(1, 1 << 30)), 0, N, L, R)
+        if rng.random() < 0.5:   # unpaired: read groups and mates in no particular order
+            rg = rng.integers(0, R, N).astype(np.uint16)
+            second = rng.integers(0, 2, N).astype(np.uint8)
+        if rng.random() < 0.5:   # N-rich, with low qualities elsewhere too
+            isn = rng.random((N, L)) < 0.1
+            seq = np.where(isn, np.uint8(ord("N")), seq)
+            qual = np.where(rng.random((N, L)) < 0.1, rng.integers(0, 8, (N, L)), qual).astype(np.uint8)
+        want_t = oracle_mod.covariate_arrays(seq, qual, corr, rg, second, L, R)
+        want_d = oracle_mod.get_delta_qs(*want_t)
+        want_o = oracle_mod.apply(seq, qual, rg, second, L, R, want_t[0], *want_d)
+        tables, deltas, out = _run_device(torch_cuda, seq, qual, corr, rg, second, L, R, 0, int(rng.integers(1, 4)))
+        for got, want, key in zip(tables, want_t, TABLE_KEYS):
+            assert np.array_equal(got, want), (key, L, R, N)
+        for got, want, key in zip(deltas, want_d, DELTA_KEYS):
+            assert np.array_equal(got, want), (key, L, R, N)
+        assert np.array_equal(out.astype(np.int16), want_o), (L, R, N)
