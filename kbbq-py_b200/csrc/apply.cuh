@@ -82,6 +82,7 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
     const uint32_t nstages = pin(sl.stages), ngs = pin(sl.ngs);
     const uint32_t revoff = t.revoff, addq = t.addq, gbytes = g.gbytes;
     const uint32_t addnq = (uint32_t)(128 - a.nq) * ONE4;  // q + this has bit 7 set iff q >= nq (q < 128)
+    const uint32_t one = pin(1u);                          // see add_fma (build.cuh)
     uint32_t stage = 0, phase = 0;
     uint32_t qgood = 0xFFFFFFFFu;
 
@@ -153,8 +154,8 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qw) : "r"(wa + abytes));
                 asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pb) : "r"(wa - 1));
 
-                const uint32_t nu = ~(qw + addnq);          // bit 7 clear <=> q >= nq: IndexError in the reference
-                const uint32_t w5 = qw + addq;
+                const uint32_t nu = ~add_fma(qw, one, addnq);  // bit 7 clear <=> q >= nq: IndexError in the reference
+                const uint32_t w5 = add_fma(qw, one, addq);
                 qgood &= nu & ~qw;
                 const uint32_t vraw = w5 & nu & ~qw;
                 const uint32_t vm8 = prmt(vraw, 0u, selv);  // 0xFF for owned bytes with minscore - 1 <= q < nq
