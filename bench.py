@@ -348,11 +348,13 @@ def run_b200(args):
             rec2 = DeviceRecalibrator(L, R, max_reads=N, device=dev)
             # as kbbq_recalibrate_host does, the corrected reads cross PCIe as a mismatch bit map made by this
             # rank's share of the host threads (KBBQ_HOST_NO_BITMAP=1: as they are)
-            use_bits = os.environ.get("KBBQ_HOST_NO_BITMAP", "0") in ("", "0")
+            host_threads = max(1, len(os.sched_getaffinity(0)) // world)
+            # ... when this rank's share is at least 8 threads: with fewer the comparison (27 ms for 1.5 Gbases on
+            # 16 threads) takes longer than the 27 ms the corrected reads need on the wire
+            use_bits = os.environ.get("KBBQ_HOST_NO_BITMAP", "0") in ("", "0") and host_threads >= 8
             nwords = (N * L + 31) // 32
             h_bits = torch.empty(nwords, dtype=torch.int32, pin_memory=True)
             d_bits = torch.empty(nwords, dtype=torch.int32, device=dev)
-            host_threads = max(1, len(os.sched_getaffinity(0)) // world)
 
             def e2e_step():
                 for k in ("seq", "qual", "second") + (("rg",) if R > 1 else ()):
@@ -389,7 +391,8 @@ def run_b200(args):
         # bytes that cross PCIe per step: kbbq_recalibrate_host sends the corrected reads as a 1-bit-per-base
         # mismatch map made by the host cores inside the call (csrc/host_pack.cpp) unless KBBQ_HOST_NO_BITMAP=1;
         # the device-API path of the multi-rank step copies all three arrays
-        bitmap = os.environ.get("KBBQ_HOST_NO_BITMAP", "0") in ("", "0")
+        bitmap = os.environ.get("KBBQ_HOST_NO_BITMAP", "0") in ("", "0") and \
+            (world == 1 or len(os.sched_getaffinity(0)) // world >= 8)
         corr_bytes = (N * L + 31) // 32 * 4 if bitmap else N * L
         e2e = {"value": world * N * L * ke / dt, "unit": UNIT,
                "h2d_bytes_per_step": 2 * N * L + corr_bytes + N + (2 * N if R > 1 else 0), "d2h_bytes_per_step": N * L,
