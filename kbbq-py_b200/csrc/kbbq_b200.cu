@@ -262,7 +262,7 @@ int kbbq_marginals(const int64_t *pos_errs, const int64_t *pos_total, int L, int
     marginals_q_kernel<<<dim3(NQ, R), 128, 0, st>>>((const long long *)pos_errs, (const long long *)pos_total,
                                                    2 * L, (long long *)q_errs, (long long *)q_total);
     KBBQ_LAUNCHED();
-    marginals_rg_kernel<<<(R + 63) / 64, 64, 0, st>>>((const long long *)q_errs, (const long long *)q_total, R,
+    marginals_rg_kernel<<<R, 64, 0, st>>>((const long long *)q_errs, (const long long *)q_total, R,
                                                       (long long *)rg_errs, (long long *)rg_total, (long long *)meanq);
     KBBQ_LAUNCHED();
     return KBBQ_OK;
