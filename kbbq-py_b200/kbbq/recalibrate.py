@@ -47,9 +47,81 @@ def fastq_to_covariate_arrays(fastq, infer_rg=False, minscore=6, maxscore=42):
     return _tables_from_batch(batch, minscore)
 
 
+STREAM_ABOVE_BYTES = 4 << 30      # larger FASTQ files go through the device in batches (host memory stays bounded)
+STREAM_BATCH_READS = 8_000_000
+
+
+def _stdout_fd():
+    """Descriptor of sys.stdout, or None when it is not a real file (a StringIO, a capture object)."""
+    try:
+        fd = sys.stdout.fileno()
+    except (AttributeError, OSError, ValueError):
+        return None
+    sys.stdout.flush()
+    return fd
+
+
+def _recalibrate_fastq_streamed(fastq, infer_rg, batch_reads):
+    """The two passes of kbbq/recalibrate.py:123-156 over batches of `batch_reads` reads: pass 1 packs a
+    batch from the indexed files, builds its tables on the GPU and adds them up (integer tables are
+    additive), the model runs once, pass 2 packs each batch again, applies and prints it.  Host memory
+    holds one batch (plus 8 bytes of index per read); the result is the one of the single-batch path."""
+    from . import fastx
+    reads, fixed = fastx.NativeFastq(fastq[0]), fastx.NativeFastq(fastq[1])
+    n = min(reads.N, fixed.N)
+    reads.check_names(fixed, n)
+    if n == 0:
+        return
+    if reads.L < 0 or fixed.L != reads.L:
+        raise ValueError("operands could not be broadcast together: reads of unequal length")
+    rg, second, keys = reads.infer(infer_rg)
+    L, R = reads.L, max(1, len(keys))
+    from concurrent.futures import ThreadPoolExecutor
+    starts = list(range(0, n, batch_reads))
+
+    def pack(lo, with_corr):
+        m = min(batch_reads, n - lo)
+        seq, qual = reads.pack(lo, m)
+        return lo, m, seq, qual, (fixed.pack(lo, m)[0] if with_corr else None)
+
+    def batches(with_corr):
+        # the next batch is tokenised (native code, GIL released) while the GPU works on this one
+        with ThreadPoolExecutor(1) as pool:
+            nxt = pool.submit(pack, starts[0], with_corr)
+            for i in range(len(starts)):
+                cur = nxt.result()
+                if i + 1 < len(starts):
+                    nxt = pool.submit(pack, starts[i + 1], with_corr)
+                yield cur
+
+    tables = None
+    for lo, m, seq, qual, corr in batches(True):
+        part = _native.build_host(seq, qual, corr, rg[lo:lo + m], second[lo:lo + m], L, R, 6)
+        tables = part if tables is None else tuple(a + b for a, b in zip(tables, part))
+    fixed.close()
+    meanq, rg_e, rg_t, q_e, q_t = _native.marginals_host(tables[0], tables[1])
+    deltas = _native.get_delta_qs_host(meanq, rg_e, rg_t, q_e, q_t, *tables)
+    fd = _stdout_fd()
+    for lo, m, seq, qual, _ in batches(False):
+        out = _native.apply_host(seq, qual, rg[lo:lo + m], second[lo:lo + m], L, R, meanq, *deltas)
+        if fd is not None:
+            reads.write(fd, out, lo, m)
+        else:
+            txt = (out + np.uint8(33)).astype(np.uint8)
+            sys.stdout.write(''.join('@%s\n%s\n+\n%s\n' % (reads.name(lo + i), seq[i].tobytes().decode(),
+                                                          txt[i].tobytes().decode('latin-1')) for i in range(m)))
+    reads.close()
+
+
 def recalibrate_fastq(fastq, infer_rg=False):
     """Recalibrate fastq[0] given its corrected twin fastq[1]; FASTQ to stdout
     (reference: kbbq/recalibrate.py:123-156: name without comment, sequence, '+', chr(q + 33))."""
+    import os
+    batch_reads = int(os.environ.get("KBBQ_BATCH_READS", "0"))
+    if batch_reads <= 0 and os.path.getsize(fastq[0]) > STREAM_ABOVE_BYTES:
+        batch_reads = STREAM_BATCH_READS
+    if batch_reads > 0:
+        return _recalibrate_fastq_streamed(fastq, infer_rg, batch_reads)
     batch = ReadBatch.from_fastq(fastq, infer_rg)
     if batch.N == 0:
         return

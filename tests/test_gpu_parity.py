@@ -100,6 +100,14 @@ def test_golden_cases_python_api(golden_case, tmp_path, capfd):
     assert all(lines[4 * i] == "@" + names[i] and lines[4 * i + 2] == "+" for i in range(len(names)))
     if "fastq_out" in g.files:
         assert text == str(g["fastq_out"])
+    # the same through the batch-streaming driver (what files above 4 GiB take): identical text
+    import os
+    os.environ["KBBQ_BATCH_READS"] = "48"
+    try:
+        recalibrate.recalibrate_fastq((str(fu), str(fc)), infer_rg=infer)
+    finally:
+        del os.environ["KBBQ_BATCH_READS"]
+    assert capfd.readouterr().out == text
 
 
 def test_delta_grid_matches_reference():
