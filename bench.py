@@ -248,6 +248,27 @@ def run_streamed(args):
         dist.destroy_process_group()
 
 
+def bind_to_gpu_cpus(gpu_index):
+    """Several ranks on one host: run this rank (and first-touch its pinned buffers) on the CPUs NVML names
+    as local to its GPU, so that the end-to-end copies do not cross sockets.  Returns the CPU count or None."""
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+        cpus = {64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -262,6 +283,8 @@ def run_b200(args):
         raise SystemExit("bench.py: no CUDA device (kbbq_b200 has no CPU path)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    total_cpus = len(os.sched_getaffinity(0))
+    numa = bind_to_gpu_cpus(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -348,7 +371,7 @@ def run_b200(args):
             rec2 = DeviceRecalibrator(L, R, max_reads=N, device=dev)
             # as kbbq_recalibrate_host does, the corrected reads cross PCIe as a mismatch bit map made by this
             # rank's share of the host threads (KBBQ_HOST_NO_BITMAP=1: as they are)
-            host_threads = max(1, len(os.sched_getaffinity(0)) // world)
+            host_threads = max(1, total_cpus // world)
             # ... when this rank's share is at least 8 threads: with fewer the comparison (27 ms for 1.5 Gbases on
             # 16 threads) takes longer than the 27 ms the corrected reads need on the wire
             use_bits = os.environ.get("KBBQ_HOST_NO_BITMAP", "0") in ("", "0") and host_threads >= 8
@@ -392,7 +415,7 @@ def run_b200(args):
         # mismatch map made by the host cores inside the call (csrc/host_pack.cpp) unless KBBQ_HOST_NO_BITMAP=1;
         # the device-API path of the multi-rank step copies all three arrays
         bitmap = os.environ.get("KBBQ_HOST_NO_BITMAP", "0") in ("", "0") and \
-            (world == 1 or len(os.sched_getaffinity(0)) // world >= 8)
+            (world == 1 or total_cpus // world >= 8)
         corr_bytes = (N * L + 31) // 32 * 4 if bitmap else N * L
         e2e = {"value": world * N * L * ke / dt, "unit": UNIT,
                "h2d_bytes_per_step": 2 * N * L + corr_bytes + N + (2 * N if R > 1 else 0), "d2h_bytes_per_step": N * L,
@@ -444,6 +467,8 @@ def run_b200(args):
     }
     if e2e:
         line["e2e"] = e2e
+    if numa:
+        line["config"]["host"] = "each rank bound to the %d CPUs local to its GPU (NVML affinity)" % numa
     if world == 1 and not args.no_cpu:
         oracle, data, sample, threads = cpu_port_throughput(N, L, R, SEED, args.cpu_seconds)
         passes, t0 = 0, time.perf_counter()
