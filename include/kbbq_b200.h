@@ -49,11 +49,13 @@ extern "C" {
 #define KBBQ_E_NAME_FIELD (-8)    /* --infer-rg: a name without a second '_' field (IndexError in the reference) */
 #define KBBQ_E_NAME_RG (-9)       /* --infer-rg: the second '_' field does not start with RG (AssertionError) */
 #define KBBQ_E_NAME_MISMATCH (-10) /* corrected read's name does not start with the read's (AssertionError) */
+#define KBBQ_E_PEER (-11)          /* multi-GPU entry points: a device cannot reach a peer's memory */
 
 /* bits of the device status word */
 #define KBBQ_FLAG_QUAL_RANGE 1 /* a quality > 42: IndexError in the reference */
 #define KBBQ_FLAG_BAD_BASE 2   /* a base outside ACGTN: TypeError in Dinucleotide.vecget */
 #define KBBQ_FLAG_RG_RANGE 4   /* rg[i] >= R */
+#define KBBQ_FLAG_SEGMENTS 8   /* kbbq_*_segmented: malformed span table (not sorted / not 16-row aligned / past rows_bound) */
 
 int kbbq_abi_version(void);
 const char *kbbq_strerror(int code);
@@ -171,6 +173,51 @@ int kbbq_apply(const uint8_t *seq_dev, const uint8_t *qual_dev, const uint16_t *
                const int64_t *posdq_dev, const int64_t *dindq_dev, int nq, int ndin1,
                uint8_t *out_qual_dev, void *workspace_dev, size_t workspace_bytes, int *status_dev,
                int path, void *stream);
+
+/*
+ * Segmented batch layout -- the HBM layout of batches with several read groups.
+ *
+ * The hot kernels keep the tables of ONE read group in shared memory.  kbbq_build / kbbq_apply accept reads of
+ * all read groups in any order (rg[] per read) and then gather the pairs of each read group through a work list
+ * (one bulk copy per pair: 37-53 % of the HBM roofline).  A SEGMENTED batch stores the rows sorted by
+ * key = 2 * rg + second:  rows [seg[k], seg[k+1]) hold the reads of key k, every seg[k] a multiple of 16 rows,
+ * rows past the last read of a span are padding (quality 0, base 'A').  Every span streams like a
+ * one-read-group batch, so the kernels run at their one-read-group speed for any R; rg[] / second[] are not read.
+ * Semantics are those of kbbq_build / kbbq_apply on the same reads in any order (tables are sums over reads,
+ * kbbq/recalibrate.py:59-64,111-119; the apply is per base, kbbq/compare_reads.py:320-328).
+ *
+ *   seg_dev   uint32[kbbq_segment_table_elems(R)]: [0 .. 2R] span offsets in rows, then 2R row counts, then scratch
+ *   dest_dev  uint32[N]: row of read i in the segmented batch (0xFFFFFFFF for a read with rg >= R)
+ *   segmented arrays hold kbbq_segment_rows_bound(N, R) rows (N rounded up to 16 + 32 R), 16-byte aligned
+ *
+ * kbbq_segment_plan computes seg and dest from rg / second (either may be NULL = all 0); kbbq_segment_rows
+ * moves one u8[N*L] array into the layout (dst row dest[i] = src row i), kbbq_segment_pad fills the padding rows
+ * of seq / qual / corr (any may be NULL), kbbq_unsegment_rows brings an array (the recalibrated qualities) back
+ * into read order.  A packer that knows rg before it writes a row can produce the layout directly.
+ * kbbq_segmented_supported: 1 when the shape has a shared-memory plan (else use kbbq_build / kbbq_apply).
+ */
+int64_t kbbq_segment_rows_bound(int64_t N, int R);
+int64_t kbbq_segment_table_elems(int R);
+int kbbq_segmented_supported(int L, int R, int minscore);
+int kbbq_segment_plan(const uint16_t *rg_dev, const uint8_t *second_dev, int64_t N, int R, uint32_t *seg_dev,
+                      uint32_t *dest_dev, int *status_dev, void *stream);
+int kbbq_segment_rows(const uint8_t *src_dev, const uint32_t *dest_dev, int64_t N, int L, uint8_t *dst_segmented_dev,
+                      void *stream);
+int kbbq_segment_pad(const uint32_t *seg_dev, int R, int L, uint8_t *seq_dev, uint8_t *qual_dev, uint8_t *corr_dev,
+                     void *stream);
+int kbbq_unsegment_rows(const uint8_t *src_segmented_dev, const uint32_t *dest_dev, int64_t N, int L,
+                        int64_t rows_bound, uint8_t *dst_dev, void *stream);
+/* kbbq_build / kbbq_apply on a segmented batch of at most rows_bound rows (workspace: kbbq_workspace_bytes(rows_bound, L, R)) */
+int kbbq_build_segmented(const uint8_t *seq_dev, const uint8_t *qual_dev, const uint8_t *corr_dev,
+                         const uint32_t *seg_dev, int64_t rows_bound, int L, int R, int minscore,
+                         int64_t *pos_errs_dev, int64_t *pos_total_dev, int64_t *din_errs_dev,
+                         int64_t *din_total_dev, void *workspace_dev, size_t workspace_bytes, int *status_dev,
+                         void *stream);
+int kbbq_apply_segmented(const uint8_t *seq_dev, const uint8_t *qual_dev, const uint32_t *seg_dev, int64_t rows_bound,
+                         int L, int R, int minscore, const int64_t *meanq_dev, const int64_t *rgdq_dev,
+                         const int64_t *qdq_dev, const int64_t *posdq_dev, const int64_t *dindq_dev, int nq,
+                         int ndin1, uint8_t *out_qual_dev, void *workspace_dev, size_t workspace_bytes,
+                         int *status_dev, void *stream);
 
 /*
  * Whole path on HOST buffers: H2D, build, marginals, deltas, apply, D2H -- what

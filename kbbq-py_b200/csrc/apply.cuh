@@ -29,6 +29,7 @@ struct ApplyArgs {
     TableCfg t;
     StageLayout sl;
     int R, nq;
+    int nsub, segmode;  // see BuildArgs
     const entry_t *entries;
     const unsigned int *seg;
     const unsigned int *uni;  // see BuildArgs
@@ -53,21 +54,15 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
     const uint32_t din_base = pin(smem_addr(smem_raw + t.din_off) + (lane & (t.drep - 1)) * 4);
-    uint32_t aeff[4];
+    uint32_t abase[4], aeff[4];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) aeff[b] = pos_base + m.cell[b];
+    for (int b = 0; b < 4; ++b) aeff[b] = abase[b] = pos_base + m.cell[b];
     uint32_t cur_flag = 1;
     const uint32_t selv = pin(m.selv), seln = pin(m.seln);
     const uint32_t rowsel = m.row >= 0 ? (uint32_t)m.row : 0u;
     const uint32_t lanemask = pin(m.row >= 0 ? 0xFFu : 0u);
     const uint32_t rowmask = pin(m.rowmask);
-    if (UNI) {
-        const uint32_t f = prmt(uni_flo, uni_fhi, rowsel) & lanemask;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) aeff[b] += (f >> 1) * t.revoff;
-        cur_flag = f;
-    }
-    const bool live = cur_flag != 0;
+    bool live = true;
     const uint32_t kgrp = g.ng * g.gbytes;
     // how this thread's word is written back: whole (0), one aligned half (1, the usual partial
     // word: reads of even length start 2-byte aligned) or byte by byte (2)
@@ -86,35 +81,48 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
     uint32_t stage = 0, phase = 0;
     uint32_t qgood = 0xFFFFFFFFu;
 
-    for (int rg = 0; rg < a.R; ++rg) {
-        uint32_t s_lo = a.seg[rg], s_hi = a.seg[rg + 1];
+    int cur_rg = -1;
+    for (int sub = 0; sub < a.nsub; ++sub) {
+        uint32_t s_lo = a.seg[sub], s_hi = a.seg[sub + 1];
         if (s_hi <= lo) continue;
         if (s_lo >= hi) break;
         if (s_lo < lo) s_lo = lo;
         if (s_hi > hi) s_hi = hi;
+        if (s_lo >= s_hi) continue;
+        const int rg = a.segmode ? sub >> 1 : sub;
 
         // stage this read group's folded tables; row 0 = "leave the quality alone": the dinuc table holds 0
         // there (invalid dinucs of any quality land on it), the cycle tables hold minscore - 1, the only
         // quality that reaches row 0 with its byte selected
-        consumer_sync(nconsumers);
-        for (int i = threadIdx.x; i < apply_table_bytes(t) / 4; i += nconsumers)
-            reinterpret_cast<int *>(smem_raw)[i] = i * 4 < t.din_off && (i * 4) % t.revoff < t.rs ? g.minscore - 1 : 0;
-        consumer_sync(nconsumers);
-        const int L = g.L, L2 = 2 * g.L;
-        const short *fc = a.fold_cyc + (size_t)rg * NQ * L2;
-        for (int i = threadIdx.x; i < (t.nrows - 1) * L2; i += nconsumers) {
-            const int r = i / L2 + 1, c2 = i - (r - 1) * L2;
-            const int half = c2 >= L, c = half ? L2 - 1 - c2 : c2;
-            int *p = reinterpret_cast<int *>(smem_raw + t.pos_off + half * t.revoff + r * t.rs) + ((c & 3) * t.sj + (c >> 2));
-            *p = fc[(size_t)(r + g.minscore - 1) * L2 + c2];
+        if (rg != cur_rg) {
+            cur_rg = rg;
+            consumer_sync(nconsumers);
+            for (int i = threadIdx.x; i < apply_table_bytes(t) / 4; i += nconsumers)
+                reinterpret_cast<int *>(smem_raw)[i] = i * 4 < t.din_off && (i * 4) % t.revoff < t.rs ? g.minscore - 1 : 0;
+            consumer_sync(nconsumers);
+            const int L = g.L, L2 = 2 * g.L;
+            const short *fc = a.fold_cyc + (size_t)rg * NQ * L2;
+            for (int i = threadIdx.x; i < (t.nrows - 1) * L2; i += nconsumers) {
+                const int r = i / L2 + 1, c2 = i - (r - 1) * L2;
+                const int half = c2 >= L, c = half ? L2 - 1 - c2 : c2;
+                int *p = reinterpret_cast<int *>(smem_raw + t.pos_off + half * t.revoff + r * t.rs) + ((c & 3) * t.sj + (c >> 2));
+                *p = fc[(size_t)(r + g.minscore - 1) * L2 + c2];
+            }
+            const short *fd = a.fold_din + (size_t)rg * NQ * DIN_SLOTS;
+            for (int i = threadIdx.x; i < (t.nrows - 1) * DIN_SLOTS * t.drep; i += nconsumers) {
+                const int cell = i / t.drep, r = cell / DIN_SLOTS + 1, s = cell & (DIN_SLOTS - 1);
+                int *p = reinterpret_cast<int *>(smem_raw + t.din_off + r * t.dq + s * (t.drep * 4)) + (i & (t.drep - 1));
+                *p = fd[(r + g.minscore - 1) * DIN_SLOTS + s];
+            }
+            consumer_sync(nconsumers);
         }
-        const short *fd = a.fold_din + (size_t)rg * NQ * DIN_SLOTS;
-        for (int i = threadIdx.x; i < (t.nrows - 1) * DIN_SLOTS * t.drep; i += nconsumers) {
-            const int cell = i / t.drep, r = cell / DIN_SLOTS + 1, s = cell & (DIN_SLOTS - 1);
-            int *p = reinterpret_cast<int *>(smem_raw + t.din_off + r * t.dq + s * (t.drep * 4)) + (i & (t.drep - 1));
-            *p = fd[(r + g.minscore - 1) * DIN_SLOTS + s];
+        if (UNI) {  // the row flag is fixed for the whole span
+            const uint32_t f = (a.segmode ? ((sub & 1) ? 3u : 1u) : prmt(uni_flo, uni_fhi, rowsel)) & lanemask;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) aeff[b] = abase[b] + (f >> 1) * t.revoff;
+            cur_flag = f;
+            live = f != 0;
         }
-        consumer_sync(nconsumers);
 
         for (uint32_t first = s_lo; first < s_hi; first += ngs) {
             mbar_wait(bar0 + stage * 8, phase);
@@ -210,8 +218,10 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
     const StageLayout &sl = a.sl;
     const int nconsumers = g.threads;
 
-    const unsigned long long E = a.seg[a.R];
+    const unsigned long long E = a.seg[a.nsub];
     const uint32_t lo = (uint32_t)(E * blockIdx.x / gridDim.x), hi = (uint32_t)(E * (blockIdx.x + 1) / gridDim.x);
+    const bool contig = a.R == 1 || a.segmode;
+    const bool uniform = contig && a.uni[0] == 0u;
 
     const uint32_t bar0 = smem_u32(smem_raw + sl.bar_off);
     if (threadIdx.x == 0) {
@@ -226,15 +236,14 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) apply_smem_kernel(const __grid
     if ((int)threadIdx.x >= nconsumers) {  // ---- producer warp ----
         ProducerArgs p;
         p.arr[0] = a.seq; p.arr[1] = a.qual; p.arr[2] = nullptr;
-        p.entries = a.entries; p.seg = a.seg; p.R = a.R; p.lo = lo; p.hi = hi;
+        p.entries = a.entries; p.seg = a.seg; p.nsub = a.nsub; p.contig = contig; p.lo = lo; p.hi = hi;
         p.gbytes = g.gbytes; p.ng = sl.ngs; p.total_bytes = a.total_bytes;
         p.pw = ((int)threadIdx.x - nconsumers) >> 5; p.nprod = g.nprod;
-        p.uniform = a.R == 1 && a.uni[0] == 0u;
+        p.uniform = uniform;
         producer_loop(p, sl, smem_raw);
         return;
     }
 
-    const bool uniform = a.R == 1 && a.uni[0] == 0u;
     if (uniform) apply_consume<KPS, true>(a, smem_raw, lo, hi, a.uni[1], a.uni[2]);
     else apply_consume<KPS, false>(a, smem_raw, lo, hi, 0u, 0u);
 }

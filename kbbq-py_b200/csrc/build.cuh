@@ -80,8 +80,8 @@ inline bool make_table_cfg(const Geom &g, int kps, int drep, TableCfg *t) {
     t->table_bytes = t->din_off + t->nrows * t->dq;
     // a cycle cell is hit at most once per (thread-group, row) and iteration; a dinuc replica cell
     // at most 4 times per thread of that lane id and iteration
-    t->flush_pos = (int)((ERR_UNIT - 1) / (uint32_t)(kps * g.ng * g.G));
-    t->fold_din = (int)((ERR_UNIT - 1) / (uint32_t)(kps * 4 * (g.threads / drep)));
+    t->flush_pos = std::max(1, (int)((ERR_UNIT - 1) / (uint32_t)(kps * g.ng * g.G)));
+    t->fold_din = std::max(1, (int)((ERR_UNIT - 1) / (uint32_t)(kps * 4 * ((g.threads + drep - 1) / drep))));
     t->addq = (uint32_t)(0x81 - g.minscore) * ONE4;
     t->cyc16[0] = (uint32_t)t->rs;
     t->cyc16[1] = (uint32_t)t->rs << 16;
@@ -97,8 +97,10 @@ struct BuildArgs {
     TableCfg t;
     StageLayout sl;
     int R;
+    int nsub;     // sub-segments of the walk: R list segments, or 2R (read group, read 1 / read 2) spans of a segmented batch
+    int segmode;  // 1: segmented batch (segment.cuh): rows sorted by 2 * rg + second, every span contiguous and uniform
     const entry_t *entries;
-    const unsigned int *seg;  // [R + 1]
+    const unsigned int *seg;  // [nsub + 1], in groups
     const unsigned int *uni;  // prepare.cuh: {0 = every group has the row flags of group 0, flags 0-3, flags 4-7}
     unsigned long long *pos_errs, *pos_total, *din_errs, *din_total;
     int *status;
@@ -245,21 +247,15 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
     const uint32_t din_base = pin(smem_addr(smem_raw + t.din_off) + (lane & (t.drep - 1)) * 4);
-    uint32_t aeff[4];  // shared address of row 0 of the read-1 (cur_flag 1) or read-2 (3) cycle table at this thread's cycles
+    uint32_t abase[4], aeff[4];  // shared address of row 0 of the read-1 (cur_flag 1) or read-2 (3) cycle table at this thread's cycles
 #pragma unroll
-    for (int b = 0; b < 4; ++b) aeff[b] = pos_base + m.cell[b];
+    for (int b = 0; b < 4; ++b) aeff[b] = abase[b] = pos_base + m.cell[b];
     uint32_t cur_flag = 1;
     const uint32_t selv = pin(m.selv), seln = pin(m.seln);
     const uint32_t rowsel = m.row >= 0 ? (uint32_t)m.row : 0u;  // prmt selector: flag byte of this thread's row
     const uint32_t lanemask = pin(m.row >= 0 ? 0xFFu : 0u);     // padding lanes never see a live row
     const uint32_t rowmask = pin(m.rowmask);
-    if (UNI) {  // the row flag never changes: re-base the cycle-table addresses once
-        const uint32_t f = prmt(uni_flo, uni_fhi, rowsel) & lanemask;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) aeff[b] += (f >> 1) * t.revoff;
-        cur_flag = f;
-    }
-    const bool live = cur_flag != 0;
+    bool live = true;
     // UNI: group j of a stage starts at (misalignment of the stage's first group) + j * gbytes
     const uint32_t data0 = pin(smem_u32(smem_raw + sl.data_off) + m.toff + (UNI ? m.grp * g.gbytes : 0));
     const uint32_t hdr0 = pin(smem_u32(smem_raw + sl.hdr_off) + m.grp * 16);
@@ -271,23 +267,55 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
     uint32_t stage = 0, phase = 0;
     uint32_t qgood = 0xFFFFFFFFu, bbad = 0;
 
-    for (int rg = 0; rg < a.R; ++rg) {
-        uint32_t s_lo = a.seg[rg], s_hi = a.seg[rg + 1];
+    for (int i = threadIdx.x; i < t.table_bytes / 4; i += nconsumers) reinterpret_cast<unsigned int *>(smem_raw)[i] = 0;
+    consumer_sync(nconsumers);
+    // Counters are packed u32 (total + ERR_UNIT * errors): the cycle table is flushed at the latest every flush_pos
+    // iterations (stages) and the dinuc replicas folded every fold_din, so that no total field can reach ERR_UNIT.
+    // Both flush and fold leave the tables zero (the trash row is never read), so they double as the reset between
+    // read groups.
+    int cur_rg = -1;
+    uint32_t since_pos = 0, since_din = 0;
+    auto flush_all = [&](int rg) {
+        consumer_sync(nconsumers);
+        flush_pos_table(a, smem_raw, rg, nconsumers);
+        fold_din_replicas(a, smem_raw, rg, nconsumers);
+        consumer_sync(nconsumers);
+        since_pos = since_din = 0;
+    };
+
+    for (int sub = 0; sub < a.nsub; ++sub) {
+        uint32_t s_lo = a.seg[sub], s_hi = a.seg[sub + 1];
         if (s_hi <= lo) continue;
         if (s_lo >= hi) break;
         if (s_lo < lo) s_lo = lo;
         if (s_hi > hi) s_hi = hi;
+        if (s_lo >= s_hi) continue;
+        // a segmented batch lists (read group, read 1) and (read group, read 2) spans in turn
+        const int rg = a.segmode ? sub >> 1 : sub;
+        if (rg != cur_rg) {
+            if (cur_rg >= 0) flush_all(cur_rg);
+            cur_rg = rg;
+        }
+        if (UNI) {  // the row flag is fixed for the whole span: re-base the cycle-table addresses once
+            const uint32_t f = (a.segmode ? ((sub & 1) ? 3u : 1u) : prmt(uni_flo, uni_fhi, rowsel)) & lanemask;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) aeff[b] = abase[b] + (f >> 1) * t.revoff;
+            cur_flag = f;
+            live = f != 0;
+        }
 
-        for (int i = threadIdx.x; i < t.table_bytes / 4; i += nconsumers) reinterpret_cast<unsigned int *>(smem_raw)[i] = 0;
-        consumer_sync(nconsumers);
-        int since_pos = 0;  // iterations since the cycle table was last flushed
-
-        // The hot loop runs in chunks of fold_din iterations; between chunks the counters whose
-        // total field could otherwise reach ERR_UNIT are folded.
         for (uint32_t first = s_lo; first < s_hi;) {
-            const uint32_t chunk_end = (uint32_t)min((unsigned long long)s_hi,
-                                                     (unsigned long long)first + (unsigned long long)t.fold_din * sl.ngs);
-            since_pos += t.fold_din;
+            if (since_pos >= (uint32_t)t.flush_pos || since_din >= (uint32_t)t.fold_din) {
+                consumer_sync(nconsumers);
+                if (since_pos >= (uint32_t)t.flush_pos) { flush_pos_table(a, smem_raw, rg, nconsumers); since_pos = 0; }
+                if (since_din >= (uint32_t)t.fold_din) { fold_din_replicas(a, smem_raw, rg, nconsumers); since_din = 0; }
+                consumer_sync(nconsumers);
+            }
+            const uint32_t room = min((uint32_t)t.flush_pos - since_pos, (uint32_t)t.fold_din - since_din);
+            const uint32_t chunk_end = (uint32_t)min((unsigned long long)s_hi, (unsigned long long)first + (unsigned long long)room * sl.ngs);
+            const uint32_t iters = (chunk_end - first + ngs - 1) / ngs;
+            since_pos += iters;
+            since_din += iters;
             for (; first < chunk_end; first += ngs) {
                 mbar_wait(bar0 + stage * 8, phase);
                 const uint32_t shdr = pin(hdr0 + stage * hdr_stride);
@@ -372,23 +400,9 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
                 if (lane == 0) mbar_arrive(bar0 + (nstages + stage) * 8);  // the stage may be refilled
                 if (++stage == nstages) { stage = 0; phase ^= 1; }
             }
-            if (first < s_hi) {
-                consumer_sync(nconsumers);
-                if (since_pos + t.fold_din > t.flush_pos) {
-                    flush_pos_table(a, smem_raw, rg, nconsumers);
-                    since_pos = 0;
-                }
-                fold_din_replicas(a, smem_raw, rg, nconsumers);
-                consumer_sync(nconsumers);
-            }
         }
-        consumer_sync(nconsumers);
-
-        // flush this read group's partial tables: u32 shared -> int64 global
-        flush_pos_table(a, smem_raw, rg, nconsumers);
-        fold_din_replicas(a, smem_raw, rg, nconsumers);
-        consumer_sync(nconsumers);
     }
+    if (cur_rg >= 0) flush_all(cur_rg);
     if (~qgood & rowmask & H4) atomicOr(a.status, KBBQ_FLAG_QUAL_RANGE);
     if (VALIDATE && (bbad & rowmask)) atomicOr(a.status, KBBQ_FLAG_BAD_BASE);
 }
@@ -402,8 +416,11 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
     const int nconsumers = g.threads;  // + one producer warp
 
     // this CTA's slice of the concatenated work list
-    const unsigned long long E = a.seg[a.R];
+    const unsigned long long E = a.seg[a.nsub];
     const uint32_t lo = (uint32_t)(E * blockIdx.x / gridDim.x), hi = (uint32_t)(E * (blockIdx.x + 1) / gridDim.x);
+    // one read group (or a segmented batch) whose groups all look alike: contiguous spans, no work list
+    const bool contig = a.R == 1 || a.segmode;
+    const bool uniform = contig && a.uni[0] == 0u;
 
     const uint32_t bar0 = smem_u32(smem_raw + sl.bar_off);
     if (threadIdx.x == 0) {
@@ -418,16 +435,15 @@ __global__ void __launch_bounds__(MAX_THREADS, 1) build_smem_kernel(const __grid
     if ((int)threadIdx.x >= nconsumers) {  // ---- producer warp ----
         ProducerArgs p;
         p.arr[0] = a.seq; p.arr[1] = a.qual; p.arr[2] = a.corr;
-        p.entries = a.entries; p.seg = a.seg; p.R = a.R; p.lo = lo; p.hi = hi;
+        p.entries = a.entries; p.seg = a.seg; p.nsub = a.nsub; p.contig = contig; p.lo = lo; p.hi = hi;
         p.gbytes = g.gbytes; p.ng = sl.ngs; p.total_bytes = a.total_bytes;
         p.pw = ((int)threadIdx.x - nconsumers) >> 5; p.nprod = g.nprod;
-        p.uniform = a.R == 1 && a.uni[0] == 0u;
+        p.uniform = uniform;
         producer_loop(p, sl, smem_raw);
         return;
     }
 
     // ---- consumer warps ----
-    const bool uniform = a.R == 1 && a.uni[0] == 0u;
     if (uniform) build_consume<KPS, VALIDATE, true>(a, smem_raw, lo, hi, a.uni[1], a.uni[2]);
     else build_consume<KPS, VALIDATE, false>(a, smem_raw, lo, hi, 0u, 0u);
 }

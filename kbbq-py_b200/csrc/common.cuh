@@ -55,7 +55,7 @@ extern char g_last_cuda_error[256];
 // CTA's consumer threads (a warp may hold lanes of two thread-groups -- everything a lane needs is a
 // per-thread constant), so only the last warp has padding lanes.  G (<= 8) is the smallest group
 // with the fewest straddling words (L = 150: G = 4, 152 lanes for 150 words; 6 thread-groups = 912
-// lanes in 29 warps).
+// lanes in 29 warps).  A segmented batch (segment.cuh) takes the same geometry with G a power of two.
 //
 // Shared-memory cycle tables are laid out [q - minscore][plane = c2 & 3][c2 >> 2] with a plane
 // stride SJ that makes the row stride a multiple of 32 words: lanes that own consecutive words of
@@ -71,7 +71,7 @@ struct Geom {
     int lps;          // lanes per thread-group (= lanes)
     int ng;           // thread-groups (groups in flight) per CTA
     int threads;      // consumer threads: ng * lps rounded up to whole warps
-    int nprod;        // producer warps behind the consumers (1 with one read group, 4 otherwise)
+    int nprod;        // producer warps behind the consumers (1 with one read group or a segmented batch, up to 8 otherwise)
     int sj;           // plane stride (words)
     int row;          // words per quality row = 4 * sj
     int minscore;     // first tallied quality
@@ -89,7 +89,7 @@ __host__ __device__ inline int gcd_int(int a, int b) {
 // the 32-groups-per-stage limit).  With several read groups the smallest group is taken: mates of a
 // pair normally share their read group, so a group of one pair is staged once, while a larger group
 // would be staged once per read group present in it.
-inline bool make_geom(int L, int minscore, bool single_rg, int nprod, Geom *g) {
+inline bool make_geom(int L, int minscore, bool single_rg, int nprod, Geom *g, bool pow2_groups = false) {
     if (L < 4 || minscore < 0 || minscore >= NQ) return false;
     const int rps = 4 / gcd_int(L, 4);
     // With several read groups every group of a stage is a copy of its own per array and one warp
@@ -99,6 +99,7 @@ inline bool make_geom(int L, int minscore, bool single_rg, int nprod, Geom *g) {
     const int budget = MAX_THREADS - 32 * nprod;
     int best_g = 0, best_lanes = 0;
     for (int G = rps; G <= MAX_G; G += rps) {
+        if (pow2_groups && (G & (G - 1))) continue;  // the spans of a segmented batch start at multiples of 16 rows
         int lanes = 0;
         for (int k = 0; k < G; ++k) lanes += ((k * L) % 4 + L + 3) / 4;
         if (lanes > budget) break;

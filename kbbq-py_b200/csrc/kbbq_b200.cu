@@ -14,6 +14,7 @@
 #include "common.cuh"
 #include "model.cuh"
 #include "prepare.cuh"
+#include "segment.cuh"
 #include "synth.cuh"
 
 namespace kbbq {
@@ -101,11 +102,13 @@ static bool plan_smem(const Geom &g, int narr, int max_smem, TableCfg *tc, Stage
 
 // Geometry + shared-memory plan; with several read groups the producer-warp count falls back from 8
 // when a ring of that many stages does not fit.
-static bool plan_kernel(int L, int R, int minscore, int narr, int max_smem, Geom *g, TableCfg *tc, StageLayout *sl) {
+static bool plan_kernel(int L, int R, int minscore, int narr, int max_smem, Geom *g, TableCfg *tc, StageLayout *sl,
+                        bool segmode = false) {
     int first = 8;
     if (const char *e = getenv("KBBQ_NPROD")) first = std::max(1, std::min(8, atoi(e)));  // tuning hook
-    for (int nprod = (R == 1 ? 1 : first); nprod >= 1; nprod >>= 1) {
-        if (!make_geom(L, minscore, R == 1, nprod, g)) return false;
+    const bool single = R == 1 || segmode;  // contiguous spans: the one-read-group geometry
+    for (int nprod = (single ? 1 : first); nprod >= 1; nprod >>= 1) {
+        if (!make_geom(L, minscore, single, nprod, g, segmode)) return false;
         if (g->row < 65536 && plan_smem(*g, narr, max_smem, tc, sl)) return true;
     }
     return false;
@@ -166,6 +169,7 @@ const char *kbbq_strerror(int code) {
     case KBBQ_E_NAME_FIELD: return "read name has no read-group field";
     case KBBQ_E_NAME_RG: return "read-group field does not start with RG";
     case KBBQ_E_NAME_MISMATCH: return "corrected read name does not start with the read name";
+    case KBBQ_E_PEER: return "multi-GPU: peer access between the devices is not available";
     default: return "unknown error";
     }
 }
@@ -194,14 +198,16 @@ int kbbq_workspace_bytes(int64_t N, int L, int R, size_t *bytes) {
     return KBBQ_OK;
 }
 
-int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,
-               const uint8_t *second, int64_t N, int L, int R, int minscore, int64_t *pos_errs,
-               int64_t *pos_total, int64_t *din_errs, int64_t *din_total, void *workspace,
-               size_t workspace_bytes, int *status, int path, void *stream) {
+// kbbq_build / kbbq_build_segmented.  seg_rows != NULL: a segmented batch of at most N rows (segment.cuh).
+static int build_impl(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,
+                      const uint8_t *second, int64_t N, int L, int R, int minscore, int64_t *pos_errs,
+                      int64_t *pos_total, int64_t *din_errs, int64_t *din_total, void *workspace,
+                      size_t workspace_bytes, int *status, int path, void *stream, const unsigned int *seg_rows) {
     if (N < 0 || L < 1 || R < 1 || R > 65535 || minscore < 0 || minscore >= NQ) return KBBQ_E_ARG;
     if (!pos_errs || !pos_total || !din_errs || !din_total || !status) return KBBQ_E_ARG;
     if (N == 0) return KBBQ_OK;
     if (!seq || !qual || !corr) return KBBQ_E_ARG;
+    const bool segmode = seg_rows != nullptr;
     cudaStream_t st = (cudaStream_t)stream;
     int device, sms, max_smem;
     int rc = current_device_info(&device, &sms, &max_smem);
@@ -211,10 +217,10 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
     TableCfg tc;
     StageLayout sl;
     const bool smem_ok = path != 2 && !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(corr, 16) &&
-                         plan_kernel(L, R, minscore, 3, max_smem, &g, &tc, &sl) &&
+                         plan_kernel(L, R, minscore, 3, max_smem, &g, &tc, &sl, segmode) &&
                          (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull;
     if (!smem_ok) {
-        if (path == 1) return KBBQ_E_ARG;
+        if (path == 1 || segmode) return KBBQ_E_ARG;
         BuildGenericArgs a = {seq, qual, corr, rg, second, N, L, R, minscore,
                               (unsigned long long *)pos_errs, (unsigned long long *)pos_total,
                               (unsigned long long *)din_errs, (unsigned long long *)din_total, status};
@@ -224,30 +230,53 @@ int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, con
     }
     Workspace w = carve_workspace(workspace, N, L, R);
     if (!workspace || workspace_bytes < w.bytes) return KBBQ_E_WORKSPACE;
-    // One read group: a partial last group would be the only one with untallied rows and cost the
-    // whole batch its header-free fast path; its few reads go through the generic kernel instead.
-    const int64_t tail = (R == 1 && N > g.G) ? N % g.G : 0;
-    if (tail) {
-        const int64_t n0 = N - tail;
-        BuildGenericArgs ga = {seq + n0 * L, qual + n0 * L, corr + n0 * L, rg ? rg + n0 : nullptr,
-                               second ? second + n0 : nullptr, tail, L, R, minscore,
-                               (unsigned long long *)pos_errs, (unsigned long long *)pos_total,
-                               (unsigned long long *)din_errs, (unsigned long long *)din_total, status};
-        build_generic_kernel<<<1, 256, 0, st>>>(ga);
+    if (segmode) {
+        seg_prepare_kernel<<<1, 256, 0, st>>>(seg_rows, 2 * R, g.G, (unsigned long long)N, w.seg, w.uni, status);
         KBBQ_LAUNCHED();
-        N = n0;
+    } else {
+        // One read group: a partial last group would be the only one with untallied rows and cost the
+        // whole batch its header-free fast path; its few reads go through the generic kernel instead.
+        const int64_t tail = (R == 1 && N > g.G) ? N % g.G : 0;
+        if (tail) {
+            const int64_t n0 = N - tail;
+            BuildGenericArgs ga = {seq + n0 * L, qual + n0 * L, corr + n0 * L, rg ? rg + n0 : nullptr,
+                                   second ? second + n0 : nullptr, tail, L, R, minscore,
+                                   (unsigned long long *)pos_errs, (unsigned long long *)pos_total,
+                                   (unsigned long long *)din_errs, (unsigned long long *)din_total, status};
+            build_generic_kernel<<<1, 256, 0, st>>>(ga);
+            KBBQ_LAUNCHED();
+            N = n0;
+        }
+        rc = run_prepare(rg, second, N, g.G, R, w, status, sms, sl.ngs, g.gbytes, sl.slot, st);
+        if (rc) return rc;
     }
-    rc = run_prepare(rg, second, N, g.G, R, w, status, sms, sl.ngs, g.gbytes, sl.slot, st);
-    if (rc) return rc;
 
     BuildArgs a;
     a.seq = seq; a.qual = qual; a.corr = corr; a.total_bytes = N * L; a.g = g; a.t = tc; a.R = R;
+    a.nsub = segmode ? 2 * R : R; a.segmode = segmode ? 1 : 0;
     a.sl = sl;
     a.entries = w.entries; a.seg = w.seg; a.uni = w.uni;
     a.pos_errs = (unsigned long long *)pos_errs; a.pos_total = (unsigned long long *)pos_total;
     a.din_errs = (unsigned long long *)din_errs; a.din_total = (unsigned long long *)din_total;
     a.status = status;
     return launch_build_smem(a, sms, a.sl.total, st);
+}
+
+int kbbq_build(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,
+               const uint8_t *second, int64_t N, int L, int R, int minscore, int64_t *pos_errs,
+               int64_t *pos_total, int64_t *din_errs, int64_t *din_total, void *workspace,
+               size_t workspace_bytes, int *status, int path, void *stream) {
+    return build_impl(seq, qual, corr, rg, second, N, L, R, minscore, pos_errs, pos_total, din_errs, din_total,
+                      workspace, workspace_bytes, status, path, stream, nullptr);
+}
+
+int kbbq_build_segmented(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint32_t *seg,
+                         int64_t rows_bound, int L, int R, int minscore, int64_t *pos_errs, int64_t *pos_total,
+                         int64_t *din_errs, int64_t *din_total, void *workspace, size_t workspace_bytes, int *status,
+                         void *stream) {
+    if (!seg || rows_bound % SEG_ALIGN) return KBBQ_E_ARG;
+    return build_impl(seq, qual, corr, nullptr, nullptr, rows_bound, L, R, minscore, pos_errs, pos_total, din_errs,
+                      din_total, workspace, workspace_bytes, status, 1, stream, seg);
 }
 
 int kbbq_marginals(const int64_t *pos_errs, const int64_t *pos_total, int L, int R, int64_t *q_errs,
@@ -474,10 +503,12 @@ int kbbq_get_delta_qs(const int64_t *meanq, const int64_t *rg_errs, const int64_
     return KBBQ_OK;
 }
 
-int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, const uint8_t *second, int64_t N,
-               int L, int R, int minscore, const int64_t *meanq, const int64_t *rgdq, const int64_t *qdq,
-               const int64_t *posdq, const int64_t *dindq, int nq, int ndin1, uint8_t *out_qual,
-               void *workspace, size_t workspace_bytes, int *status, int path, void *stream) {
+static int apply_impl(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, const uint8_t *second, int64_t N,
+                      int L, int R, int minscore, const int64_t *meanq, const int64_t *rgdq, const int64_t *qdq,
+                      const int64_t *posdq, const int64_t *dindq, int nq, int ndin1, uint8_t *out_qual,
+                      void *workspace, size_t workspace_bytes, int *status, int path, void *stream,
+                      const unsigned int *seg_rows) {
+    const bool segmode = seg_rows != nullptr;
     if (N < 0 || L < 1 || R < 1 || R > 65535 || minscore < 0 || minscore >= NQ) return KBBQ_E_ARG;
     if (nq < 1 || nq > NQ || ndin1 < 16 || ndin1 > 64) return KBBQ_E_ARG;
     if (!meanq || !rgdq || !qdq || !posdq || !dindq || !status) return KBBQ_E_ARG;
@@ -500,16 +531,16 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
     TableCfg tc;
     StageLayout sl;
     const bool smem_ok = path != 2 && !misaligned(seq, 16) && !misaligned(qual, 16) && !misaligned(out_qual, 4) &&
-                         plan_kernel(L, R, minscore, 2, max_smem, &g, &tc, &sl) &&
+                         plan_kernel(L, R, minscore, 2, max_smem, &g, &tc, &sl, segmode) &&
                          (uint64_t)((N + g.G - 1) / g.G) < 0xFFFFFFFFull;
     if (!smem_ok) {
-        if (path == 1) return KBBQ_E_ARG;
+        if (path == 1 || segmode) return KBBQ_E_ARG;
         ApplyGenericArgs a = {seq, qual, rg, second, out_qual, N, L, R, minscore, nq, w.fold_cyc, w.fold_din, status};
         apply_generic_kernel<<<sms * 8, 256, 0, st>>>(a);
         KBBQ_LAUNCHED();
         return KBBQ_OK;
     }
-    const int64_t tail = (R == 1 && N > g.G) ? N % g.G : 0;  // see kbbq_build
+    const int64_t tail = (!segmode && R == 1 && N > g.G) ? N % g.G : 0;  // see kbbq_build
     if (tail) {
         const int64_t n0 = N - tail;
         ApplyGenericArgs ga = {seq + n0 * L, qual + n0 * L, rg ? rg + n0 : nullptr, second ? second + n0 : nullptr,
@@ -518,13 +549,110 @@ int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, cons
         KBBQ_LAUNCHED();
         N = n0;
     }
-    rc = run_prepare(rg, second, N, g.G, R, w, status, sms, sl.ngs, g.gbytes, sl.slot, st);
-    if (rc) return rc;
+    if (segmode) {
+        seg_prepare_kernel<<<1, 256, 0, st>>>(seg_rows, 2 * R, g.G, (unsigned long long)N, w.seg, w.uni, status);
+        KBBQ_LAUNCHED();
+    } else {
+        rc = run_prepare(rg, second, N, g.G, R, w, status, sms, sl.ngs, g.gbytes, sl.slot, st);
+        if (rc) return rc;
+    }
     ApplyArgs a;
+    a.nsub = segmode ? 2 * R : R; a.segmode = segmode ? 1 : 0;
     a.seq = seq; a.qual = qual; a.out = out_qual; a.total_bytes = N * L; a.g = g; a.t = tc; a.R = R; a.nq = nq;
     a.sl = sl;
     a.entries = w.entries; a.seg = w.seg; a.uni = w.uni; a.fold_cyc = w.fold_cyc; a.fold_din = w.fold_din; a.status = status;
     return launch_apply_smem(a, sms, a.sl.total, st);
+}
+
+int kbbq_apply(const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, const uint8_t *second, int64_t N,
+               int L, int R, int minscore, const int64_t *meanq, const int64_t *rgdq, const int64_t *qdq,
+               const int64_t *posdq, const int64_t *dindq, int nq, int ndin1, uint8_t *out_qual,
+               void *workspace, size_t workspace_bytes, int *status, int path, void *stream) {
+    return apply_impl(seq, qual, rg, second, N, L, R, minscore, meanq, rgdq, qdq, posdq, dindq, nq, ndin1, out_qual,
+                      workspace, workspace_bytes, status, path, stream, nullptr);
+}
+
+int kbbq_apply_segmented(const uint8_t *seq, const uint8_t *qual, const uint32_t *seg, int64_t rows_bound, int L, int R,
+                         int minscore, const int64_t *meanq, const int64_t *rgdq, const int64_t *qdq,
+                         const int64_t *posdq, const int64_t *dindq, int nq, int ndin1, uint8_t *out_qual,
+                         void *workspace, size_t workspace_bytes, int *status, void *stream) {
+    if (!seg || rows_bound % SEG_ALIGN) return KBBQ_E_ARG;
+    return apply_impl(seq, qual, nullptr, nullptr, rows_bound, L, R, minscore, meanq, rgdq, qdq, posdq, dindq, nq, ndin1,
+                      out_qual, workspace, workspace_bytes, status, 1, stream, seg);
+}
+
+// ---- segmented batch layout (segment.cuh) ----
+
+int64_t kbbq_segment_rows_bound(int64_t N, int R) {
+    if (N < 0 || R < 1) return -1;
+    return (N + SEG_ALIGN - 1) / SEG_ALIGN * SEG_ALIGN + (int64_t)2 * R * SEG_ALIGN;
+}
+
+int64_t kbbq_segment_table_elems(int R) { return R < 1 ? -1 : (int64_t)6 * R + 1; }
+
+int kbbq_segmented_supported(int L, int R, int minscore) {
+    if (L < 1 || R < 1 || R > 65535) return 0;
+    Geom g;
+    TableCfg tc;
+    StageLayout sl;
+    return plan_kernel(L, R, minscore, 3, 232448, &g, &tc, &sl, true) && plan_kernel(L, R, minscore, 2, 232448, &g, &tc, &sl, true);
+}
+
+int kbbq_segment_plan(const uint16_t *rg, const uint8_t *second, int64_t N, int R, uint32_t *seg, uint32_t *dest,
+                      int *status, void *stream) {
+    if (N < 0 || R < 1 || R > 65535 || !seg || !status || (N > 0 && !dest)) return KBBQ_E_ARG;
+    if (kbbq_segment_rows_bound(N, R) >= 0xFFFFFFFFll) return KBBQ_E_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int nkeys = 2 * R;
+    SegPlanArgs a = {rg, second, N, R, seg, seg + 2 * nkeys + 1, dest, status};
+    KBBQ_CUDA(cudaMemsetAsync(a.cursor, 0, sizeof(unsigned int) * nkeys, st));
+    const int per_thread = 8;
+    const long long per_block = (long long)SEG_THREADS * per_thread;
+    const unsigned int blocks = (unsigned int)((N + per_block - 1) / per_block);
+    const size_t smem = nkeys <= SEG_SMEM_KEYS ? sizeof(unsigned int) * nkeys : 0;
+    if (blocks) {
+        seg_bucket_kernel<0><<<blocks, SEG_THREADS, smem, st>>>(a, per_thread);
+        KBBQ_LAUNCHED();
+    }
+    seg_scan_kernel<<<1, 1024, 0, st>>>(a);
+    KBBQ_LAUNCHED();
+    if (blocks) {
+        seg_bucket_kernel<1><<<blocks, SEG_THREADS, smem, st>>>(a, per_thread);
+        KBBQ_LAUNCHED();
+    }
+    return KBBQ_OK;
+}
+
+static int move_rows(const uint8_t *src, const uint32_t *dest, int64_t N, int L, uint8_t *dst, int64_t src_rows, bool scatter,
+                     cudaStream_t st) {
+    if (N < 0 || L < 1 || src_rows < 0) return KBBQ_E_ARG;
+    if (N == 0) return KBBQ_OK;
+    if (!src || !dest || !dst) return KBBQ_E_ARG;
+    int device, sms, max_smem;
+    int rc = current_device_info(&device, &sms, &max_smem);
+    if (rc) return rc;
+    const long long warps_per_block = SEG_THREADS / 32;
+    const unsigned int blocks = (unsigned int)std::min<long long>((N + warps_per_block - 1) / warps_per_block, (long long)sms * 32);
+    if (scatter) seg_move_rows_kernel<true><<<blocks, SEG_THREADS, 0, st>>>(src, dst, dest, N, L, src_rows);
+    else seg_move_rows_kernel<false><<<blocks, SEG_THREADS, 0, st>>>(src, dst, dest, N, L, src_rows);
+    KBBQ_LAUNCHED();
+    return KBBQ_OK;
+}
+
+int kbbq_segment_rows(const uint8_t *src, const uint32_t *dest, int64_t N, int L, uint8_t *dst_segmented, void *stream) {
+    return move_rows(src, dest, N, L, dst_segmented, N, true, (cudaStream_t)stream);
+}
+
+int kbbq_unsegment_rows(const uint8_t *src_segmented, const uint32_t *dest, int64_t N, int L, int64_t rows_bound,
+                        uint8_t *dst, void *stream) {
+    return move_rows(src_segmented, dest, N, L, dst, rows_bound, false, (cudaStream_t)stream);
+}
+
+int kbbq_segment_pad(const uint32_t *seg, int R, int L, uint8_t *seq, uint8_t *qual, uint8_t *corr, void *stream) {
+    if (!seg || R < 1 || R > 65535 || L < 1) return KBBQ_E_ARG;
+    seg_pad_kernel<<<2 * R, 128, 0, (cudaStream_t)stream>>>(seg, 2 * R, L, seq, qual, corr);
+    KBBQ_LAUNCHED();
+    return KBBQ_OK;
 }
 
 int kbbq_synth_reads(uint64_t seed, int64_t first_read, int64_t n, int L, int R, uint8_t *seq, uint8_t *qual,

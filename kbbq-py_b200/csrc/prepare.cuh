@@ -245,7 +245,7 @@ inline Workspace carve_workspace(void *base, long long N, int L, int R) {
     // a group never lists more entries than it has rows, so N (+ padding) entries always suffice;
     // with one read group the list is one entry per group of at least 1 read
     const size_t max_entries = (size_t)N + MAX_G;
-    w.seg = (unsigned int *)(p + off);      off = align_up(off + sizeof(unsigned int) * ((size_t)R + 1), 256);
+    w.seg = (unsigned int *)(p + off);      off = align_up(off + sizeof(unsigned int) * (2 * (size_t)R + 2), 256);  // [R + 1], or [2R + 1] spans of a segmented batch
     w.cursor = (unsigned int *)(p + off);   off = align_up(off + sizeof(unsigned int) * (size_t)R, 256);
     w.uni = (unsigned int *)(p + off);      off = align_up(off + sizeof(unsigned int) * 4, 256);
     w.entries = (entry_t *)(p + off);       off = align_up(off + sizeof(entry_t) * max_entries, 256);

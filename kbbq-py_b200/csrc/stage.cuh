@@ -92,7 +92,8 @@ struct ProducerArgs {
     const uint8_t *arr[3];
     const entry_t *entries;
     const unsigned int *seg;
-    int R;
+    int nsub;             // sub-segments (BuildArgs::nsub)
+    bool contig;          // one read group or a segmented batch: every stage is one contiguous span of groups
     uint32_t lo, hi;      // this CTA's slice of the work list
     uint32_t gbytes;
     int ng;                 // groups per stage (StageLayout::ngs)
@@ -114,31 +115,38 @@ __device__ __forceinline__ void producer_loop(const ProducerArgs &p, const Stage
     uint32_t stage = 0, phase = 0;
     const unsigned long long end16 = ((unsigned long long)p.total_bytes + 15ull) & ~15ull;
 
-    if (p.R == 1) {  // identity list: one contiguous span per stage, one producer warp
+    if (p.contig) {  // identity list: one contiguous span per stage, one producer warp
         if (lane != 0 || p.pw != 0) return;
-        for (uint32_t first = p.lo; first < p.hi; first += p.ng) {
-            const uint32_t n = min((uint32_t)p.ng, p.hi - first);
-            const uint32_t full = bar0 + stage * 8, empty = bar0 + (sl.stages + stage) * 8;
-            const unsigned long long start = (unsigned long long)first * p.gbytes;
-            const uint32_t mis = (uint32_t)start & 15u;
-            const unsigned long long src = start - mis;
-            uint32_t bytes = (mis + n * p.gbytes + 15u) & ~15u;
-            // the last group of a batch may be partial: stop at the end of the arrays
-            bytes = src >= end16 ? 0u : (uint32_t)min((unsigned long long)bytes, end16 - src);
-            mbar_wait(empty, phase ^ 1);
-            // a short last stage: the slots past the list must read as "no rows"
-            if (!p.uniform)
-                for (uint32_t j = n; j < (uint32_t)p.ng; ++j)
-                    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(hdr0 + (stage * p.ng + j) * 16u), "r"(0u) : "memory");
-            mbar_arrive_expect_tx(full, bytes * sl.narr + (p.uniform ? 0u : n * 16u));
-            const uint32_t dst = data0 + stage * sl.narr * sl.abytes;
-            if (bytes) {
+        for (int sub = 0; sub < p.nsub; ++sub) {
+            uint32_t s_lo = p.seg[sub], s_hi = p.seg[sub + 1];
+            if (s_hi <= p.lo) continue;
+            if (s_lo >= p.hi) break;
+            if (s_lo < p.lo) s_lo = p.lo;
+            if (s_hi > p.hi) s_hi = p.hi;
+            for (uint32_t first = s_lo; first < s_hi; first += p.ng) {
+                const uint32_t n = min((uint32_t)p.ng, s_hi - first);
+                const uint32_t full = bar0 + stage * 8, empty = bar0 + (sl.stages + stage) * 8;
+                const unsigned long long start = (unsigned long long)first * p.gbytes;
+                const uint32_t mis = (uint32_t)start & 15u;
+                const unsigned long long src = start - mis;
+                uint32_t bytes = (mis + n * p.gbytes + 15u) & ~15u;
+                // the last group of a batch may be partial: stop at the end of the arrays
+                bytes = src >= end16 ? 0u : (uint32_t)min((unsigned long long)bytes, end16 - src);
+                mbar_wait(empty, phase ^ 1);
+                // a short last stage: the slots past the list must read as "no rows"
+                if (!p.uniform)
+                    for (uint32_t j = n; j < (uint32_t)p.ng; ++j)
+                        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(hdr0 + (stage * p.ng + j) * 16u), "r"(0u) : "memory");
+                mbar_arrive_expect_tx(full, bytes * sl.narr + (p.uniform ? 0u : n * 16u));
+                const uint32_t dst = data0 + stage * sl.narr * sl.abytes;
+                if (bytes) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k)
-                    if (k < sl.narr) bulk_g2s(dst + k * sl.abytes, p.arr[k] + src, bytes, full);
+                    for (int k = 0; k < 3; ++k)
+                        if (k < sl.narr) bulk_g2s(dst + k * sl.abytes, p.arr[k] + src, bytes, full);
+                }
+                if (!p.uniform) bulk_g2s(hdr0 + stage * p.ng * 16u, p.entries + first, n * 16u, full);
+                if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
             }
-            if (!p.uniform) bulk_g2s(hdr0 + stage * p.ng * 16u, p.entries + first, n * 16u, full);
-            if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
         }
         return;
     }
@@ -147,7 +155,7 @@ __device__ __forceinline__ void producer_loop(const ProducerArgs &p, const Stage
     // the iterations round-robin (one warp issues a bulk copy every ~90 cycles).  The group indices of
     // a warp's next iteration are fetched while the current one is issued.
     uint32_t it = 0;  // iteration counter over all segments: stage = it % stages
-    for (int rg = 0; rg < p.R; ++rg) {
+    for (int rg = 0; rg < p.nsub; ++rg) {
         uint32_t s_lo = p.seg[rg], s_hi = p.seg[rg + 1];
         if (s_hi <= p.lo) continue;
         if (s_lo >= p.hi) break;

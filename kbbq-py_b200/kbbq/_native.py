@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libkbbq_b200.so")
 
 NQ = 43
-FLAG_QUAL_RANGE, FLAG_BAD_BASE, FLAG_RG_RANGE = 1, 2, 4
+FLAG_QUAL_RANGE, FLAG_BAD_BASE, FLAG_RG_RANGE, FLAG_SEGMENTS = 1, 2, 4, 8
 E_DATA = -4
 
 _lib = None
@@ -64,6 +64,15 @@ SIGNATURES = {
     "kbbq_host_mismatch_bits": (_i, [_vp, _vp, _i64, _vp, _i]),
     "kbbq_expand_mismatch_bits": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "kbbq_plan_info": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i)]),
+    "kbbq_segment_rows_bound": (_i64, [_i64, _i]),
+    "kbbq_segment_table_elems": (_i64, [_i]),
+    "kbbq_segmented_supported": (_i, [_i, _i, _i]),
+    "kbbq_segment_plan": (_i, [_vp, _vp, _i64, _i, _vp, _vp, _vp, _vp]),
+    "kbbq_segment_rows": (_i, [_vp, _vp, _i64, _i, _vp, _vp]),
+    "kbbq_segment_pad": (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    "kbbq_unsegment_rows": (_i, [_vp, _vp, _i64, _i, _i64, _vp, _vp]),
+    "kbbq_build_segmented": (_i, [_vp] * 4 + [_i64, _i, _i, _i] + [_vp] * 4 + [_vp, _sz, _vp, _vp]),
+    "kbbq_apply_segmented": (_i, [_vp] * 3 + [_i64, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, _vp, _sz, _vp, _vp]),
 }
 
 
@@ -110,6 +119,8 @@ def raise_for_status(status):
         raise TypeError("sequence contains a base outside A, C, G, T, N")
     if status & FLAG_RG_RANGE:
         raise IndexError("read group index out of range")
+    if status & FLAG_SEGMENTS:
+        raise ValueError("malformed span table of a segmented batch")
 
 
 def ptr(a):

@@ -23,6 +23,28 @@ def _p(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _on_device(fn):
+    """Run a method with self.device current: the C ABI launches on, and uploads its constants to, the
+    CURRENT device, while the stream and the pointers handed over belong to self.device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with torch.cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
+class SegmentedBatch:
+    """A batch in the segmented HBM layout (include/kbbq_b200.h, "Segmented batch layout"): rows sorted by
+    2 * rg + second, spans padded to 16 rows.  seq / qual / corr: u8 [rows_bound, L]; seg: the span table;
+    dest: int32 [N], row of read i."""
+
+    def __init__(self, seq, qual, corr, seg, dest, n_reads, rows_bound):
+        self.seq, self.qual, self.corr, self.seg, self.dest = seq, qual, corr, seg, dest
+        self.N, self.rows_bound = n_reads, rows_bound
+
+
 class DeviceRecalibrator:
     """Owns the tables, model buffers and workspace for batches of up to `max_reads` reads."""
 
@@ -55,6 +77,7 @@ class DeviceRecalibrator:
         self.ws_reads = -1
         self._ensure_workspace(max_reads)
 
+    @_on_device
     def _ensure_workspace(self, n_reads):
         if n_reads <= self.ws_reads:
             return
@@ -71,6 +94,7 @@ class DeviceRecalibrator:
         self.tables.zero_()
         self.status.zero_()
 
+    @_on_device
     def build(self, seq, qual, corr, rg=None, second=None, path=0):
         """Accumulate one batch into the tables (kbbq_build). Tensors: u8 [N, L] (rg int16/uint16 [N])."""
         N = seq.numel() // self.L
@@ -80,16 +104,68 @@ class DeviceRecalibrator:
                                  _p(self.workspace), self.ws_bytes, _p(self.status), path, self._stream())
         _native.check(rc)
 
+    @_on_device
     def build_from_bits(self, seq, qual, bits, corr_scratch, rg=None, second=None):
         """build() when the corrected reads arrive as the 1-bit-per-base mismatch map of
         kbbq_host_mismatch_bits (int32 tensor): it is expanded into `corr_scratch` (u8, like seq) first."""
         _native.check(self.lib.kbbq_expand_mismatch_bits(_p(seq), _p(bits), seq.numel(), _p(corr_scratch), self._stream()))
         self.build(seq, qual, corr_scratch, rg, second)
 
+    @_on_device
+    def segment(self, seq, qual, corr=None, rg=None, second=None):
+        """Rewrite a batch into the segmented layout on the device (kbbq_segment_plan / _rows / _pad).
+        Several read groups then run at the one-read-group speed of the kernels (build_segmented /
+        apply_segmented); unsegment() brings recalibrated qualities back into read order."""
+        N, L, R = seq.numel() // self.L, self.L, self.R
+        if not self.lib.kbbq_segmented_supported(L, R, self.minscore):
+            raise _native.KbbqNativeError("no shared-memory plan for L=%d, R=%d: use build() / apply()" % (L, R))
+        rows = int(self.lib.kbbq_segment_rows_bound(N, R))
+        dev, st = self.device, self._stream()
+        seg = torch.empty(int(self.lib.kbbq_segment_table_elems(R)), dtype=torch.int32, device=dev)
+        dest = torch.empty(max(N, 1), dtype=torch.int32, device=dev)
+        _native.check(self.lib.kbbq_segment_plan(_p(rg), _p(second), N, R, _p(seg), _p(dest), _p(self.status), st))
+        outs = []
+        for src in (seq, qual, corr):
+            if src is None:
+                outs.append(None)
+                continue
+            dst = torch.empty(rows * L + 16, dtype=torch.uint8, device=dev)
+            _native.check(self.lib.kbbq_segment_rows(_p(src), _p(dest), N, L, _p(dst), st))
+            outs.append(dst)
+        _native.check(self.lib.kbbq_segment_pad(_p(seg), R, L, _p(outs[0]), _p(outs[1]), _p(outs[2]), st))
+        return SegmentedBatch(outs[0], outs[1], outs[2], seg, dest, N, rows)
+
+    @_on_device
+    def build_segmented(self, sb):
+        """kbbq_build on a segmented batch (kbbq_build_segmented)."""
+        self._ensure_workspace(sb.rows_bound)
+        rc = self.lib.kbbq_build_segmented(_p(sb.seq), _p(sb.qual), _p(sb.corr), _p(sb.seg), sb.rows_bound, self.L, self.R,
+                                           self.minscore, _p(self.pos_errs), _p(self.pos_total), _p(self.din_errs),
+                                           _p(self.din_total), _p(self.workspace), self.ws_bytes, _p(self.status),
+                                           self._stream())
+        _native.check(rc)
+
+    @_on_device
+    def apply_segmented(self, sb, out_seg):
+        """kbbq_apply on a segmented batch; out_seg: u8 [rows_bound, L] in the segmented order."""
+        self._ensure_workspace(sb.rows_bound)
+        rc = self.lib.kbbq_apply_segmented(_p(sb.seq), _p(sb.qual), _p(sb.seg), sb.rows_bound, self.L, self.R, self.minscore,
+                                           _p(self.meanq), _p(self.rgdq), _p(self.qdq), _p(self.posdq), _p(self.dindq),
+                                           NQ, 17, _p(out_seg), _p(self.workspace), self.ws_bytes, _p(self.status),
+                                           self._stream())
+        _native.check(rc)
+
+    @_on_device
+    def unsegment(self, sb, out_seg, out):
+        """out row i = out_seg row dest[i] (kbbq_unsegment_rows)."""
+        _native.check(self.lib.kbbq_unsegment_rows(_p(out_seg), _p(sb.dest), sb.N, self.L, sb.rows_bound, _p(out),
+                                                   self._stream()))
+
     def allreduce(self):
         """Sum the partial tables over all ranks: the one collective of the path."""
         parallel.allreduce_tables(self.tables, self.pg)
 
+    @_on_device
     def model(self):
         """marginals + meanq + hierarchical delta tables (kbbq_marginals, kbbq_get_delta_qs)."""
         L, R = self.L, self.R
@@ -102,6 +178,7 @@ class DeviceRecalibrator:
                                                  R, NQ, 2 * L, 16, _p(self.rgdq), _p(self.qdq), _p(self.posdq),
                                                  _p(self.dindq), self._stream()))
 
+    @_on_device
     def apply(self, seq, qual, out, rg=None, second=None, path=0):
         """Write recalibrated qualities of one batch into `out` (kbbq_apply)."""
         N = seq.numel() // self.L
@@ -112,6 +189,7 @@ class DeviceRecalibrator:
                                  self._stream())
         _native.check(rc)
 
+    @_on_device
     def build_bam(self, seq, qual, err, skip=None, rg=None, flags=None, aln_start=None, aln_end=None, fast=True):
         """Accumulate a batch of aligned reads (kbbq_build_bam): err / skip u8 [N, L] from the host's CIGAR
         walk, flags u8 [N] (bit 0 read 2, bit 1 reverse strand), aln_start / aln_end int16 [N]."""
@@ -123,6 +201,7 @@ class DeviceRecalibrator:
                                      0 if ws is None else ws.numel(), _p(self.status), self._stream())
         _native.check(rc)
 
+    @_on_device
     def _bam_workspace(self, n_reads):
         """Canonical copies of a BAM batch + the build / apply workspace (kbbq_bam_workspace_bytes)."""
         if n_reads > getattr(self, "bam_ws_reads", -1):
@@ -132,6 +211,7 @@ class DeviceRecalibrator:
             self.bam_ws_reads = n_reads
         return self.bam_ws
 
+    @_on_device
     def apply_bam(self, seq, qual, out, rg=None, flags=None, fast=True):
         """Recalibrated qualities of a batch of aligned reads (kbbq_apply_bam)."""
         N = seq.numel() // self.L
@@ -142,6 +222,7 @@ class DeviceRecalibrator:
                                      self._stream())
         _native.check(rc)
 
+    @_on_device
     def check_status(self):
         """Synchronise and raise the reference's exception for any data error seen on the device."""
         st = int(self.status.item())
@@ -166,6 +247,7 @@ def calibration_counts(qual, err=None, seq=None, corr=None, skip=None, total=Non
     (allocated when None) and returns them, so batches -- and, after an all-reduce, ranks -- add up."""
     lib = _native.lib()
     dev = qual.device
+    torch.cuda.set_device(dev)
     if total is None:
         total = torch.zeros(256, dtype=torch.int64, device=dev)
     if errs is None:
@@ -180,6 +262,7 @@ def synth_reads(seed, first_read, n, L, R, device=None, want_corr=True):
     """Counter-based synthetic reads generated on the GPU (kbbq_synth_reads): bench / test input."""
     lib = _native.lib()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    torch.cuda.set_device(dev)
     seq = torch.empty(n, L, dtype=torch.uint8, device=dev)
     qual = torch.empty(n, L, dtype=torch.uint8, device=dev)
     corr = torch.empty(n, L, dtype=torch.uint8, device=dev)

@@ -59,11 +59,49 @@ def _run_device(torch, seq, qual, corr, rg, second, L, R, path, splits=1):
     return tables, deltas, np.concatenate(outs).reshape(N, L)
 
 
-@pytest.mark.parametrize("path", [1, 2])
+SEGMENTED = 3  # "path" of the helpers below: the segmented HBM layout (kbbq_segment_* + kbbq_*_segmented)
+
+
+def _run_segmented(torch, seq, qual, corr, rg, second, L, R, splits=1):
+    """Same contract as _run_device, through the segmented batch layout: every split is segmented on the device,
+    built and applied with the *_segmented entry points, and its qualities brought back into read order."""
+    from kbbq.device import DeviceRecalibrator
+    N = seq.shape[0]
+    rec = DeviceRecalibrator(L, R, max_reads=N)
+    bounds = [N * i // splits // 16 * 16 for i in range(splits)] + [N]
+    parts = []
+    for lo, hi in zip(bounds, bounds[1:]):
+        s, q, c, g, sec = _dev(torch, seq[lo:hi], qual[lo:hi], corr[lo:hi], rg[lo:hi] if rg is not None else None,
+                               second[lo:hi] if second is not None else None)
+        sb = rec.segment(s, q, c, g, sec)
+        parts.append((sb, q))
+        rec.build_segmented(sb)
+    tables = rec.covariate_arrays()
+    deltas = rec.delta_qs()
+    outs = []
+    for sb, q in parts:
+        o_seg = torch.full((sb.rows_bound * L + 16,), 255, dtype=torch.uint8, device=q.device)
+        o = torch.full_like(q, 255)
+        rec.apply_segmented(sb, o_seg)
+        rec.unsegment(sb, o_seg, o)
+        outs.append(o.cpu().numpy())
+    rec.check_status()
+    return tables, deltas, np.concatenate(outs).reshape(N, L)
+
+
+def _segmented_ok(L, R):
+    from kbbq import _native
+    return bool(_native.lib().kbbq_segmented_supported(L, R, 6))
+
+
+@pytest.mark.parametrize("path", [1, 2, SEGMENTED])
 def test_golden_cases_device_api(torch_cuda, golden_case, path):
     g = golden_case
     L, R = int(g["L"]), int(g["R"])
-    tables, deltas, out = _run_device(torch_cuda, g["seq"], g["qual"], g["corr"], g["rg"], g["second"], L, R, path)
+    if path == SEGMENTED:
+        tables, deltas, out = _run_segmented(torch_cuda, g["seq"], g["qual"], g["corr"], g["rg"], g["second"], L, R)
+    else:
+        tables, deltas, out = _run_device(torch_cuda, g["seq"], g["qual"], g["corr"], g["rg"], g["second"], L, R, path)
     for got, key in zip(tables, TABLE_KEYS):
         assert np.array_equal(got, g[key]), key
     for got, key in zip(deltas, DELTA_KEYS):
@@ -153,8 +191,11 @@ def test_synthetic_configs_vs_oracle(torch_cuda, oracle_mod, case):
     want_t = oracle_mod.covariate_arrays(seq, qual, corr, rg, second, L, R)
     want_d = oracle_mod.get_delta_qs(*want_t)
     want_o = oracle_mod.apply(seq, qual, rg, second, L, R, want_t[0], *want_d)
-    for path, splits in ((1, 1), (1, 3), (2, 1)):
-        tables, deltas, out = _run_device(torch_cuda, seq, qual, corr, rg, second, L, R, path, splits)
+    for path, splits in ((1, 1), (1, 3), (2, 1), (SEGMENTED, 1), (SEGMENTED, 3)):
+        if path == SEGMENTED:
+            tables, deltas, out = _run_segmented(torch_cuda, seq, qual, corr, rg, second, L, R, splits)
+        else:
+            tables, deltas, out = _run_device(torch_cuda, seq, qual, corr, rg, second, L, R, path, splits)
         for got, want, key in zip(tables, want_t, TABLE_KEYS):
             assert np.array_equal(got, want), (key, path, splits)
         for got, want, key in zip(deltas, want_d, DELTA_KEYS):
@@ -260,6 +301,11 @@ def test_full_size_properties(torch_cuda, case):
     rec.reset()
     rec.build(seq, qual, corr, rg, second, path=2)
     assert torch.equal(rec.tables, whole)
+    # the segmented layout (rows sorted by read group and mate) gives the same tables ...
+    rec.reset()
+    sb = rec.segment(seq, qual, corr, rg, second)
+    rec.build_segmented(sb)
+    assert torch.equal(rec.tables, whole)
     # apply: untouched below minscore, bounded otherwise, smem == generic
     rec.model()
     out = torch.empty_like(qual)
@@ -268,6 +314,12 @@ def test_full_size_properties(torch_cuda, case):
     assert int(out[valid].max()) <= 60
     out2 = torch.empty_like(qual)
     rec.apply(seq, qual, out2, rg, second, path=2)
+    assert torch.equal(out, out2)
+    # ... and the same output bytes once they are back in read order
+    out_seg = torch.empty(sb.rows_bound * L + 16, dtype=torch.uint8, device=qual.device)
+    rec.apply_segmented(sb, out_seg)
+    out2.fill_(255)
+    rec.unsegment(sb, out_seg, out2)
     assert torch.equal(out, out2)
     rec.check_status()
 
@@ -293,9 +345,46 @@ def test_random_shapes_vs_oracle(torch_cuda, oracle_mod):
         want_t = oracle_mod.covariate_arrays(seq, qual, corr, rg, second, L, R)
         want_d = oracle_mod.get_delta_qs(*want_t)
         want_o = oracle_mod.apply(seq, qual, rg, second, L, R, want_t[0], *want_d)
-        tables, deltas, out = _run_device(torch_cuda, seq, qual, corr, rg, second, L, R, 0, int(rng.integers(1, 4)))
-        for got, want, key in zip(tables, want_t, TABLE_KEYS):
-            assert np.array_equal(got, want), (key, L, R, N)
-        for got, want, key in zip(deltas, want_d, DELTA_KEYS):
-            assert np.array_equal(got, want), (key, L, R, N)
-        assert np.array_equal(out.astype(np.int16), want_o), (L, R, N)
+        runs = [_run_device(torch_cuda, seq, qual, corr, rg, second, L, R, 0, int(rng.integers(1, 4)))]
+        if _segmented_ok(L, R):
+            runs.append(_run_segmented(torch_cuda, seq, qual, corr, rg, second, L, R, int(rng.integers(1, 4))))
+        for tables, deltas, out in runs:
+            for got, want, key in zip(tables, want_t, TABLE_KEYS):
+                assert np.array_equal(got, want), (key, L, R, N)
+            for got, want, key in zip(deltas, want_d, DELTA_KEYS):
+                assert np.array_equal(got, want), (key, L, R, N)
+            assert np.array_equal(out.astype(np.int16), want_o), (L, R, N)
+
+
+def test_segmented_layout_invariants(torch_cuda):
+    """kbbq_segment_plan: spans sorted by 2 * rg + second, 16-row aligned, dest a bijection onto the occupied
+    rows; a malformed span table is refused by the kernels (KBBQ_FLAG_SEGMENTS -> ValueError)."""
+    torch = torch_cuda
+    from kbbq import synth
+    from kbbq.device import DeviceRecalibrator
+    N, L, R = 20_011, 150, 5
+    seq, qual, corr, rg, second = synth.synth_reads(77, 0, N, L, R)
+    rg = np.random.default_rng(1).integers(0, R - 1, N).astype(np.uint16)   # the last read group stays empty
+    s, q, c, g, sec = _dev(torch, seq, qual, corr, rg, second)
+    rec = DeviceRecalibrator(L, R, max_reads=N)
+    sb = rec.segment(s, q, c, g, sec)
+    seg = sb.seg.cpu().numpy().astype(np.int64)
+    off, cnt = seg[:2 * R + 1], seg[2 * R + 1:4 * R + 1]
+    key = 2 * rg.astype(np.int64) + second
+    assert off[0] == 0 and np.all(off % 16 == 0) and np.all(np.diff(off) >= 0)
+    assert np.array_equal(cnt, np.bincount(key, minlength=2 * R))
+    assert np.all(off[1:] - off[:-1] >= cnt) and np.all(off[1:] - off[:-1] - cnt < 16)
+    dest = sb.dest.cpu().numpy().astype(np.int64)[:N]
+    assert np.all((dest >= off[key]) & (dest < off[key] + cnt[key])) and len(np.unique(dest)) == N
+    rows = sb.seq[:sb.rows_bound * L].view(-1, L).cpu().numpy()
+    assert np.array_equal(rows[dest], seq)
+    pad = np.ones(off[-1], bool)
+    pad[dest] = False
+    assert np.all(sb.qual[:sb.rows_bound * L].view(-1, L).cpu().numpy()[:off[-1]][pad] == 0)
+    rec.check_status()
+    bad = sb.seg.clone()
+    bad[1] = 8   # not a multiple of 16
+    sb.seg = bad
+    rec.build_segmented(sb)
+    with pytest.raises(ValueError):
+        rec.check_status()
