@@ -222,19 +222,71 @@ int kbbq_apply_segmented(const uint8_t *seq_dev, const uint8_t *qual_dev, const 
 /*
  * Whole path on HOST buffers: H2D, build, marginals, deltas, apply, D2H -- what
  * recalibrate.recalibrate_fastq (kbbq/recalibrate.py:123-156) does between parsing and printing.
- * Reads are streamed in chunks over two CUDA streams; tables_host (optional, may be NULL) receives
+ * Reads are streamed in chunks over three CUDA streams (upload, compute, download); the corrected reads cross
+ * PCIe as a 1-bit-per-base mismatch map (kbbq_host_mismatch_bits); with several read groups every chunk is
+ * rewritten into the segmented layout on the device.  tables_host (optional, may be NULL) receives
  * [pos_errs | pos_total | din_errs | din_total]; deltas_host (optional) receives
- * [meanq R | rgdq R | qdq R*43 | posdq R*43*2L | dindq R*43*17].  Synchronous; calls on one device
- * are serialised.
+ * [meanq R | rgdq R | qdq R*43 | posdq R*43*2L | dindq R*43*17].  Synchronous; calls are serialised.
+ *
+ * kbbq_recalibrate_host_multi is the same call over n_dev devices of one box: reads are
+ * sharded in contiguous ranges with boundaries at multiples of 16 reads (kbbq/parallel.py: shard_range), one host
+ * thread and one session per device; after the build pass every device adds up all the partial tables itself --
+ * one kernel reading the peers' tables over NVLink (through pinned host memory when a device cannot reach a
+ * peer) -- so all devices hold the same integers, recompute the same deltas and apply them to their shard.
+ * rg[] holds the global first-seen read-group numbers (kbbq/recalibrate.py:59-64), assigned before sharding.
+ * Results are bit-identical for any device list; a device may be listed more than once.
  */
 int kbbq_recalibrate_host(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr,
                           const uint16_t *rg, const uint8_t *second, int64_t N, int L, int R,
                           int minscore, uint8_t *out_qual, int64_t *tables_host,
                           int64_t *deltas_host, int *status_out, int device);
+int kbbq_recalibrate_host_multi(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr,
+                                const uint16_t *rg, const uint8_t *second, int64_t N, int L, int R,
+                                int minscore, uint8_t *out_qual, int64_t *tables_host,
+                                int64_t *deltas_host, int *status_out, const int *devices, int n_dev);
 
-/* kbbq_recalibrate_host keeps its device buffers and streams between calls (allocating several GB
- * per call costs far more than the kernels); this frees them for `device`. */
+/* The whole-path entry points keep their sessions (device buffers, streams) between calls: allocating several
+ * GB per call costs far more than the kernels.  This frees what is cached for `device`. */
 int kbbq_host_release(int device);
+
+/*
+ * Sessions: the two passes of kbbq/recalibrate.py:123-156 on one device, fed chunk by chunk from host memory
+ * (files that do not fit host or device memory at once; several processes, one per GPU).
+ *   create        chunk_reads = capacity of a chunk (<= 0: ~256 MiB per array); resident_reads_cap = how many reads
+ *                 may stay in HBM between the passes (0: streaming, pass 2 sends the reads again);
+ *                 host_threads = host threads for the mismatch map (<= 0: all)
+ *   build_chunk   pass 1 of a chunk: upload + build, accumulating into the session's tables.  Returns once the
+ *                 host buffers have been read (they may be reused); the build itself runs behind.
+ *   tables / set_tables / tables_dev   the partial tables [pos_errs | pos_total | din_errs | din_total] for sums
+ *                 over sessions or ranks (tables_dev: device pointer, element count and the session's compute
+ *                 stream; call kbbq_session_flush before touching them from another stream)
+ *   model         marginals + meanq + delta tables from the current tables (deltas_host: optional copy, layout
+ *                 as kbbq_recalibrate_host's)
+ *   apply_resident / apply_chunk   pass 2 of a chunk kept in pass 1 (by its index) / of reads sent again;
+ *                 out_qual is complete after kbbq_session_sync (chunks drain in order)
+ *   sync          wait for everything; *status_out = device status word (KBBQ_E_DATA when non-zero)
+ *   reset         forget tables and chunks, keep the memory
+ * One host thread at a time per session.
+ */
+typedef struct kbbq_session kbbq_session;
+int kbbq_session_create(int device, int L, int R, int minscore, int64_t chunk_reads, int64_t resident_reads_cap,
+                        int host_threads, kbbq_session **out);
+void kbbq_session_destroy(kbbq_session *s);
+int64_t kbbq_session_chunk_reads(const kbbq_session *s);
+int kbbq_session_reset(kbbq_session *s);
+int kbbq_session_build_chunk(kbbq_session *s, const uint8_t *seq, const uint8_t *qual, const uint8_t *corr,
+                             const uint16_t *rg, const uint8_t *second, int64_t n, int keep_resident);
+int kbbq_session_tables(kbbq_session *s, int64_t *tables_host);
+int kbbq_session_set_tables(kbbq_session *s, const int64_t *tables_host);
+int kbbq_session_tables_dev(kbbq_session *s, int64_t **tables_dev, int64_t *elems, void **stream);
+int kbbq_session_model(kbbq_session *s, int64_t *deltas_host);
+int kbbq_session_apply_resident(kbbq_session *s, int64_t chunk, uint8_t *out_qual);
+int kbbq_session_apply_chunk(kbbq_session *s, const uint8_t *seq, const uint8_t *qual, const uint16_t *rg,
+                             const uint8_t *second, int64_t n, uint8_t *out_qual);
+int kbbq_session_flush(kbbq_session *s);
+int kbbq_session_sync(kbbq_session *s, int *status_out);
+/* bytes the session has copied over PCIe since create / reset */
+int kbbq_session_traffic(const kbbq_session *s, int64_t *h2d_bytes, int64_t *d2h_bytes);
 
 /* Host-buffer variants of the two halves (drop-in backing of fastq_to_covariate_arrays and of
  * the apply loop when the caller keeps the tables). Synchronous. */

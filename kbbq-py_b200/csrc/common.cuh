@@ -1,6 +1,7 @@
 // common.cuh -- shared definitions of the B200 kbbq hot-path kernels (sm_100a only).
 #pragma once
 #include <algorithm>
+#include <atomic>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
@@ -21,7 +22,7 @@ constexpr uint32_t H4 = 0x80808080u;   // high bit of every byte
 constexpr uint32_t ONE4 = 0x01010101u;
 
 // Launch counter (bench.py reports it as gpu_launches).
-extern long long g_launches;
+extern std::atomic<long long> g_launches;
 extern char g_last_cuda_error[256];
 
 #define KBBQ_CUDA(call)                                                                  \

@@ -1,0 +1,759 @@
+// host_api.cu -- host-buffer side of the C ABI: sessions, the whole-path entry points, several GPUs.
+//
+// What recalibrate.recalibrate_fastq (kbbq/recalibrate.py:123-156) does between parsing and printing is two
+// passes over the reads around one small model step.  A SESSION is that path on one device, fed chunk by
+// chunk from host memory:
+//
+//     kbbq_session_build_chunk  x n     H2D (seq, qual, 1-bit mismatch map) -> [segment rows] -> build   pass 1
+//     (tables may be summed with other sessions / ranks here: they are additive integers)
+//     kbbq_session_model                marginals + delta tables
+//     kbbq_session_apply_*      x n     [H2D] -> apply -> [unsegment] -> D2H                              pass 2
+//
+// Three streams (upload, compute, download) and two staging slots per direction keep the copy engines and the
+// SMs busy together; chunks can stay resident in HBM between the passes (segmented when there are several read
+// groups, segment.cuh) or be sent again (files larger than the device).  kbbq_recalibrate_host is one session
+// over one buffer, kbbq_recalibrate_host_multi one session per device on its own host thread with the partial
+// tables summed over NVLink peer memory (one kernel per device reads every peer's table and writes the sum),
+// through pinned host memory when the devices cannot reach each other.  Every kernel launched here goes through
+// the device-pointer entry points of kbbq_b200.cu.
+#include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <sched.h>
+#include <stdlib.h>
+#include <string.h>
+#include <thread>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace kbbq;
+
+namespace {
+
+#define KBBQ_TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
+
+constexpr int MAX_DEVICES = 16;
+
+struct Carver {  // bump allocator over one allocation (first pass with base == nullptr measures)
+    char *base;
+    size_t off = 0;
+    explicit Carver(void *b) : base((char *)b) {}
+    template <class T> T *take(size_t n_elems) {
+        T *p = base ? (T *)(base + off) : nullptr;
+        off = (off + n_elems * sizeof(T) + 255) / 256 * 256;
+        return p;
+    }
+};
+
+// [q_errs R*43 | q_total R*43 | rg_errs R | rg_total R | meanq R | rgdq R | qdq R*43 | posdq R*43*2L | dindq R*43*17]
+struct ModelPtrs {
+    int64_t *q_errs, *q_total, *rg_errs, *rg_total, *meanq, *rgdq, *qdq, *posdq, *dindq;
+    size_t elems;
+};
+ModelPtrs carve_model(int64_t *base, int L, int R) {
+    ModelPtrs m;
+    size_t o = 0;
+    m.q_errs = base + o; o += (size_t)R * NQ;
+    m.q_total = base + o; o += (size_t)R * NQ;
+    m.rg_errs = base + o; o += R;
+    m.rg_total = base + o; o += R;
+    m.meanq = base + o; o += R;
+    m.rgdq = base + o; o += R;
+    m.qdq = base + o; o += (size_t)R * NQ;
+    m.posdq = base + o; o += (size_t)R * NQ * 2 * L;
+    m.dindq = base + o; o += (size_t)R * NQ * 17;
+    m.elems = o;
+    return m;
+}
+
+struct PeerTables {
+    const long long *src[MAX_DEVICES];
+};
+
+// out[i] = sum over the n tables; src[k] may live on a peer device (NVLink loads)
+__global__ void sum_tables_kernel(PeerTables p, int n, long long *out, size_t elems) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < elems; i += (size_t)gridDim.x * blockDim.x) {
+        long long v = 0;
+        for (int k = 0; k < n; ++k) v += p.src[k][i];
+        out[i] = v;
+    }
+}
+
+struct UpSlot {   // one upload in flight: the chunk as the host has it (read order)
+    uint8_t *seq = nullptr, *qual = nullptr, *corr = nullptr, *sec = nullptr;
+    uint16_t *rg = nullptr;
+    uint32_t *bits = nullptr;
+    // streaming sessions with several read groups: the segmented copy of the chunk
+    uint8_t *sseq = nullptr, *squal = nullptr, *scorr = nullptr;
+    uint32_t *seg = nullptr, *dest = nullptr;
+    uint32_t *h_bits = nullptr;   // pinned
+    cudaEvent_t uploaded = nullptr, consumed = nullptr;
+};
+
+struct Resident {  // a chunk kept in HBM between the passes
+    uint8_t *seq = nullptr, *qual = nullptr, *sec = nullptr;
+    uint16_t *rg = nullptr;
+    uint32_t *seg = nullptr, *dest = nullptr;
+    int64_t n = 0;
+};
+
+struct OutSlot {
+    uint8_t *out = nullptr, *out_seg = nullptr;
+    cudaEvent_t applied = nullptr, drained = nullptr;
+};
+
+}  // namespace
+
+struct kbbq_session {
+    int device = 0, L = 0, R = 1, minscore = 6;
+    int64_t C = 0;          // reads per chunk (capacity)
+    int64_t M = 0;          // reads that can stay resident (0: streaming session)
+    int64_t rowsC = 0;      // rows of a chunk in the segmented layout
+    bool segmode = false, use_bits = true;
+    int host_threads = 0;
+    void *base = nullptr;
+    size_t cap = 0;
+    void *pinned = nullptr;
+    cudaStream_t s_up = nullptr, s_comp = nullptr, s_down = nullptr;
+    int64_t *d_tab = nullptr, *d_sum = nullptr, *d_model = nullptr;
+    int *d_status = nullptr;
+    void *d_ws = nullptr;
+    size_t ws_bytes = 0, ntab = 0;
+    ModelPtrs mp;
+    UpSlot up[2];
+    OutSlot down[2];
+    std::vector<Resident> res;
+    int64_t built = 0, applied = 0;
+    bool summed = false;    // the model reads d_sum (tables of several sessions added up) instead of d_tab
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
+    std::mutex mu;
+
+    ~kbbq_session() {
+        cudaSetDevice(device);
+        for (auto s : {s_up, s_comp, s_down}) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+        for (auto &u : up) { if (u.uploaded) cudaEventDestroy(u.uploaded); if (u.consumed) cudaEventDestroy(u.consumed); }
+        for (auto &o : down) { if (o.applied) cudaEventDestroy(o.applied); if (o.drained) cudaEventDestroy(o.drained); }
+        if (base) cudaFree(base);
+        if (pinned) cudaFreeHost(pinned);
+    }
+};
+
+namespace {
+
+int64_t default_chunk_reads(int L) {
+    int64_t chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / L);   // ~256 MiB per array per chunk
+    if (const char *e = getenv("KBBQ_HOST_CHUNK_READS")) chunk = std::max<int64_t>(16, atoll(e));  // test hook
+    return (chunk + 15) / 16 * 16;                                    // chunk starts stay 16-byte aligned
+}
+
+bool env_flag_off(const char *name) {   // unset or "0"
+    const char *e = getenv(name);
+    return !e || atoi(e) == 0;
+}
+
+// several read groups: chunks are rewritten into the segmented layout on the device (segment.cuh) unless the
+// shape has no shared-memory plan or the padding (32 R rows per chunk) would rival the chunk itself
+bool want_segmode(int L, int R, int minscore, int64_t C) {
+    return R > 1 && kbbq_segmented_supported(L, R, minscore) && (int64_t)32 * R * 8 <= C && env_flag_off("KBBQ_HOST_NO_SEGMENT");
+}
+
+int session_create(int device, int L, int R, int minscore, int64_t C, int64_t M, int host_threads, kbbq_session **out) {
+    if (device < 0 || L < 1 || R < 1 || R > 65535 || C < 1 || M < 0 || !out) return KBBQ_E_ARG;
+    KBBQ_CUDA(cudaSetDevice(device));
+    std::unique_ptr<kbbq_session> S(new kbbq_session);
+    S->device = device; S->L = L; S->R = R; S->minscore = minscore;
+    S->C = (C + 15) / 16 * 16;
+    S->M = M;
+    S->host_threads = host_threads;
+    S->use_bits = env_flag_off("KBBQ_HOST_NO_BITMAP");
+    S->segmode = want_segmode(L, R, minscore, S->C);
+    S->rowsC = S->segmode ? kbbq_segment_rows_bound(S->C, R) : S->C;
+    KBBQ_CUDA(cudaStreamCreateWithFlags(&S->s_up, cudaStreamNonBlocking));
+    KBBQ_CUDA(cudaStreamCreateWithFlags(&S->s_comp, cudaStreamNonBlocking));
+    KBBQ_CUDA(cudaStreamCreateWithFlags(&S->s_down, cudaStreamNonBlocking));
+    for (auto &u : S->up) {
+        KBBQ_CUDA(cudaEventCreateWithFlags(&u.uploaded, cudaEventDisableTiming));
+        KBBQ_CUDA(cudaEventCreateWithFlags(&u.consumed, cudaEventDisableTiming));
+    }
+    for (auto &o : S->down) {
+        KBBQ_CUDA(cudaEventCreateWithFlags(&o.applied, cudaEventDisableTiming));
+        KBBQ_CUDA(cudaEventCreateWithFlags(&o.drained, cudaEventDisableTiming));
+    }
+    const size_t npos = (size_t)R * NQ * 2 * L, ndin = (size_t)R * NQ * 16;
+    S->ntab = 2 * npos + 2 * ndin;
+    const size_t nmodel = carve_model(nullptr, L, R).elems;
+    KBBQ_TRY(kbbq_workspace_bytes(S->rowsC, L, R, &S->ws_bytes));
+    const size_t cb = (size_t)S->C * L + 16, rb = (size_t)S->rowsC * L + 16;
+    const size_t bits_words = ((size_t)S->C * L + 31) / 32 + 4;
+    const size_t seg_elems = (size_t)kbbq_segment_table_elems(R);
+    const int64_t nres = M ? (M + S->C - 1) / S->C : 0;
+    const bool seg = S->segmode, stream_seg = seg && nres == 0;
+    S->res.resize((size_t)nres);
+    for (int pass = 0; pass < 2; ++pass) {
+        Carver c(pass ? S->base : nullptr);
+        S->d_tab = c.take<int64_t>(S->ntab);
+        S->d_sum = c.take<int64_t>(S->ntab);
+        S->d_model = c.take<int64_t>(nmodel);
+        S->d_status = c.take<int>(64);
+        S->d_ws = c.take<uint8_t>(S->ws_bytes);
+        for (auto &u : S->up) {
+            // resident chunks of a plain batch are uploaded straight into their place: no staging copy of seq / qual
+            const bool staged = seg || nres == 0;
+            u.seq = staged ? c.take<uint8_t>(cb) : nullptr;
+            u.qual = staged ? c.take<uint8_t>(cb) : nullptr;
+            u.rg = staged ? c.take<uint16_t>((size_t)S->C + 8) : nullptr;
+            u.sec = staged ? c.take<uint8_t>((size_t)S->C + 16) : nullptr;
+            u.corr = c.take<uint8_t>(cb);
+            u.bits = S->use_bits ? c.take<uint32_t>(bits_words) : nullptr;
+            u.scorr = seg ? c.take<uint8_t>(rb) : nullptr;
+            u.sseq = stream_seg ? c.take<uint8_t>(rb) : nullptr;
+            u.squal = stream_seg ? c.take<uint8_t>(rb) : nullptr;
+            u.seg = stream_seg ? c.take<uint32_t>(seg_elems) : nullptr;
+            u.dest = stream_seg ? c.take<uint32_t>((size_t)S->C) : nullptr;
+        }
+        for (auto &o : S->down) {
+            o.out = c.take<uint8_t>(cb);
+            o.out_seg = seg ? c.take<uint8_t>(rb) : nullptr;
+        }
+        for (auto &r : S->res) {
+            r.seq = c.take<uint8_t>(seg ? rb : cb);
+            r.qual = c.take<uint8_t>(seg ? rb : cb);
+            r.rg = seg ? nullptr : c.take<uint16_t>((size_t)S->C + 8);
+            r.sec = seg ? nullptr : c.take<uint8_t>((size_t)S->C + 16);
+            r.seg = seg ? c.take<uint32_t>(seg_elems) : nullptr;
+            r.dest = seg ? c.take<uint32_t>((size_t)S->C) : nullptr;
+        }
+        if (!pass) {
+            S->cap = c.off;
+            KBBQ_CUDA(cudaMalloc(&S->base, S->cap));
+        }
+    }
+    S->mp = carve_model(S->d_model, L, R);
+    if (S->use_bits) {
+        KBBQ_CUDA(cudaHostAlloc(&S->pinned, 2 * bits_words * 4, cudaHostAllocDefault));
+        S->up[0].h_bits = (uint32_t *)S->pinned;
+        S->up[1].h_bits = (uint32_t *)S->pinned + bits_words;
+    }
+    KBBQ_CUDA(cudaMemsetAsync(S->d_tab, 0, S->ntab * 8, S->s_comp));
+    KBBQ_CUDA(cudaMemsetAsync(S->d_status, 0, 64 * sizeof(int), S->s_comp));
+    *out = S.release();
+    return KBBQ_OK;
+}
+
+// Forget the tables and chunks of the previous run (the device memory stays).
+int session_reset(kbbq_session *S) {
+    KBBQ_CUDA(cudaSetDevice(S->device));
+    KBBQ_CUDA(cudaStreamSynchronize(S->s_up));
+    KBBQ_CUDA(cudaStreamSynchronize(S->s_down));
+    KBBQ_CUDA(cudaMemsetAsync(S->d_tab, 0, S->ntab * 8, S->s_comp));
+    KBBQ_CUDA(cudaMemsetAsync(S->d_status, 0, sizeof(int), S->s_comp));
+    S->built = S->applied = 0;
+    S->summed = false;
+    S->h2d_bytes = S->d2h_bytes = 0;
+    for (auto &r : S->res) r.n = 0;
+    return KBBQ_OK;
+}
+
+int upload_reads(kbbq_session *S, const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, const uint8_t *second,
+                 int64_t n, uint8_t *d_seq, uint8_t *d_qual, uint16_t *d_rg, uint8_t *d_sec) {
+    const size_t nb = (size_t)n * S->L;
+    KBBQ_CUDA(cudaMemcpyAsync(d_seq, seq, nb, cudaMemcpyHostToDevice, S->s_up));
+    KBBQ_CUDA(cudaMemcpyAsync(d_qual, qual, nb, cudaMemcpyHostToDevice, S->s_up));
+    S->h2d_bytes += 2 * (int64_t)nb;
+    if (rg) { KBBQ_CUDA(cudaMemcpyAsync(d_rg, rg, (size_t)n * 2, cudaMemcpyHostToDevice, S->s_up)); S->h2d_bytes += 2 * n; }
+    if (second) { KBBQ_CUDA(cudaMemcpyAsync(d_sec, second, (size_t)n, cudaMemcpyHostToDevice, S->s_up)); S->h2d_bytes += n; }
+    return KBBQ_OK;
+}
+
+// Pass 1 of one chunk, asynchronous: nothing here waits for the device except for the reuse of the pinned
+// bit-map slot (two chunks back).  keep: the chunk stays in HBM for kbbq_session_apply_resident.
+int build_chunk_async(kbbq_session *S, const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,
+                      const uint8_t *second, int64_t n, bool keep) {
+    if (n < 0 || n > S->C) return KBBQ_E_ARG;
+    if (n == 0) return KBBQ_OK;
+    if (!seq || !qual || !corr) return KBBQ_E_ARG;
+    const int64_t k = S->built;
+    if (keep && k >= (int64_t)S->res.size()) return KBBQ_E_ARG;
+    S->built++;
+    UpSlot &u = S->up[k & 1];
+    Resident *r = keep ? &S->res[(size_t)k] : nullptr;
+    const int L = S->L, R = S->R;
+    const size_t nb = (size_t)n * L;
+    const bool direct = keep && !S->segmode;   // plain resident chunk: uploaded into its place
+    uint8_t *d_seq = direct ? r->seq : u.seq, *d_qual = direct ? r->qual : u.qual;
+    uint16_t *d_rg = rg ? (direct ? r->rg : u.rg) : nullptr;
+    uint8_t *d_sec = second ? (direct ? r->sec : u.sec) : nullptr;
+    if (r) r->n = n;
+
+    KBBQ_CUDA(cudaStreamWaitEvent(S->s_up, u.consumed, 0));   // the slot's previous chunk has been built
+    KBBQ_TRY(upload_reads(S, seq, qual, rg, second, n, d_seq, d_qual, d_rg, d_sec));
+    if (S->use_bits) {
+        // the host cores compare while the copy engine moves seq and qual of this chunk (host_pack.cpp)
+        KBBQ_CUDA(cudaEventSynchronize(u.uploaded));           // the pinned map of two chunks back is on the device
+        KBBQ_TRY(kbbq_host_mismatch_bits(seq, corr, (int64_t)nb, u.h_bits, S->host_threads));
+        const size_t bb = ((nb + 31) / 32) * 4;
+        KBBQ_CUDA(cudaMemcpyAsync(u.bits, u.h_bits, bb, cudaMemcpyHostToDevice, S->s_up));
+        S->h2d_bytes += (int64_t)bb;
+    } else {
+        KBBQ_CUDA(cudaMemcpyAsync(u.corr, corr, nb, cudaMemcpyHostToDevice, S->s_up));
+        S->h2d_bytes += (int64_t)nb;
+    }
+    KBBQ_CUDA(cudaEventRecord(u.uploaded, S->s_up));
+    KBBQ_CUDA(cudaStreamWaitEvent(S->s_comp, u.uploaded, 0));
+    if (S->use_bits) KBBQ_TRY(kbbq_expand_mismatch_bits(d_seq, u.bits, (int64_t)nb, u.corr, S->s_comp));
+    const size_t npos = (size_t)R * NQ * 2 * L, ndin = (size_t)R * NQ * 16;
+    int64_t *pe = S->d_tab, *pt = pe + npos, *de = pt + npos, *dt = de + ndin;
+    if (S->segmode) {
+        uint32_t *seg = keep ? r->seg : u.seg, *dest = keep ? r->dest : u.dest;
+        uint8_t *sseq = keep ? r->seq : u.sseq, *squal = keep ? r->qual : u.squal;
+        KBBQ_TRY(kbbq_segment_plan(d_rg, d_sec, n, R, seg, dest, S->d_status, S->s_comp));
+        KBBQ_TRY(kbbq_segment_rows(d_seq, dest, n, L, sseq, S->s_comp));
+        KBBQ_TRY(kbbq_segment_rows(d_qual, dest, n, L, squal, S->s_comp));
+        KBBQ_TRY(kbbq_segment_rows(u.corr, dest, n, L, u.scorr, S->s_comp));
+        KBBQ_TRY(kbbq_segment_pad(seg, R, L, sseq, squal, u.scorr, S->s_comp));
+        KBBQ_TRY(kbbq_build_segmented(sseq, squal, u.scorr, seg, S->rowsC, L, R, S->minscore, pe, pt, de, dt, S->d_ws,
+                                      S->ws_bytes, S->d_status, S->s_comp));
+    } else {
+        KBBQ_TRY(kbbq_build(d_seq, d_qual, u.corr, d_rg, d_sec, n, L, R, S->minscore, pe, pt, de, dt, S->d_ws, S->ws_bytes,
+                            S->d_status, 0, S->s_comp));
+    }
+    KBBQ_CUDA(cudaEventRecord(u.consumed, S->s_comp));
+    return KBBQ_OK;
+}
+
+int model_async(kbbq_session *S) {
+    const int L = S->L, R = S->R;
+    const size_t npos = (size_t)R * NQ * 2 * L, ndin = (size_t)R * NQ * 16;
+    int64_t *pe = S->summed ? S->d_sum : S->d_tab, *pt = pe + npos, *de = pt + npos, *dt = de + ndin;
+    const ModelPtrs &mp = S->mp;
+    KBBQ_TRY(kbbq_marginals(pe, pt, L, R, mp.q_errs, mp.q_total, mp.rg_errs, mp.rg_total, mp.meanq, S->s_comp));
+    KBBQ_TRY(kbbq_get_delta_qs(mp.meanq, mp.rg_errs, mp.rg_total, mp.q_errs, mp.q_total, pe, pt, de, dt, R, NQ, 2 * L, 16,
+                               mp.rgdq, mp.qdq, mp.posdq, mp.dindq, S->s_comp));
+    return KBBQ_OK;
+}
+
+// apply + (unsegment) + D2H of one chunk that is on the device; the compute stream is positioned behind whatever
+// put it there
+int apply_and_download(kbbq_session *S, const uint8_t *d_seq, const uint8_t *d_qual, const uint16_t *d_rg,
+                       const uint8_t *d_sec, const uint32_t *seg, const uint32_t *dest, int64_t n, uint8_t *out_host) {
+    const int L = S->L, R = S->R;
+    OutSlot &o = S->down[S->applied++ & 1];
+    const ModelPtrs &mp = S->mp;
+    KBBQ_CUDA(cudaStreamWaitEvent(S->s_comp, o.drained, 0));   // the slot's previous chunk is in host memory
+    if (S->segmode) {
+        KBBQ_TRY(kbbq_apply_segmented(d_seq, d_qual, seg, S->rowsC, L, R, S->minscore, mp.meanq, mp.rgdq, mp.qdq, mp.posdq,
+                                      mp.dindq, NQ, 17, o.out_seg, S->d_ws, S->ws_bytes, S->d_status, S->s_comp));
+        KBBQ_TRY(kbbq_unsegment_rows(o.out_seg, dest, n, L, S->rowsC, o.out, S->s_comp));
+    } else {
+        KBBQ_TRY(kbbq_apply(d_seq, d_qual, d_rg, d_sec, n, L, R, S->minscore, mp.meanq, mp.rgdq, mp.qdq, mp.posdq, mp.dindq,
+                            NQ, 17, o.out, S->d_ws, S->ws_bytes, S->d_status, 0, S->s_comp));
+    }
+    KBBQ_CUDA(cudaEventRecord(o.applied, S->s_comp));
+    KBBQ_CUDA(cudaStreamWaitEvent(S->s_down, o.applied, 0));
+    KBBQ_CUDA(cudaMemcpyAsync(out_host, o.out, (size_t)n * L, cudaMemcpyDeviceToHost, S->s_down));
+    S->d2h_bytes += n * L;
+    KBBQ_CUDA(cudaEventRecord(o.drained, S->s_down));
+    return KBBQ_OK;
+}
+
+int apply_resident_async(kbbq_session *S, int64_t k, uint8_t *out_host) {
+    if (k < 0 || k >= (int64_t)S->res.size() || !out_host) return KBBQ_E_ARG;
+    const Resident &r = S->res[(size_t)k];
+    if (r.n == 0) return KBBQ_OK;
+    return apply_and_download(S, r.seq, r.qual, r.rg, r.sec, r.seg, r.dest, r.n, out_host);
+}
+
+// pass 2 of a chunk that is not resident: the reads are sent again
+int apply_chunk_async(kbbq_session *S, const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, const uint8_t *second,
+                      int64_t n, uint8_t *out_host) {
+    if (n < 0 || n > S->C || !S->up[0].seq) return KBBQ_E_ARG;
+    if (n == 0) return KBBQ_OK;
+    if (!seq || !qual || !out_host) return KBBQ_E_ARG;
+    UpSlot &u = S->up[S->applied & 1];
+    const int L = S->L, R = S->R;
+    uint16_t *d_rg = rg ? u.rg : nullptr;
+    uint8_t *d_sec = second ? u.sec : nullptr;
+    KBBQ_CUDA(cudaStreamWaitEvent(S->s_up, u.consumed, 0));
+    KBBQ_TRY(upload_reads(S, seq, qual, rg, second, n, u.seq, u.qual, d_rg, d_sec));
+    KBBQ_CUDA(cudaEventRecord(u.uploaded, S->s_up));
+    KBBQ_CUDA(cudaStreamWaitEvent(S->s_comp, u.uploaded, 0));
+    const uint8_t *a_seq = u.seq, *a_qual = u.qual;
+    if (S->segmode) {
+        uint8_t *sseq = u.sseq ? u.sseq : nullptr, *squal = u.squal;
+        if (!sseq) return KBBQ_E_ARG;   // a resident session has no streaming buffers
+        KBBQ_TRY(kbbq_segment_plan(d_rg, d_sec, n, R, u.seg, u.dest, S->d_status, S->s_comp));
+        KBBQ_TRY(kbbq_segment_rows(u.seq, u.dest, n, L, sseq, S->s_comp));
+        KBBQ_TRY(kbbq_segment_rows(u.qual, u.dest, n, L, squal, S->s_comp));
+        KBBQ_TRY(kbbq_segment_pad(u.seg, R, L, sseq, squal, nullptr, S->s_comp));
+        a_seq = sseq; a_qual = squal;
+    }
+    KBBQ_TRY(apply_and_download(S, a_seq, a_qual, d_rg, d_sec, u.seg, u.dest, n, out_host));
+    KBBQ_CUDA(cudaEventRecord(u.consumed, S->s_comp));
+    return KBBQ_OK;
+}
+
+int session_sync(kbbq_session *S, int *status_out) {
+    int st = 0;
+    KBBQ_CUDA(cudaStreamSynchronize(S->s_up));
+    KBBQ_CUDA(cudaStreamSynchronize(S->s_comp));
+    KBBQ_CUDA(cudaStreamSynchronize(S->s_down));
+    KBBQ_CUDA(cudaMemcpy(&st, S->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (status_out) *status_out = st;
+    return st ? KBBQ_E_DATA : KBBQ_OK;
+}
+
+// ---- sessions kept between calls of the whole-path entry points (allocating several GB per call costs tens of
+// milliseconds to a second of driver page scrubbing, far more than the kernels) ----
+struct CacheSlot {
+    std::mutex mu;
+    std::unique_ptr<kbbq_session> s;
+};
+CacheSlot g_cache[MAX_DEVICES];
+
+int cached_session(int slot, int device, int L, int R, int minscore, int64_t C, int64_t M, int host_threads,
+                   kbbq_session **out) {
+    CacheSlot &c = g_cache[slot];
+    kbbq_session *s = c.s.get();
+    const int64_t C16 = (C + 15) / 16 * 16;
+    const int64_t nres = M ? (M + C16 - 1) / C16 : 0;
+    if (s && s->device == device && s->L == L && s->R == R && s->minscore == minscore && s->C == C16 &&
+        (int64_t)s->res.size() >= nres && (nres > 0) == (s->M > 0) && s->use_bits == env_flag_off("KBBQ_HOST_NO_BITMAP") &&
+        s->segmode == want_segmode(L, R, minscore, C16)) {
+        s->host_threads = host_threads;
+        KBBQ_TRY(session_reset(s));
+        *out = s;
+        return KBBQ_OK;
+    }
+    c.s.reset();
+    kbbq_session *fresh = nullptr;
+    KBBQ_TRY(session_create(device, L, R, minscore, C, M, host_threads, &fresh));
+    c.s.reset(fresh);
+    *out = fresh;
+    return KBBQ_OK;
+}
+
+// how many reads of a batch of N can stay resident on `device` (0: stream them twice)
+int64_t resident_reads(int device, int64_t N, int L, int R, int64_t C, size_t already_ours) {
+    size_t free_b = 0, total_b = 0;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 0;
+    free_b += already_ours;
+    const double per_read = 2.0 * L + 8.0;   // seq + qual + (dest or rg / second)
+    const double staging = 12.0 * (double)(C + 32 * R) * L;
+    bool resident = (double)N * per_read * 1.02 + staging < 0.85 * (double)free_b;
+    if (const char *e = getenv("KBBQ_HOST_FORCE_STREAMING")) resident = resident && atoi(e) == 0;   // test hook
+    return resident ? N : 0;
+}
+
+// one device's share of the two passes
+int run_build_pass(kbbq_session *S, const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,
+                   const uint8_t *second, int64_t N) {
+    const int L = S->L;
+    const int64_t C = S->C, nchunks = N ? (N + C - 1) / C : 0;
+    for (int64_t k = 0; k < nchunks; ++k) {
+        const int64_t r0 = k * C, n = std::min(C, N - r0);
+        KBBQ_TRY(build_chunk_async(S, seq + (size_t)r0 * L, qual + (size_t)r0 * L, corr + (size_t)r0 * L, rg ? rg + r0 : nullptr,
+                                   second ? second + r0 : nullptr, n, S->M > 0));
+    }
+    return KBBQ_OK;
+}
+
+int run_apply_pass(kbbq_session *S, const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, const uint8_t *second,
+                   int64_t N, uint8_t *out_qual) {
+    const int L = S->L;
+    const int64_t C = S->C, nchunks = N ? (N + C - 1) / C : 0;
+    KBBQ_TRY(model_async(S));
+    for (int64_t k = 0; k < nchunks; ++k) {
+        const int64_t r0 = k * C, n = std::min(C, N - r0);
+        if (S->M > 0) KBBQ_TRY(apply_resident_async(S, k, out_qual + (size_t)r0 * L));
+        else KBBQ_TRY(apply_chunk_async(S, seq + (size_t)r0 * L, qual + (size_t)r0 * L, rg ? rg + r0 : nullptr,
+                                        second ? second + r0 : nullptr, n, out_qual + (size_t)r0 * L));
+    }
+    return KBBQ_OK;
+}
+
+int fetch_results(kbbq_session *S, int64_t *tables_host, int64_t *deltas_host) {
+    const int L = S->L, R = S->R;
+    if (tables_host)
+        KBBQ_CUDA(cudaMemcpyAsync(tables_host, S->summed ? S->d_sum : S->d_tab, S->ntab * 8, cudaMemcpyDeviceToHost, S->s_comp));
+    if (deltas_host)
+        KBBQ_CUDA(cudaMemcpyAsync(deltas_host, S->mp.meanq, ((size_t)2 * R + (size_t)R * NQ * (1 + 2 * L + 17)) * 8,
+                                  cudaMemcpyDeviceToHost, S->s_comp));
+    return KBBQ_OK;
+}
+
+struct Barrier {   // std::barrier is C++20
+    std::mutex mu;
+    std::condition_variable cv;
+    int n, waiting = 0, generation = 0;
+    explicit Barrier(int n_) : n(n_) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        const int gen = generation;
+        if (++waiting == n) { waiting = 0; ++generation; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != generation; });
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+int kbbq_session_create(int device, int L, int R, int minscore, int64_t chunk_reads, int64_t resident_reads_cap,
+                        int host_threads, kbbq_session **out) {
+    if (chunk_reads <= 0) chunk_reads = default_chunk_reads(L > 0 ? L : 1);
+    return session_create(device, L, R, minscore, chunk_reads, resident_reads_cap, host_threads, out);
+}
+
+void kbbq_session_destroy(kbbq_session *s) { delete s; }
+
+int64_t kbbq_session_chunk_reads(const kbbq_session *s) { return s ? s->C : -1; }
+
+int kbbq_session_reset(kbbq_session *s) {
+    if (!s) return KBBQ_E_ARG;
+    std::lock_guard<std::mutex> lock(s->mu);
+    return session_reset(s);
+}
+
+int kbbq_session_build_chunk(kbbq_session *s, const uint8_t *seq, const uint8_t *qual, const uint8_t *corr,
+                             const uint16_t *rg, const uint8_t *second, int64_t n, int keep_resident) {
+    if (!s) return KBBQ_E_ARG;
+    std::lock_guard<std::mutex> lock(s->mu);
+    KBBQ_CUDA(cudaSetDevice(s->device));
+    const int64_t k = s->built;
+    KBBQ_TRY(build_chunk_async(s, seq, qual, corr, rg, second, n, keep_resident != 0));
+    if (n > 0) KBBQ_CUDA(cudaEventSynchronize(s->up[k & 1].uploaded));   // the caller may reuse its buffers
+    return KBBQ_OK;
+}
+
+int kbbq_session_tables(kbbq_session *s, int64_t *tables_host) {
+    if (!s || !tables_host) return KBBQ_E_ARG;
+    std::lock_guard<std::mutex> lock(s->mu);
+    KBBQ_CUDA(cudaSetDevice(s->device));
+    KBBQ_CUDA(cudaMemcpyAsync(tables_host, s->summed ? s->d_sum : s->d_tab, s->ntab * 8, cudaMemcpyDeviceToHost, s->s_comp));
+    KBBQ_CUDA(cudaStreamSynchronize(s->s_comp));
+    return KBBQ_OK;
+}
+
+int kbbq_session_set_tables(kbbq_session *s, const int64_t *tables_host) {
+    if (!s || !tables_host) return KBBQ_E_ARG;
+    std::lock_guard<std::mutex> lock(s->mu);
+    KBBQ_CUDA(cudaSetDevice(s->device));
+    KBBQ_CUDA(cudaMemcpyAsync(s->d_tab, tables_host, s->ntab * 8, cudaMemcpyHostToDevice, s->s_comp));
+    KBBQ_CUDA(cudaStreamSynchronize(s->s_comp));
+    s->summed = false;
+    return KBBQ_OK;
+}
+
+int kbbq_session_tables_dev(kbbq_session *s, int64_t **tables_dev, int64_t *elems, void **stream) {
+    if (!s || !tables_dev) return KBBQ_E_ARG;
+    *tables_dev = s->d_tab;
+    if (elems) *elems = (int64_t)s->ntab;
+    if (stream) *stream = (void *)s->s_comp;
+    return KBBQ_OK;
+}
+
+int kbbq_session_model(kbbq_session *s, int64_t *deltas_host) {
+    if (!s) return KBBQ_E_ARG;
+    std::lock_guard<std::mutex> lock(s->mu);
+    KBBQ_CUDA(cudaSetDevice(s->device));
+    KBBQ_TRY(model_async(s));
+    if (deltas_host) {
+        KBBQ_TRY(fetch_results(s, nullptr, deltas_host));
+        KBBQ_CUDA(cudaStreamSynchronize(s->s_comp));
+    }
+    return KBBQ_OK;
+}
+
+int kbbq_session_apply_resident(kbbq_session *s, int64_t chunk, uint8_t *out_qual) {
+    if (!s) return KBBQ_E_ARG;
+    std::lock_guard<std::mutex> lock(s->mu);
+    KBBQ_CUDA(cudaSetDevice(s->device));
+    return apply_resident_async(s, chunk, out_qual);
+}
+
+int kbbq_session_apply_chunk(kbbq_session *s, const uint8_t *seq, const uint8_t *qual, const uint16_t *rg,
+                             const uint8_t *second, int64_t n, uint8_t *out_qual) {
+    if (!s) return KBBQ_E_ARG;
+    std::lock_guard<std::mutex> lock(s->mu);
+    KBBQ_CUDA(cudaSetDevice(s->device));
+    const int64_t k = s->applied;
+    KBBQ_TRY(apply_chunk_async(s, seq, qual, rg, second, n, out_qual));
+    if (n > 0) KBBQ_CUDA(cudaEventSynchronize(s->up[k & 1].uploaded));   // the caller may reuse its input buffers
+    return KBBQ_OK;
+}
+
+int kbbq_session_flush(kbbq_session *s) {
+    if (!s) return KBBQ_E_ARG;
+    std::lock_guard<std::mutex> lock(s->mu);
+    KBBQ_CUDA(cudaSetDevice(s->device));
+    KBBQ_CUDA(cudaStreamSynchronize(s->s_up));
+    KBBQ_CUDA(cudaStreamSynchronize(s->s_comp));
+    return KBBQ_OK;
+}
+
+int kbbq_session_sync(kbbq_session *s, int *status_out) {
+    if (!s) return KBBQ_E_ARG;
+    std::lock_guard<std::mutex> lock(s->mu);
+    KBBQ_CUDA(cudaSetDevice(s->device));
+    return session_sync(s, status_out);
+}
+
+int kbbq_session_traffic(const kbbq_session *s, int64_t *h2d_bytes, int64_t *d2h_bytes) {
+    if (!s) return KBBQ_E_ARG;
+    if (h2d_bytes) *h2d_bytes = s->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = s->d2h_bytes;
+    return KBBQ_OK;
+}
+
+int kbbq_host_release(int device) {
+    if (device < 0) return KBBQ_E_ARG;
+    for (auto &c : g_cache) {
+        std::lock_guard<std::mutex> lock(c.mu);
+        if (c.s && c.s->device == device) c.s.reset();
+    }
+    return KBBQ_OK;
+}
+
+int kbbq_recalibrate_host(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,
+                          const uint8_t *second, int64_t N, int L, int R, int minscore, uint8_t *out_qual,
+                          int64_t *tables_host, int64_t *deltas_host, int *status_out, int device) {
+    const int devices[1] = {device};
+    return kbbq_recalibrate_host_multi(seq, qual, corr, rg, second, N, L, R, minscore, out_qual, tables_host, deltas_host,
+                                       status_out, devices, 1);
+}
+
+int kbbq_recalibrate_host_multi(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,
+                                const uint8_t *second, int64_t N, int L, int R, int minscore, uint8_t *out_qual,
+                                int64_t *tables_host, int64_t *deltas_host, int *status_out, const int *devices,
+                                int n_dev) {
+    if (N < 0 || L < 1 || R < 1 || R > 65535 || !devices || n_dev < 1 || n_dev > MAX_DEVICES) return KBBQ_E_ARG;
+    if (N > 0 && (!seq || !qual || !corr || !out_qual)) return KBBQ_E_ARG;
+    int ndev_visible = 0;
+    KBBQ_CUDA(cudaGetDeviceCount(&ndev_visible));
+    for (int i = 0; i < n_dev; ++i)
+        if (devices[i] < 0 || devices[i] >= ndev_visible) return KBBQ_E_ARG;
+
+    // can every device read every other device's tables?  (the same device listed twice trivially can)
+    bool p2p = n_dev > 1;
+    if (const char *e = getenv("KBBQ_MULTI_NO_P2P")) p2p = p2p && atoi(e) == 0;   // test hook: sum through the host
+    for (int i = 0; i < n_dev && p2p; ++i)
+        for (int j = 0; j < n_dev && p2p; ++j) {
+            if (devices[i] == devices[j]) continue;
+            int ok = 0;
+            if (cudaDeviceCanAccessPeer(&ok, devices[i], devices[j]) != cudaSuccess || !ok) p2p = false;
+        }
+    if (p2p)
+        for (int i = 0; i < n_dev; ++i) {
+            KBBQ_CUDA(cudaSetDevice(devices[i]));
+            for (int j = 0; j < n_dev; ++j) {
+                if (devices[i] == devices[j]) continue;
+                const cudaError_t e = cudaDeviceEnablePeerAccess(devices[j], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess) { cudaGetLastError(); p2p = false; }
+            }
+        }
+
+    std::vector<std::unique_lock<std::mutex>> locks;
+    for (int i = 0; i < n_dev; ++i) locks.emplace_back(g_cache[i].mu);
+    int hw = (int)std::thread::hardware_concurrency();
+    {
+        cpu_set_t set;
+        if (sched_getaffinity(0, sizeof(set), &set) == 0) hw = CPU_COUNT(&set);
+    }
+    const int host_threads = std::max(1, hw / n_dev);
+    const int64_t units = (N + 15) / 16;
+    std::vector<kbbq_session *> S((size_t)n_dev, nullptr);
+    std::vector<int64_t> lo((size_t)n_dev), hi((size_t)n_dev);
+    for (int i = 0; i < n_dev; ++i) {   // kbbq/parallel.py: shard_range -- contiguous, boundaries at multiples of 16 reads
+        lo[i] = std::min(N, units * i / n_dev * 16);
+        hi[i] = std::min(N, units * (i + 1) / n_dev * 16);
+    }
+    for (int i = 0; i < n_dev; ++i) {
+        const int64_t n = hi[i] - lo[i];
+        const int64_t C = std::min<int64_t>(default_chunk_reads(L), std::max<int64_t>(16, (n + 15) / 16 * 16));
+        size_t ours = 0;
+        for (int j = 0; j < n_dev; ++j)
+            if (g_cache[j].s && g_cache[j].s->device == devices[i]) ours += j == i ? g_cache[j].s->cap : 0;
+        KBBQ_TRY(cached_session(i, devices[i], L, R, minscore, C, resident_reads(devices[i], n, L, R, C, ours), host_threads, &S[i]));
+    }
+
+    std::vector<int> rcs((size_t)n_dev, KBBQ_OK), sts((size_t)n_dev, 0);
+    Barrier bar(n_dev);
+    std::vector<int64_t> h_sum;              // the sum through the host when the devices cannot reach each other
+    std::vector<std::vector<int64_t>> h_part;
+    if (n_dev > 1 && !p2p) { h_sum.assign(S[0]->ntab, 0); h_part.resize((size_t)n_dev); }
+    std::atomic<int> failed{0};
+
+    // Sum of the partial tables, called by every worker between its passes.  Each worker passes the same barriers
+    // whatever happened to it, so that a failure on one device cannot leave the others waiting.
+    auto sum_tables = [&](int i, int rc) -> int {
+        kbbq_session *self = S[i];
+        if (n_dev == 1) return rc;
+        // every session's tables complete ...
+        if (rc == KBBQ_OK && cudaStreamSynchronize(self->s_comp) != cudaSuccess) rc = KBBQ_E_CUDA;
+        if (rc == KBBQ_OK && !p2p) {
+            h_part[i].resize(self->ntab);
+            if (cudaMemcpy(h_part[i].data(), self->d_tab, self->ntab * 8, cudaMemcpyDeviceToHost) != cudaSuccess) rc = KBBQ_E_CUDA;
+        }
+        if (rc) failed.store(1);
+        bar.wait();
+        const bool go = !failed.load();
+        // ... then each device adds them all up for itself: identical integers everywhere, no broadcast
+        if (go && p2p) {
+            PeerTables p;
+            for (int j = 0; j < n_dev; ++j) p.src[j] = (const long long *)S[j]->d_tab;
+            int sms = KBBQ_SM_COUNT_FALLBACK;
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, self->device);
+            sum_tables_kernel<<<sms * 2, 256, 0, self->s_comp>>>(p, n_dev, (long long *)self->d_sum, self->ntab);
+            ++g_launches;
+            // a peer must not start its next run (which clears its tables) before this kernel has read them
+            if (cudaGetLastError() != cudaSuccess || cudaStreamSynchronize(self->s_comp) != cudaSuccess) rc = KBBQ_E_CUDA;
+        }
+        if (!p2p) {
+            if (go && i == 0)
+                for (int j = 0; j < n_dev; ++j)
+                    for (size_t e = 0; e < h_sum.size(); ++e) h_sum[e] += h_part[j][e];
+            bar.wait();
+            if (go && (cudaMemcpyAsync(self->d_sum, h_sum.data(), self->ntab * 8, cudaMemcpyHostToDevice, self->s_comp) != cudaSuccess ||
+                       cudaStreamSynchronize(self->s_comp) != cudaSuccess)) rc = KBBQ_E_CUDA;
+        }
+        self->summed = true;
+        if (rc) failed.store(1);
+        bar.wait();
+        if (rc == KBBQ_OK && failed.load()) rc = KBBQ_E_CUDA;   // another device failed: nothing to apply
+        return rc;
+    };
+    auto worker = [&](int i) {
+        kbbq_session *s = S[i];
+        const int64_t r0 = lo[i], n = hi[i] - lo[i];
+        const uint16_t *rg_i = rg ? rg + r0 : nullptr;
+        const uint8_t *sec_i = second ? second + r0 : nullptr;
+        int rc = cudaSetDevice(s->device) == cudaSuccess ? KBBQ_OK : KBBQ_E_CUDA;
+        if (rc == KBBQ_OK) rc = run_build_pass(s, seq + (size_t)r0 * L, qual + (size_t)r0 * L, corr + (size_t)r0 * L, rg_i, sec_i, n);
+        rc = sum_tables(i, rc);
+        if (rc == KBBQ_OK) rc = run_apply_pass(s, seq + (size_t)r0 * L, qual + (size_t)r0 * L, rg_i, sec_i, n, out_qual + (size_t)r0 * L);
+        if (rc == KBBQ_OK && i == 0) rc = fetch_results(s, tables_host, deltas_host);
+        const int rc2 = session_sync(s, &sts[i]);
+        rcs[i] = rc ? rc : rc2;
+    };
+    if (n_dev == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < n_dev; ++i) th.emplace_back(worker, i);
+        for (auto &t : th) t.join();
+    }
+    int st = 0, rc = KBBQ_OK;
+    for (int i = 0; i < n_dev; ++i) {
+        st |= sts[i];
+        if (rcs[i] && rcs[i] != KBBQ_E_DATA && rc == KBBQ_OK) rc = rcs[i];
+    }
+    if (status_out) *status_out = st;
+    if (rc) return rc;
+    return st ? KBBQ_E_DATA : KBBQ_OK;
+}
+
+}  // extern "C"

@@ -19,40 +19,38 @@
 
 namespace kbbq {
 
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 char g_last_cuda_error[256] = "";
 
-static std::once_flag g_const_once[64];
+// per-device __constant__ images of the model tables; a failed upload is retried by the next call
+static std::mutex g_const_mu;
+static bool g_const_done[64];
 
 static int upload_constants(int device) {
-    // per-device __constant__ images
-    int rc = KBBQ_OK;
-    auto up = [&]() -> int {
-        KBBQ_CUDA(cudaMemcpyToSymbol(c_lnp, KBBQ_LN_P, sizeof(double) * NQ));
-        KBBQ_CUDA(cudaMemcpyToSymbol(c_ln1mp, KBBQ_LN_1MP, sizeof(double) * NQ));
-        KBBQ_CUDA(cudaMemcpyToSymbol(c_prior, KBBQ_PRIOR, sizeof(double) * NQ));
-        KBBQ_CUDA(cudaMemcpyToSymbol(c_p, KBBQ_P, sizeof(double) * NQ));
-        KBBQ_CUDA(cudaMemcpyToSymbol(c_bound_hi, KBBQ_BOUND_HI, sizeof(double) * NQ));
-        KBBQ_CUDA(cudaMemcpyToSymbol(c_bound_lo, KBBQ_BOUND_LO, sizeof(double) * NQ));
-        return KBBQ_OK;
-    };
-    if (device < 0 || device >= 64) return up();
-    std::call_once(g_const_once[device], [&]() { rc = up(); });
-    return rc;
+    std::lock_guard<std::mutex> lock(g_const_mu);
+    if (device >= 0 && device < 64 && g_const_done[device]) return KBBQ_OK;
+    KBBQ_CUDA(cudaMemcpyToSymbol(c_lnp, KBBQ_LN_P, sizeof(double) * NQ));
+    KBBQ_CUDA(cudaMemcpyToSymbol(c_ln1mp, KBBQ_LN_1MP, sizeof(double) * NQ));
+    KBBQ_CUDA(cudaMemcpyToSymbol(c_prior, KBBQ_PRIOR, sizeof(double) * NQ));
+    KBBQ_CUDA(cudaMemcpyToSymbol(c_p, KBBQ_P, sizeof(double) * NQ));
+    KBBQ_CUDA(cudaMemcpyToSymbol(c_bound_hi, KBBQ_BOUND_HI, sizeof(double) * NQ));
+    KBBQ_CUDA(cudaMemcpyToSymbol(c_bound_lo, KBBQ_BOUND_LO, sizeof(double) * NQ));
+    if (device >= 0 && device < 64) g_const_done[device] = true;
+    return KBBQ_OK;
 }
 
 static int current_device_info(int *device, int *sms, int *max_smem) {
     KBBQ_CUDA(cudaGetDevice(device));
-    static int s_sms[64], s_smem[64];
-    if (*device < 64 && s_sms[*device]) {
-        *sms = s_sms[*device];
-        *max_smem = s_smem[*device];
+    static std::atomic<int> s_sms[64], s_smem[64];   // several host threads (one per device) come through here
+    if (*device < 64 && s_sms[*device].load()) {
+        *sms = s_sms[*device].load();
+        *max_smem = s_smem[*device].load();
         return KBBQ_OK;
     }
     KBBQ_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, *device));
     KBBQ_CUDA(cudaDeviceGetAttribute(max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, *device));
     if (*sms <= 0) *sms = KBBQ_SM_COUNT_FALLBACK;
-    if (*device < 64) { s_sms[*device] = *sms; s_smem[*device] = *max_smem; }
+    if (*device < 64) { s_smem[*device].store(*max_smem); s_sms[*device].store(*sms); }
     return KBBQ_OK;
 }
 
@@ -178,7 +176,7 @@ const char *kbbq_last_cuda_error(void) { return g_last_cuda_error; }
 
 int64_t kbbq_pos_table_elems(int L, int R) { return (int64_t)R * NQ * 2 * L; }
 int64_t kbbq_din_table_elems(int R) { return (int64_t)R * NQ * 16; }
-int64_t kbbq_launch_count(void) { return g_launches; }
+int64_t kbbq_launch_count(void) { return g_launches.load(); }
 
 int kbbq_plan_info(int L, int R, int minscore, int arrays, int max_smem, int *out) {
     if (!out || L < 1 || R < 1 || (arrays != 2 && arrays != 3)) return KBBQ_E_ARG;
@@ -703,47 +701,7 @@ __global__ void expand_corr_kernel(const uint8_t *seq, const uint32_t *bits, uin
     }
 }
 
-// Device memory and streams kbbq_recalibrate_host keeps between calls (per device): allocating
-// and freeing several GB per call costs from tens of milliseconds to a second (driver page
-// scrubbing), far more than the kernels.  Grown on demand, released by kbbq_host_release().
-struct HostArena {
-    std::mutex mu;
-    void *base = nullptr;
-    size_t cap = 0;
-    cudaStream_t copy = nullptr, comp = nullptr;
-    void *pinned = nullptr;   // page-locked staging for the mismatch bit map
-    size_t pinned_cap = 0;
-    int ensure_pinned(size_t bytes) {
-        if (bytes <= pinned_cap) return KBBQ_OK;
-        if (pinned) { KBBQ_CUDA(cudaFreeHost(pinned)); pinned = nullptr; pinned_cap = 0; }
-        KBBQ_CUDA(cudaHostAlloc(&pinned, bytes, cudaHostAllocDefault));
-        pinned_cap = bytes;
-        return KBBQ_OK;
-    }
-    int ensure(size_t bytes) {
-        if (bytes <= cap) return KBBQ_OK;
-        if (base) { KBBQ_CUDA(cudaFree(base)); base = nullptr; cap = 0; }
-        KBBQ_CUDA(cudaMalloc(&base, bytes));
-        cap = bytes;
-        return KBBQ_OK;
-    }
-    int streams() {
-        if (!copy) KBBQ_CUDA(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
-        if (!comp) KBBQ_CUDA(cudaStreamCreateWithFlags(&comp, cudaStreamNonBlocking));
-        return KBBQ_OK;
-    }
-    void release() {
-        if (base) cudaFree(base);
-        if (pinned) cudaFreeHost(pinned);
-        pinned = nullptr; pinned_cap = 0;
-        if (copy) cudaStreamDestroy(copy);
-        if (comp) cudaStreamDestroy(comp);
-        base = nullptr; cap = 0; copy = comp = nullptr;
-    }
-};
-HostArena g_arena[64];
-
-// bump allocator over the arena (first pass with base == nullptr measures)
+// bump allocator over one device allocation (first pass with base == nullptr measures)
 struct Carver {
     char *base;
     size_t off = 0;
@@ -755,39 +713,7 @@ struct Carver {
     }
 };
 
-struct Events {
-    std::vector<cudaEvent_t> ev;
-    ~Events() { for (auto e : ev) cudaEventDestroy(e); }
-    int make(cudaEvent_t *e) {
-        KBBQ_CUDA(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
-        ev.push_back(*e);
-        return KBBQ_OK;
-    }
-};
-
 #define KBBQ_TRY(x) do { int rc_ = (x); if (rc_) return rc_; } while (0)
-
-// Model step on device tables: marginals + deltas; layout of `model`:
-// [q_errs R*43 | q_total R*43 | rg_errs R | rg_total R | meanq R | rgdq R | qdq R*43 | posdq R*43*2L | dindq R*43*17]
-struct ModelPtrs {
-    int64_t *q_errs, *q_total, *rg_errs, *rg_total, *meanq, *rgdq, *qdq, *posdq, *dindq;
-    size_t elems;
-};
-ModelPtrs carve_model(int64_t *base, int L, int R) {
-    ModelPtrs m;
-    size_t o = 0;
-    m.q_errs = base + o; o += (size_t)R * NQ;
-    m.q_total = base + o; o += (size_t)R * NQ;
-    m.rg_errs = base + o; o += R;
-    m.rg_total = base + o; o += R;
-    m.meanq = base + o; o += R;
-    m.rgdq = base + o; o += R;
-    m.qdq = base + o; o += (size_t)R * NQ;
-    m.posdq = base + o; o += (size_t)R * NQ * 2 * L;
-    m.dindq = base + o; o += (size_t)R * NQ * 17;
-    m.elems = o;
-    return m;
-}
 
 }  // namespace
 
@@ -800,175 +726,6 @@ int kbbq_expand_mismatch_bits(const uint8_t *seq, const uint32_t *bits, int64_t 
     expand_corr_kernel<<<(unsigned)((n + 16 * 256 - 1) / (16 * 256)), 256, 0, (cudaStream_t)stream>>>(seq, bits, corr, n);
     KBBQ_LAUNCHED();
     return KBBQ_OK;
-}
-
-int kbbq_host_release(int device) {
-    if (device < 0 || device >= 64) return KBBQ_E_ARG;
-    HostArena &A = g_arena[device];
-    std::lock_guard<std::mutex> lock(A.mu);
-    if (A.base || A.copy || A.comp || A.pinned) {
-        KBBQ_CUDA(cudaSetDevice(device));
-        A.release();
-    }
-    return KBBQ_OK;
-}
-
-int kbbq_recalibrate_host(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,
-                          const uint8_t *second, int64_t N, int L, int R, int minscore, uint8_t *out_qual,
-                          int64_t *tables_host, int64_t *deltas_host, int *status_out, int device) {
-    if (N < 0 || L < 1 || R < 1 || R > 65535 || device < 0 || device >= 64) return KBBQ_E_ARG;
-    if (N > 0 && (!seq || !qual || !corr || !out_qual)) return KBBQ_E_ARG;
-    KBBQ_CUDA(cudaSetDevice(device));
-    HostArena &A = g_arena[device];
-    std::lock_guard<std::mutex> lock(A.mu);
-    KBBQ_TRY(A.streams());
-    cudaStream_t s_copy = A.copy, s_comp = A.comp;
-    Events E;
-
-    const size_t npos = (size_t)R * NQ * 2 * L, ndin = (size_t)R * NQ * 16;
-    const size_t ntab = 2 * npos + 2 * ndin;
-    const size_t nmodel = carve_model(nullptr, L, R).elems;
-
-    // chunking: whole batch resident when it fits, otherwise two passes through rotating buffers
-    size_t free_b = 0, total_b = 0;
-    KBBQ_CUDA(cudaMemGetInfo(&free_b, &total_b));
-    free_b += A.cap;  // what the arena already holds is ours to use
-    const size_t per_read_resident = (size_t)4 * L + 3;
-    bool resident = (double)N * per_read_resident < 0.8 * (double)free_b;
-    int64_t chunk = std::max<int64_t>(1, ((int64_t)256 << 20) / L);   // ~256 MiB per array per chunk
-    // test hooks: force small chunks / the two-pass streaming mode on small inputs
-    if (const char *e = getenv("KBBQ_HOST_CHUNK_READS")) chunk = std::max<int64_t>(16, atoll(e));
-    if (const char *e = getenv("KBBQ_HOST_FORCE_STREAMING")) resident = resident && atoi(e) == 0;
-    chunk = (chunk + 15) / 16 * 16;                                    // keep chunk starts 16-byte aligned
-    if (chunk > N) chunk = std::max<int64_t>(N, 1);
-    const int64_t nchunks = N ? (N + chunk - 1) / chunk : 0;
-    const int nbuf = resident ? 1 : 2;
-    const int64_t buf_reads = resident ? N : chunk;
-    size_t ws_bytes = 0;
-    KBBQ_TRY(kbbq_workspace_bytes(chunk, L, R, &ws_bytes));
-    // the corrected reads cross PCIe as a mismatch bit map made by the host cores (host_pack.cpp)
-    bool use_bits = true;
-    if (const char *e = getenv("KBBQ_HOST_NO_BITMAP")) use_bits = atoi(e) == 0;
-    const size_t bits_words = ((size_t)chunk * L + 31) / 32 + 4;   // per chunk
-    uint32_t *h_bits = nullptr;
-    if (use_bits && N > 0) {
-        KBBQ_TRY(A.ensure_pinned((size_t)nchunks * bits_words * 4));
-        h_bits = (uint32_t *)A.pinned;
-    }
-
-    // carve everything out of the arena: measure, grow if needed, carve for real
-    int64_t *d_tab = nullptr, *d_model = nullptr;
-    int *d_status = nullptr;
-    uint8_t *d_seq[2] = {}, *d_qual[2] = {}, *d_corr[2] = {}, *d_out[2] = {}, *d_sec[2] = {};
-    uint16_t *d_rg[2] = {};
-    uint32_t *d_bits[2] = {};
-    void *d_ws = nullptr;
-    for (int pass = 0; pass < 2; ++pass) {
-        Carver c(pass ? A.base : nullptr);
-        d_tab = c.take<int64_t>(ntab);
-        d_model = c.take<int64_t>(nmodel);
-        d_status = c.take<int>(64);
-        for (int b = 0; b < nbuf; ++b) {
-            d_seq[b] = c.take<uint8_t>((size_t)buf_reads * L + 16);
-            d_qual[b] = c.take<uint8_t>((size_t)buf_reads * L + 16);
-            d_rg[b] = rg ? c.take<uint16_t>((size_t)buf_reads + 8) : nullptr;
-            d_sec[b] = second ? c.take<uint8_t>((size_t)buf_reads + 16) : nullptr;
-        }
-        for (int b = 0; b < 2; ++b) {  // corrected reads and outputs always rotate through two chunk buffers
-            d_corr[b] = c.take<uint8_t>((size_t)chunk * L + 16);
-            d_out[b] = c.take<uint8_t>((size_t)chunk * L + 16);
-            d_bits[b] = use_bits ? c.take<uint32_t>(bits_words) : nullptr;
-        }
-        d_ws = c.take<uint8_t>(ws_bytes);
-        if (!pass) KBBQ_TRY(A.ensure(c.off));
-    }
-    ModelPtrs mp = carve_model(d_model, L, R);
-    KBBQ_CUDA(cudaMemsetAsync(d_tab, 0, ntab * 8, s_comp));
-    KBBQ_CUDA(cudaMemsetAsync(d_status, 0, sizeof(int), s_comp));
-    int64_t *pe = d_tab, *pt = pe + npos, *de = pt + npos, *dt = de + ndin;
-
-    std::vector<cudaEvent_t> copied(nchunks), consumed(nchunks);
-    for (int64_t k = 0; k < nchunks; ++k) { KBBQ_TRY(E.make(&copied[k])); KBBQ_TRY(E.make(&consumed[k])); }
-
-    auto rd = [&](int64_t k) { return std::min(chunk, N - k * chunk); };
-    // ---- pass 1: H2D + build ----
-    for (int64_t k = 0; k < nchunks; ++k) {
-        const int b = resident ? 0 : (int)(k & 1), cb = (int)(k & 1);
-        const int64_t r0 = k * chunk, n = rd(k);
-        const size_t doff = resident ? (size_t)r0 * L : 0, roff = resident ? (size_t)r0 : 0;
-        if (k >= 2) KBBQ_CUDA(cudaStreamWaitEvent(s_copy, consumed[k - 2], 0));
-        KBBQ_CUDA(cudaMemcpyAsync(d_seq[b] + doff, seq + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, s_copy));
-        KBBQ_CUDA(cudaMemcpyAsync(d_qual[b] + doff, qual + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, s_copy));
-        if (rg) KBBQ_CUDA(cudaMemcpyAsync(d_rg[b] + roff, rg + r0, (size_t)n * 2, cudaMemcpyHostToDevice, s_copy));
-        if (second) KBBQ_CUDA(cudaMemcpyAsync(d_sec[b] + roff, second + r0, (size_t)n, cudaMemcpyHostToDevice, s_copy));
-        if (use_bits) {
-            // the host cores compare while the copy engine is busy with seq and qual of this chunk
-            uint32_t *hb = h_bits + (size_t)k * bits_words;
-            KBBQ_TRY(kbbq_host_mismatch_bits(seq + (size_t)r0 * L, corr + (size_t)r0 * L, n * L, hb, 0));
-            KBBQ_CUDA(cudaMemcpyAsync(d_bits[cb], hb, (((size_t)n * L + 31) / 32) * 4, cudaMemcpyHostToDevice, s_copy));
-        } else {
-            KBBQ_CUDA(cudaMemcpyAsync(d_corr[cb], corr + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, s_copy));
-        }
-        KBBQ_CUDA(cudaEventRecord(copied[k], s_copy));
-        KBBQ_CUDA(cudaStreamWaitEvent(s_comp, copied[k], 0));
-        if (use_bits) {
-            const long long nb = (long long)n * L;
-            expand_corr_kernel<<<(unsigned)((nb + 16 * 256 - 1) / (16 * 256)), 256, 0, s_comp>>>(
-                d_seq[b] + doff, d_bits[cb], d_corr[cb], nb);
-            KBBQ_LAUNCHED();
-        }
-        KBBQ_TRY(kbbq_build(d_seq[b] + doff, d_qual[b] + doff, d_corr[cb], rg ? d_rg[b] + roff : nullptr,
-                            second ? d_sec[b] + roff : nullptr, n, L, R, minscore, pe, pt, de, dt, d_ws, ws_bytes,
-                            d_status, 0, s_comp));
-        KBBQ_CUDA(cudaEventRecord(consumed[k], s_comp));
-    }
-    // ---- model ----
-    KBBQ_TRY(kbbq_marginals(pe, pt, L, R, mp.q_errs, mp.q_total, mp.rg_errs, mp.rg_total, mp.meanq, s_comp));
-    KBBQ_TRY(kbbq_get_delta_qs(mp.meanq, mp.rg_errs, mp.rg_total, mp.q_errs, mp.q_total, pe, pt, de, dt, R, NQ,
-                               2 * L, 16, mp.rgdq, mp.qdq, mp.posdq, mp.dindq, s_comp));
-    if (tables_host) KBBQ_CUDA(cudaMemcpyAsync(tables_host, d_tab, ntab * 8, cudaMemcpyDeviceToHost, s_comp));
-    if (deltas_host)
-        KBBQ_CUDA(cudaMemcpyAsync(deltas_host, mp.meanq, ((size_t)2 * R + (size_t)R * NQ * (1 + 2 * L + 17)) * 8,
-                                  cudaMemcpyDeviceToHost, s_comp));
-    // ---- pass 2: (H2D) + apply + D2H ----
-    std::vector<cudaEvent_t> applied(nchunks), drained(nchunks), copied2(nchunks);
-    for (int64_t k = 0; k < nchunks; ++k) {
-        KBBQ_TRY(E.make(&applied[k])); KBBQ_TRY(E.make(&drained[k])); KBBQ_TRY(E.make(&copied2[k]));
-    }
-    cudaEvent_t model_done;
-    KBBQ_TRY(E.make(&model_done));
-    KBBQ_CUDA(cudaEventRecord(model_done, s_comp));
-    for (int64_t k = 0; k < nchunks; ++k) {
-        const int b = resident ? 0 : (int)(k & 1), ob = (int)(k & 1);
-        const int64_t r0 = k * chunk, n = rd(k);
-        const size_t doff = resident ? (size_t)r0 * L : 0, roff = resident ? (size_t)r0 : 0;
-        if (!resident) {
-            // the build pass finished with these buffers long ago; only the previous apply pass matters
-            if (k >= 2) KBBQ_CUDA(cudaStreamWaitEvent(s_copy, applied[k - 2], 0));
-            else KBBQ_CUDA(cudaStreamWaitEvent(s_copy, model_done, 0));
-            KBBQ_CUDA(cudaMemcpyAsync(d_seq[b], seq + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, s_copy));
-            KBBQ_CUDA(cudaMemcpyAsync(d_qual[b], qual + (size_t)r0 * L, (size_t)n * L, cudaMemcpyHostToDevice, s_copy));
-            if (rg) KBBQ_CUDA(cudaMemcpyAsync(d_rg[b], rg + r0, (size_t)n * 2, cudaMemcpyHostToDevice, s_copy));
-            if (second) KBBQ_CUDA(cudaMemcpyAsync(d_sec[b], second + r0, (size_t)n, cudaMemcpyHostToDevice, s_copy));
-            KBBQ_CUDA(cudaEventRecord(copied2[k], s_copy));
-            KBBQ_CUDA(cudaStreamWaitEvent(s_comp, copied2[k], 0));
-        }
-        if (k >= 2) KBBQ_CUDA(cudaStreamWaitEvent(s_comp, drained[k - 2], 0));
-        KBBQ_TRY(kbbq_apply(d_seq[b] + doff, d_qual[b] + doff, rg ? d_rg[b] + roff : nullptr,
-                            second ? d_sec[b] + roff : nullptr, n, L, R, minscore, mp.meanq, mp.rgdq, mp.qdq, mp.posdq,
-                            mp.dindq, NQ, 17, d_out[ob], d_ws, ws_bytes, d_status, 0, s_comp));
-        KBBQ_CUDA(cudaEventRecord(applied[k], s_comp));
-        // D2H on the copy stream so that it overlaps the next chunk's apply (and H2D when streaming)
-        KBBQ_CUDA(cudaStreamWaitEvent(s_copy, applied[k], 0));
-        KBBQ_CUDA(cudaMemcpyAsync(out_qual + (size_t)r0 * L, d_out[ob], (size_t)n * L, cudaMemcpyDeviceToHost, s_copy));
-        KBBQ_CUDA(cudaEventRecord(drained[k], s_copy));
-    }
-    int st_host = 0;
-    KBBQ_CUDA(cudaStreamSynchronize(s_copy));
-    KBBQ_CUDA(cudaMemcpyAsync(&st_host, d_status, sizeof(int), cudaMemcpyDeviceToHost, s_comp));
-    KBBQ_CUDA(cudaStreamSynchronize(s_comp));
-    if (status_out) *status_out = st_host;
-    return st_host ? KBBQ_E_DATA : KBBQ_OK;
 }
 
 int kbbq_build_host(const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,

@@ -33,7 +33,22 @@ SIGNATURES = {
     "kbbq_get_delta_qs": (_i, [_vp] * 9 + [_i, _i, _i, _i] + [_vp] * 4 + [_vp]),
     "kbbq_apply": (_i, [_vp] * 4 + [_i64, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, _vp, _sz, _vp, _i, _vp]),
     "kbbq_recalibrate_host": (_i, [_vp] * 5 + [_i64, _i, _i, _i] + [_vp] * 3 + [C.POINTER(_i), _i]),
+    "kbbq_recalibrate_host_multi": (_i, [_vp] * 5 + [_i64, _i, _i, _i] + [_vp] * 3 + [C.POINTER(_i), C.POINTER(_i), _i]),
     "kbbq_host_release": (_i, [_i]),
+    "kbbq_session_create": (_i, [_i, _i, _i, _i, _i64, _i64, _i, C.POINTER(_vp)]),
+    "kbbq_session_destroy": (None, [_vp]),
+    "kbbq_session_chunk_reads": (_i64, [_vp]),
+    "kbbq_session_reset": (_i, [_vp]),
+    "kbbq_session_build_chunk": (_i, [_vp] * 6 + [_i64, _i]),
+    "kbbq_session_tables": (_i, [_vp, _vp]),
+    "kbbq_session_set_tables": (_i, [_vp, _vp]),
+    "kbbq_session_tables_dev": (_i, [_vp, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp)]),
+    "kbbq_session_model": (_i, [_vp, _vp]),
+    "kbbq_session_apply_resident": (_i, [_vp, _i64, _vp]),
+    "kbbq_session_apply_chunk": (_i, [_vp] * 5 + [_i64, _vp]),
+    "kbbq_session_flush": (_i, [_vp]),
+    "kbbq_session_sync": (_i, [_vp, C.POINTER(_i)]),
+    "kbbq_session_traffic": (_i, [_vp, C.POINTER(_i64), C.POINTER(_i64)]),
     "kbbq_build_host": (_i, [_vp] * 5 + [_i64, _i, _i, _i] + [_vp] * 4 + [C.POINTER(_i), _i]),
     "kbbq_apply_host": (_i, [_vp] * 4 + [_i64, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, C.POINTER(_i), _i]),
     "kbbq_get_delta_qs_host": (_i, [_vp] * 9 + [_i, _i, _i, _i] + [_vp] * 4 + [_i]),
@@ -280,8 +295,23 @@ def apply_host(seq, qual, rg, second, L, R, meanq, rgdq, qdq, posdq, dindq, mins
     return out
 
 
-def recalibrate_host(seq, qual, corr, rg, second, L, R, minscore=6, want_tables=False, device=None, out=None):
-    """Whole path on host buffers; returns out_qual [N, L] u8 (and tables / deltas if asked)."""
+def device_list(devices=None):
+    """Devices of the whole-path entry points: an explicit list, else KBBQ_DEVICES ("0,1,2,3"), else [DEVICE]."""
+    if devices is None:
+        env = os.environ.get("KBBQ_DEVICES", "").strip()
+        devices = [int(x) for x in env.split(",") if x.strip() != ""] if env else [DEVICE]
+    elif isinstance(devices, int):
+        devices = [devices]
+    devices = [int(d) for d in devices]
+    if not devices:
+        raise ValueError("empty device list")
+    return devices
+
+
+def recalibrate_host(seq, qual, corr, rg, second, L, R, minscore=6, want_tables=False, device=None, out=None,
+                     devices=None):
+    """Whole path on host buffers; returns out_qual [N, L] u8 (and tables / deltas if asked).
+    devices: several GPUs of this box share the reads (kbbq_recalibrate_host_multi); the result is the same."""
     seq, qual, corr = u8(seq).ravel(), u8(qual).ravel(), u8(corr).ravel()
     N = seq.size // L
     rg = None if rg is None else np.ascontiguousarray(rg, dtype=np.uint16)
@@ -293,19 +323,118 @@ def recalibrate_host(seq, qual, corr, rg, second, L, R, minscore=6, want_tables=
         tables = np.zeros(2 * R * NQ * 2 * L + 2 * R * NQ * 16, np.int64)
         deltas = np.zeros(2 * R + R * NQ * (1 + 2 * L + 17), np.int64)
     st = C.c_int(0)
-    rc = lib().kbbq_recalibrate_host(ptr(seq), ptr(qual), ptr(corr), ptr(rg), ptr(second), N, L, R, minscore,
-                                     ptr(out), ptr(tables), ptr(deltas), C.byref(st),
-                                     DEVICE if device is None else device)
+    devs = device_list(devices if devices is not None else device)
+    dev_arr = (C.c_int * len(devs))(*devs)
+    rc = lib().kbbq_recalibrate_host_multi(ptr(seq), ptr(qual), ptr(corr), ptr(rg), ptr(second), N, L, R, minscore,
+                                           ptr(out), ptr(tables), ptr(deltas), C.byref(st), dev_arr, len(devs))
     check(rc, st.value)
     if not want_tables:
         return out
     npos, ndin = R * NQ * 2 * L, R * NQ * 16
     tabs = (tables[:npos].reshape(R, NQ, 2 * L), tables[npos:2 * npos].reshape(R, NQ, 2 * L),
             tables[2 * npos:2 * npos + ndin].reshape(R, NQ, 16), tables[2 * npos + ndin:].reshape(R, NQ, 16))
+    return out, tabs, split_deltas(deltas, L, R)
+
+
+def split_deltas(deltas, L, R):
+    """[meanq R | rgdq R | qdq R*43 | posdq R*43*2L | dindq R*43*17] -> the five arrays"""
+    npos = R * NQ * 2 * L
     o = 0
     meanq = deltas[o:o + R]; o += R
     rgdq = deltas[o:o + R]; o += R
     qdq = deltas[o:o + R * NQ].reshape(R, NQ); o += R * NQ
     posdq = deltas[o:o + npos].reshape(R, NQ, 2 * L); o += npos
     dindq = deltas[o:].reshape(R, NQ, 17)
-    return out, tabs, (meanq, rgdq, qdq, posdq, dindq)
+    return meanq, rgdq, qdq, posdq, dindq
+
+
+class Session:
+    """kbbq_session: the two passes of the path on one device, fed chunk by chunk from host arrays
+    (include/kbbq_b200.h).  resident_reads > 0 keeps that many reads in HBM between the passes."""
+
+    def __init__(self, L, R=1, minscore=6, chunk_reads=0, resident_reads=0, device=None, host_threads=0):
+        self.L, self.R = int(L), int(R)
+        self.device = DEVICE if device is None else int(device)
+        h = C.c_void_p()
+        check(lib().kbbq_session_create(self.device, self.L, self.R, minscore, chunk_reads, resident_reads,
+                                        host_threads, C.byref(h)))
+        self.h = h
+        self.chunk_reads = int(lib().kbbq_session_chunk_reads(h))
+        self.ntab = 2 * R * NQ * 2 * L + 2 * R * NQ * 16
+        self._keep = []   # output arrays still being written by the device
+
+    def close(self):
+        if self.h:
+            lib().kbbq_session_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def reset(self):
+        check(lib().kbbq_session_reset(self.h))
+
+    def build_chunk(self, seq, qual, corr, rg=None, second=None, keep=False):
+        seq, qual, corr = u8(seq).ravel(), u8(qual).ravel(), u8(corr).ravel()
+        n = seq.size // self.L
+        rg = None if rg is None else np.ascontiguousarray(rg, dtype=np.uint16)
+        second = None if second is None else u8(second)
+        check(lib().kbbq_session_build_chunk(self.h, ptr(seq), ptr(qual), ptr(corr), ptr(rg), ptr(second), n, int(keep)))
+
+    def tables(self):
+        t = np.zeros(self.ntab, np.int64)
+        check(lib().kbbq_session_tables(self.h, ptr(t)))
+        return t
+
+    def set_tables(self, t):
+        t = i64(t).ravel()
+        assert t.size == self.ntab
+        check(lib().kbbq_session_set_tables(self.h, ptr(t)))
+
+    def tables_dev(self):
+        """(device pointer, element count, cudaStream_t) of the session's table buffer"""
+        p, n, st = C.c_void_p(), C.c_int64(), C.c_void_p()
+        check(lib().kbbq_session_tables_dev(self.h, C.byref(p), C.byref(n), C.byref(st)))
+        return p.value, n.value, st.value
+
+    def flush(self):
+        check(lib().kbbq_session_flush(self.h))
+
+    def model(self, want_deltas=False):
+        d = np.zeros(2 * self.R + self.R * NQ * (1 + 2 * self.L + 17), np.int64) if want_deltas else None
+        check(lib().kbbq_session_model(self.h, ptr(d)))
+        return split_deltas(d, self.L, self.R) if want_deltas else None
+
+    def apply_resident(self, chunk, out):
+        assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"]
+        self._keep.append(out)
+        check(lib().kbbq_session_apply_resident(self.h, chunk, ptr(out)))
+
+    def apply_chunk(self, seq, qual, rg, second, out):
+        seq, qual = u8(seq).ravel(), u8(qual).ravel()
+        n = seq.size // self.L
+        rg = None if rg is None else np.ascontiguousarray(rg, dtype=np.uint16)
+        second = None if second is None else u8(second)
+        assert out.dtype == np.uint8 and out.flags["C_CONTIGUOUS"] and out.size >= n * self.L
+        self._keep.append(out)
+        check(lib().kbbq_session_apply_chunk(self.h, ptr(seq), ptr(qual), ptr(rg), ptr(second), n, ptr(out)))
+
+    def sync(self):
+        st = C.c_int(0)
+        rc = lib().kbbq_session_sync(self.h, C.byref(st))
+        self._keep = []
+        check(rc, st.value)
+
+    def traffic(self):
+        a, b = C.c_int64(), C.c_int64()
+        check(lib().kbbq_session_traffic(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value

@@ -62,6 +62,7 @@ class ReadBatch:
         self.N, self.L = seq.shape if seq.ndim == 2 else (0, 0)
         self.R = max(1, len(rg_keys))
         self.source = source
+        self.N_all = self.N   # reads of fastq[0] (>= N when the corrected file is shorter)
 
     @property
     def names(self):
@@ -72,7 +73,7 @@ class ReadBatch:
     @classmethod
     def from_fastq(cls, fastq, infer_rg_flag=False, need_corrected=True):
         reads = fastx.NativeFastq(fastq[0])
-        n = reads.N
+        n = n_all = reads.N
         corr = None
         if need_corrected:
             fixed = fastx.NativeFastq(fastq[1])
@@ -89,4 +90,6 @@ class ReadBatch:
                 raise ValueError("operands could not be broadcast together: corrected reads differ in length")
             corr, _ = fixed.pack(0, n)
             fixed.close()
-        return cls(None, seq, qual, corr, rg[:n], second[:n], keys, reads)
+        b = cls(None, seq, qual, corr, rg[:n], second[:n], keys, reads)
+        b.N_all = n_all
+        return b

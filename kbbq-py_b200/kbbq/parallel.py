@@ -31,3 +31,50 @@ def max_over_ranks(value, device, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+class _DevArray:
+    """A device buffer owned by the C library, viewed by torch without a copy (__cuda_array_interface__)."""
+
+    def __init__(self, ptr, n, typestr="<i8"):
+        self.__cuda_array_interface__ = {"shape": (int(n),), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2, "strides": None}
+
+
+def session_tables_tensor(session, device):
+    """The session's packed table buffer as an int64 torch tensor on `device` (no copy)."""
+    ptr, n, _ = session.tables_dev()
+    return torch.as_tensor(_DevArray(ptr, n), device=device)
+
+
+def recalibrate_host_distributed(seq, qual, corr, rg, second, L, R, out, session=None, group=None, device=None,
+                                 minscore=6):
+    """One rank's share of the whole path under torch.distributed (one process per GPU):
+    this rank's reads (host arrays, rg = global first-seen numbers) go through a session (pass 1), the partial
+    tables of all ranks are summed in place with ONE all-reduce (NCCL over NVLink on GPUs) on the session's own
+    table buffer, every rank recomputes the same deltas and applies them to its reads (pass 2) into `out`.
+    Returns the session (reusable for the next call with the same shape)."""
+    from . import _native
+    n = seq.shape[0] if seq.ndim == 2 else seq.size // L
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if session is None:
+        session = _native.Session(L, R, minscore, chunk_reads=0, resident_reads=max(n, 1), device=dev.index)
+    else:
+        session.reset()
+    C = session.chunk_reads
+    seq2, qual2, corr2 = seq.reshape(-1, L), qual.reshape(-1, L), corr.reshape(-1, L)
+    for lo in range(0, n, C):
+        hi = min(n, lo + C)
+        session.build_chunk(seq2[lo:hi], qual2[lo:hi], corr2[lo:hi], None if rg is None else rg[lo:hi],
+                            None if second is None else second[lo:hi], keep=True)
+    session.flush()                                # the partial tables are complete
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        t = session_tables_tensor(session, dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        torch.cuda.current_stream(dev).synchronize()
+    session.model()
+    out2 = out.reshape(-1, L)
+    for k, lo in enumerate(range(0, n, C)):
+        session.apply_resident(k, out2[lo:min(n, lo + C)])
+    session.sync()
+    return session

@@ -61,72 +61,91 @@ def _stdout_fd():
     return fd
 
 
-def _recalibrate_fastq_streamed(fastq, infer_rg, batch_reads):
-    """The two passes of kbbq/recalibrate.py:123-156 over batches of `batch_reads` reads: pass 1 packs a
-    batch from the indexed files, builds its tables on the GPU and adds them up (integer tables are
-    additive), the model runs once, pass 2 packs each batch again, applies and prints it.  Host memory
-    holds one batch (plus 8 bytes of index per read); the result is the one of the single-batch path."""
+def _recalibrate_fastq_streamed(fastq, infer_rg, batch_reads, devices=None):
+    """The two passes of kbbq/recalibrate.py:123-156 over batches of `batch_reads` reads through a session
+    (kbbq_session_*, csrc/host_api.cu): pass 1 packs a batch from the indexed files and hands it to the session,
+    which uploads it and adds it to the tables on the GPU while the next batch is being packed; the model runs
+    once; pass 2 packs each batch again, applies and prints it.  Host memory holds two batches (plus 8 bytes of
+    index per read); the result is the one of the single-batch path.  Pass 1 covers the reads both files have
+    (zip() in the reference stops at the shorter one), pass 2 every read of fastq[0] (kbbq/recalibrate.py:141)."""
     from . import fastx
     reads, fixed = fastx.NativeFastq(fastq[0]), fastx.NativeFastq(fastq[1])
-    n = min(reads.N, fixed.N)
-    reads.check_names(fixed, n)
-    if n == 0:
+    n_build = min(reads.N, fixed.N)
+    reads.check_names(fixed, n_build)
+    if reads.N == 0:
         return
-    if reads.L < 0 or fixed.L != reads.L:
+    if reads.L < 0 or (n_build and fixed.L != reads.L):
         raise ValueError("operands could not be broadcast together: reads of unequal length")
     rg, second, keys = reads.infer(infer_rg)
     L, R = reads.L, max(1, len(keys))
     from concurrent.futures import ThreadPoolExecutor
-    starts = list(range(0, n, batch_reads))
+    device = _native.device_list(devices)[0]
 
-    def pack(lo, with_corr):
-        m = min(batch_reads, n - lo)
+    def pack(lo, hi_total, with_corr):
+        m = min(batch_reads, hi_total - lo)
         seq, qual = reads.pack(lo, m)
         return lo, m, seq, qual, (fixed.pack(lo, m)[0] if with_corr else None)
 
-    def batches(with_corr):
+    def batches(total, with_corr):
         # the next batch is tokenised (native code, GIL released) while the GPU works on this one
+        starts = list(range(0, total, batch_reads))
+        if not starts:
+            return
         with ThreadPoolExecutor(1) as pool:
-            nxt = pool.submit(pack, starts[0], with_corr)
+            nxt = pool.submit(pack, starts[0], total, with_corr)
             for i in range(len(starts)):
                 cur = nxt.result()
                 if i + 1 < len(starts):
-                    nxt = pool.submit(pack, starts[i + 1], with_corr)
+                    nxt = pool.submit(pack, starts[i + 1], total, with_corr)
                 yield cur
 
-    tables = None
-    for lo, m, seq, qual, corr in batches(True):
-        part = _native.build_host(seq, qual, corr, rg[lo:lo + m], second[lo:lo + m], L, R, 6)
-        tables = part if tables is None else tuple(a + b for a, b in zip(tables, part))
-    fixed.close()
-    meanq, rg_e, rg_t, q_e, q_t = _native.marginals_host(tables[0], tables[1])
-    deltas = _native.get_delta_qs_host(meanq, rg_e, rg_t, q_e, q_t, *tables)
-    fd = _stdout_fd()
-    for lo, m, seq, qual, _ in batches(False):
-        out = _native.apply_host(seq, qual, rg[lo:lo + m], second[lo:lo + m], L, R, meanq, *deltas)
-        if fd is not None:
-            reads.write(fd, out, lo, m)
-        else:
-            txt = (out + np.uint8(33)).astype(np.uint8)
-            sys.stdout.write(''.join('@%s\n%s\n+\n%s\n' % (reads.name(lo + i), seq[i].tobytes().decode(),
-                                                          txt[i].tobytes().decode('latin-1')) for i in range(m)))
+    with _native.Session(L, R, 6, chunk_reads=batch_reads, resident_reads=0, device=device) as sess:
+        for lo, m, seq, qual, corr in batches(n_build, True):
+            sess.build_chunk(seq, qual, corr, rg[lo:lo + m], second[lo:lo + m])
+        fixed.close()
+        sess.model()
+        fd = _stdout_fd()
+        for lo, m, seq, qual, _ in batches(reads.N, False):
+            out = np.empty((m, L), np.uint8)
+            sess.apply_chunk(seq, qual, rg[lo:lo + m], second[lo:lo + m], out)
+            sess.sync()   # raises the reference's exception for bad input; `out` is complete
+            if fd is not None:
+                reads.write(fd, out, lo, m)
+            else:
+                txt = (out + np.uint8(33)).astype(np.uint8)
+                sys.stdout.write(''.join('@%s\n%s\n+\n%s\n' % (reads.name(lo + i), seq[i].tobytes().decode(),
+                                                              txt[i].tobytes().decode('latin-1')) for i in range(m)))
     reads.close()
 
 
-def recalibrate_fastq(fastq, infer_rg=False):
+def _fastq_size(path):
+    """Size of a regular file; 0 for anything else (pipes, process substitution)."""
+    import os
+    try:
+        return os.path.getsize(path) if os.path.isfile(path) else 0
+    except OSError:
+        return 0
+
+
+def recalibrate_fastq(fastq, infer_rg=False, devices=None):
     """Recalibrate fastq[0] given its corrected twin fastq[1]; FASTQ to stdout
-    (reference: kbbq/recalibrate.py:123-156: name without comment, sequence, '+', chr(q + 33))."""
+    (reference: kbbq/recalibrate.py:123-156: name without comment, sequence, '+', chr(q + 33)).
+    devices: GPUs of this box that share the reads (default: KBBQ_DEVICES, else one); the output is the same."""
     import os
     batch_reads = int(os.environ.get("KBBQ_BATCH_READS", "0"))
-    if batch_reads <= 0 and os.path.getsize(fastq[0]) > STREAM_ABOVE_BYTES:
+    if batch_reads <= 0 and _fastq_size(fastq[0]) > STREAM_ABOVE_BYTES:
         batch_reads = STREAM_BATCH_READS
     if batch_reads > 0:
-        return _recalibrate_fastq_streamed(fastq, infer_rg, batch_reads)
+        return _recalibrate_fastq_streamed(fastq, infer_rg, batch_reads, devices)
     batch = ReadBatch.from_fastq(fastq, infer_rg)
     if batch.N == 0:
         return
+    if batch.N_all != batch.N:
+        # fastq[0] holds more reads than the corrected file: the tables come from the pairs, every read is written
+        batch.source.close()
+        return _recalibrate_fastq_streamed(fastq, infer_rg, STREAM_BATCH_READS, devices)
     out = _native.recalibrate_host(batch.seq, batch.qual, batch.corr, batch.rg, batch.second,
-                                   batch.L, batch.R, 6)
+                                   batch.L, batch.R, 6, devices=devices)
     # native formatter straight to the stdout descriptor when there is one; text fallback otherwise
     # (e.g. sys.stdout replaced by an in-memory stream)
     w = sys.stdout
@@ -155,13 +174,13 @@ def recalibrate_bam(bam, use_oq=False, set_oq=False):
         Try converting your BAM to a FASTQ file with the samtools fastq command.')
 
 
-def recalibrate(bam, fastq, infer_rg=False, use_oq=False, set_oq=False, gatkreport=None):
-    """reference: kbbq/recalibrate.py:166-174."""
+def recalibrate(bam, fastq, infer_rg=False, use_oq=False, set_oq=False, gatkreport=None, devices=None):
+    """reference: kbbq/recalibrate.py:166-174 (devices: see recalibrate_fastq)."""
     if gatkreport is not None:
         raise NotImplementedError('GATKreport reading / creation is not yet supported.')
     elif bam is not None:
         recalibrate_bam(bam, use_oq, set_oq)
     elif fastq is not None:
-        recalibrate_fastq(fastq, infer_rg=infer_rg)
+        recalibrate_fastq(fastq, infer_rg=infer_rg, devices=devices)
     else:
         raise ValueError("A BAM or FASTQ file should be provided for recalibration.")
