@@ -54,9 +54,9 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
     const uint32_t din_base = pin(smem_addr(smem_raw + t.din_off) + (lane & (t.drep - 1)) * 4);
-    uint32_t abase[4], aeff[4];
+    uint32_t aeff[4];
 #pragma unroll
-    for (int b = 0; b < 4; ++b) aeff[b] = abase[b] = pos_base + m.cell[b];
+    for (int b = 0; b < 4; ++b) aeff[b] = pos_base + m.cell[b];
     uint32_t cur_flag = 1;
     const uint32_t selv = pin(m.selv), seln = pin(m.seln);
     const uint32_t rowsel = m.row >= 0 ? (uint32_t)m.row : 0u;
@@ -118,8 +118,11 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
         }
         if (UNI) {  // the row flag is fixed for the whole span
             const uint32_t f = (a.segmode ? ((sub & 1) ? 3u : 1u) : prmt(uni_flo, uni_fhi, rowsel)) & lanemask;
+            // moved by the difference to the last flag (as the work-list path does) and pinned: ptxas would otherwise
+            // keep the base addresses live, or redo a multiply-add per word, at the price of constant-bank reloads
+            const uint32_t delta = ((f >> 1) - (cur_flag >> 1)) * t.revoff;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) aeff[b] = abase[b] + (f >> 1) * t.revoff;
+            for (int b = 0; b < 4; ++b) aeff[b] = pin(aeff[b] + delta);
             cur_flag = f;
             live = f != 0;
         }
