@@ -499,14 +499,19 @@ def measure_e2e(args, wl, dev, world, rank, local, barrier, first_read):
                                                                out_np, session=state["s"], device=dev)
         api = ("kbbq.parallel.recalibrate_host_distributed (one kbbq_session per rank fed from pinned host buffers; "
                "ONE NCCL all-reduce on the sessions' table buffers)")
-    e2e_step()  # warm-up (allocations, first touch)
-    ke = max(1, min(args.steps, args.e2e_steps))
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(ke):
+    for _ in range(2):   # warm-up (allocations, first touch of the pinned buffers)
         e2e_step()
-    torch.cuda.synchronize()
-    dt = parallel.max_over_ranks(time.perf_counter() - t0, dev)
+    # every step timed on its own (wall clock around the blocking call, max over ranks); the figure reported is the
+    # MEDIAN step: on a freshly leased box the host side (page cache, memory bandwidth) is noisy for the first seconds
+    ke = max(3, args.e2e_steps)
+    times = []
+    for _ in range(ke):
+        barrier()
+        t0 = time.perf_counter()
+        e2e_step()
+        torch.cuda.synchronize()
+        times.append(parallel.max_over_ranks(time.perf_counter() - t0, dev))
+    dt = statistics.median(times) * ke
     # check against the device API on the same reads (tables summed over the ranks alike)
     rec = DeviceRecalibrator(L, R, max_reads=n, device=dev)
     rg_arg = rg if R > 1 else None
@@ -527,7 +532,7 @@ def measure_e2e(args, wl, dev, world, rank, local, barrier, first_read):
     ideal = h2d / (links["h2d_gbs_per_gpu"] * 1e9) + n * L / (links["d2h_gbs_per_gpu"] * 1e9)
     return {"value": world * n * L * ke / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": n * L,
             "host_input_bytes_per_step": 3 * n * L + n + (2 * n if R > 1 else 0), "ms_per_step": 1e3 * dt / ke,
-            "steps": ke, "reads_per_gpu": n, "api": api +
+            "steps": ke, "ms_all_steps": [1e3 * x for x in times], "statistic": "median step", "reads_per_gpu": n, "api": api +
             ("; corrected reads cross PCIe as a 1-bit mismatch map" if bits else "") +
             ("; chunks segmented by read group on the device" if R > 1 else ""),
             "link": links, "frac_of_link": ideal / (dt / ke),
@@ -874,7 +879,7 @@ def main():
                     help="HBM layout of the resident batch (auto: segmented with several read groups)")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--total-reads", type=int, default=200_000_000, help="--scaling strong: reads split over the GPUs")
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--e2e-reads", type=int, default=10_000_000, help="reads per GPU of the end-to-end measurement (pinned host memory: 6 B per base)")
     ap.add_argument("--fastq-reads", type=int, default=2_000_000)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

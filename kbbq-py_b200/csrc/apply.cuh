@@ -67,7 +67,7 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
     // how this thread's word is written back: whole (0), one aligned half (1, the usual partial
     // word: reads of even length start 2-byte aligned) or byte by byte (2)
     const bool half_lo = m.rowmask == 0x0000FFFFu, half_hi = m.rowmask == 0xFFFF0000u;
-    const uint32_t wmode = pin(m.rowmask == 0xFFFFFFFFu ? 0u : (half_lo || half_hi) ? 1u : 2u);
+    const bool st32 = m.rowmask == 0xFFFFFFFFu, st16 = half_lo || half_hi, st8 = !st32 && !st16 && m.rowmask != 0u;
     const uint32_t wshift = pin(half_hi ? 16u : 0u);
     unsigned long long outp = (unsigned long long)(a.out + m.toff + (half_hi ? 2 : 0));
     asm volatile("" : "+l"(outp));
@@ -137,29 +137,8 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
                 nlive = s_hi - first;
             }
             sdata = pin(sdata);
-#pragma unroll
-            for (int k = 0; k < KPS; ++k) {
-                uint32_t soff, hgrp;
-                if (UNI) {
-                    if (!live || (uint32_t)(m.grp + k * g.ng) >= nlive) continue;
-                    soff = k * kgrp;
-                    hgrp = first + m.grp + k * g.ng;
-                } else {
-                    uint32_t flo, fhi;
-                    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                 : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
-                                 : "r"(shdr + k * krec));
-                    // cycle-table addresses are kept for the last row flag seen (see build.cuh)
-                    const uint32_t flag = prmt(flo, fhi, rowsel) & lanemask;
-                    if (flag != cur_flag) {
-                        if (!flag) continue;
-                        const uint32_t delta = ((flag >> 1) - (cur_flag >> 1)) * revoff;
-#pragma unroll
-                        for (int b = 0; b < 4; ++b) aeff[b] += delta;
-                        cur_flag = flag;
-                    }
-                }
-                const uint32_t wa = sdata + soff;
+            // one (row, word) of one group: four qualities of one read
+            auto apply_word = [&](const uint32_t wa, const uint32_t hgrp) {
                 uint32_t sw, qw, pb;
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sw) : "r"(wa));
                 asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qw) : "r"(wa + abytes));
@@ -194,15 +173,45 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
                 const uint32_t res = (sum4 & vm8) | (qw & ~vm8);
                 // group base + this thread's offset inside the group (64-bit multiply-add, one instruction)
                 const unsigned long long dst = outp + (unsigned long long)hgrp * gbytes;
-                if (wmode == 0) {
-                    asm volatile("st.global.u32 [%0], %1;" ::"l"(dst), "r"(res) : "memory");
-                } else if (wmode == 1) {
-                    asm volatile("st.global.u16 [%0], %1;" ::"l"(dst), "h"((unsigned short)(res >> wshift)) : "memory");
-                } else {
+                // three independent, predicated stores (the mode is a per-thread constant; no branch in the usual cases)
+                if (st32) asm volatile("st.global.u32 [%0], %1;" ::"l"(dst), "r"(res) : "memory");
+                if (st16) asm volatile("st.global.u16 [%0], %1;" ::"l"(dst), "h"((unsigned short)(res >> wshift)) : "memory");
+                if (st8) {
 #pragma unroll
                     for (int b = 0; b < 4; ++b)
                         if ((rowmask >> (8 * b)) & 1u)
                             asm volatile("st.global.u8 [%0], %1;" ::"l"(dst + b), "r"(res >> (8 * b)) : "memory");
+                }
+            };
+            if (UNI && nlive >= sl.ngs) {
+                // a full stage of a uniform batch, the usual case: no per-word predicates (padding lanes own no byte
+                // and store nothing)
+#pragma unroll
+                for (int k = 0; k < KPS; ++k) apply_word(sdata + k * kgrp, first + m.grp + k * g.ng);
+            } else {
+#pragma unroll
+                for (int k = 0; k < KPS; ++k) {
+                    uint32_t soff, hgrp;
+                    if (UNI) {
+                        if (!live || (uint32_t)(m.grp + k * g.ng) >= nlive) continue;
+                        soff = k * kgrp;
+                        hgrp = first + m.grp + k * g.ng;
+                    } else {
+                        uint32_t flo, fhi;
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                     : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
+                                     : "r"(shdr + k * krec));
+                        // cycle-table addresses are kept for the last row flag seen (see build.cuh)
+                        const uint32_t flag = prmt(flo, fhi, rowsel) & lanemask;
+                        if (flag != cur_flag) {
+                            if (!flag) continue;
+                            const uint32_t delta = ((flag >> 1) - (cur_flag >> 1)) * revoff;
+#pragma unroll
+                            for (int b = 0; b < 4; ++b) aeff[b] += delta;
+                            cur_flag = flag;
+                        }
+                    }
+                    apply_word(sdata + soff, hgrp);
                 }
             }
             __syncwarp();

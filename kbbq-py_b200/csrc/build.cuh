@@ -63,6 +63,7 @@ struct TableCfg {
     uint32_t cyc16[2];  // {rs, rs << 16}: with the row-index word as b this is (byte 0 or 2) * rs, (byte 1 or 3) * rs
     uint32_t din16;     // (2 * drep) | dq << 16: b = (2 * slot, row) byte pairs -> slot * drep * 4 + row * dq
     uint32_t ohe[4];    // 255 << 8b: IDP.4A with the mismatch byte mask 0xFF -> 65025
+    uint32_t val16[2];  // {1 | 16 << 16, 256 | 4096 << 16}: packs the 3-bit codes of four bases into four selector nibbles
 };
 
 inline bool make_table_cfg(const Geom &g, int kps, int drep, TableCfg *t) {
@@ -87,6 +88,8 @@ inline bool make_table_cfg(const Geom &g, int kps, int drep, TableCfg *t) {
     t->cyc16[1] = (uint32_t)t->rs << 16;
     t->din16 = (uint32_t)(drep * 2) | ((uint32_t)t->dq << 16);
     for (int b = 0; b < 4; ++b) t->ohe[b] = 255u << (8 * b);
+    t->val16[0] = 1u | (16u << 16);
+    t->val16[1] = 256u | (4096u << 16);
     return true;
 }
 
@@ -160,6 +163,12 @@ __device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, int sj) {
     m.rowmask = 0; m.toff = 0; m.selv = 0x4444u; m.seln = 0x4444u;
 #pragma unroll
     for (int b = 0; b < 4; ++b) { m.cell[b] = 0; m.cyc[b] = -1; }
+    if (m.row < 0) {
+        // padding lanes run along in full stages with nothing selected (trash rows only): spread them over the banks
+        // of the trash row instead of letting them collide on one cell
+#pragma unroll
+        for (int b = 0; b < 4; ++b) m.cell[b] = 4u * (uint32_t)(((tid & 31) + 32 * b) % (4 * sj));
+    }
     if (m.row >= 0) {
         const int a = (m.row * g.L) & 3;
         m.toff = m.row * g.L - a + 4 * w;
@@ -171,7 +180,11 @@ __device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, int sj) {
                 m.rowmask |= 0xFFu << (8 * b);
                 m.selv = (m.selv & ~(0xFu << (4 * b))) | ((8u | b) << (4 * b));
                 if (c != 0) m.seln = (m.seln & ~(0xFu << (4 * b))) | ((8u | b) << (4 * b));
+#ifdef KBBQ_EXPERIMENT_NOCONFLICT
+                m.cell[b] = 4u * ((tid & 31) + 32 * b);  // timing experiment only: every lane its own bank (wrong tables)
+#else
                 m.cell[b] = 4u * ((c & 3) * sj + (c >> 2));
+#endif
             }
         }
     }
@@ -260,7 +273,7 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
     const uint32_t data0 = pin(smem_u32(smem_raw + sl.data_off) + m.toff + (UNI ? m.grp * g.gbytes : 0));
     const uint32_t hdr0 = pin(smem_u32(smem_raw + sl.hdr_off) + m.grp * 16);
     const uint32_t kgrp = g.ng * g.gbytes;
-    const uint32_t stage_bytes = pin(sl.narr * sl.abytes), abytes = pin(sl.abytes), hdr_stride = sl.ngs * 16, krec = g.ng * 16;
+    const uint32_t stage_bytes = pin(sl.narr * sl.abytes), abytes = pin(sl.abytes), abytes2 = pin(2 * sl.abytes), hdr_stride = sl.ngs * 16, krec = g.ng * 16;
     const uint32_t nstages = pin(sl.stages), ngs = pin(sl.ngs);
     const uint32_t revoff = t.revoff, addq = t.addq;
     const uint32_t one = pin(1u), lut_acgt = pin(0x47544341u);  // 'A' 'C' 'T' 'G' by 2-bit code
@@ -329,35 +342,12 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
                     nlive = s_hi - first;  // groups in this stage (>= ngs except in the last one)
                 }
                 sdata = pin(sdata);
-#pragma unroll
-                for (int k = 0; k < KPS; ++k) {
-                    uint32_t soff;
-                    if (UNI) {
-                        if (!live || (uint32_t)(m.grp + k * g.ng) >= nlive) continue;
-                        soff = k * kgrp;
-                    } else {
-                        // this thread-group's k-th record of the stage
-                        uint32_t hgrp, flo, fhi;
-                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                     : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
-                                     : "r"(shdr + k * krec));
-                        // flag byte of this thread's row: 0 = not in this segment (or a padding lane), 1 = read 1,
-                        // 3 = read 2.  A row usually keeps its flag from group to group, so the cycle-table
-                        // addresses are kept ready for the last flag seen and only re-based when it changes.
-                        const uint32_t flag = prmt(flo, fhi, rowsel) & lanemask;
-                        if (flag != cur_flag) {
-                            if (!flag) continue;
-                            const uint32_t delta = ((flag >> 1) - (cur_flag >> 1)) * revoff;
-#pragma unroll
-                            for (int b = 0; b < 4; ++b) aeff[b] += delta;
-                            cur_flag = flag;
-                        }
-                    }
-                    const uint32_t wa = sdata + soff;
+                // one (row, word) of one group: four bases of one read
+                auto tally_word = [&](const uint32_t wa) {
                     uint32_t sw, qw, cw, pb;
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(sw) : "r"(wa));
                     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(qw) : "r"(wa + abytes));
-                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(wa + 2 * abytes));
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(cw) : "r"(wa + abytes2));
                     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pb) : "r"(wa - 1));
 
                     // ---- quality -> row index, byte-parallel ----
@@ -381,11 +371,12 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
                     const uint32_t e8 = prmt((sw ^ cw) + 0x7F7F7F7Fu, 0u, 0xBA98u);
 
                     if (VALIDATE) {
-                        // rebuild each byte from its 3-bit code with an 8-entry byte LUT; any difference = bad base
+                        // rebuild each byte from its 3-bit code (bits 1-3) with an 8-entry byte LUT; any difference = bad
+                        // base.  The four codes are gathered into the selector nibbles by two 16-bit x 8-bit dot products
+                        // (weights 1, 16 and 256, 4096) on the FMA pipe instead of shift / or / permute on the ALU pipe.
                         const uint32_t code3 = (sw >> 1) & 0x07070707u;
-                        const uint32_t y = code3 | (code3 >> 4);
-                        const uint32_t sel = __byte_perm(y, 0, 0x4420);
-                        const uint32_t recon = __byte_perm(lut_acgt, 0x4E000000u /* . . . N */, sel);
+                        const uint32_t sel = __dp2a_hi(t.val16[1], code3, __dp2a_lo(t.val16[0], code3, 0u));
+                        const uint32_t recon = prmt(lut_acgt, 0x4E000000u /* . . . N */, sel);  // raw PRMT: __byte_perm would mask the selector
                         bbad |= recon ^ sw;  // foreign bytes are masked off at the end (ownership is per byte position)
                     }
 
@@ -397,6 +388,39 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
                         const uint32_t da = (b & 1) ? __dp2a_hi(t.din16, xb, din_base) : __dp2a_lo(t.din16, xb, din_base);
                         red_shared_add(pa, inc);
                         red_shared_add(da, inc);
+                    }
+                };
+                if (UNI && nlive >= sl.ngs) {
+                    // a full stage of a uniform batch, the usual case: no per-word predicates, no divergence.  The
+                    // padding lanes of the last warp run along on group 0 with nothing selected: trash rows only.
+#pragma unroll
+                    for (int k = 0; k < KPS; ++k) tally_word(sdata + k * kgrp);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < KPS; ++k) {
+                        uint32_t soff;
+                        if (UNI) {
+                            if (!live || (uint32_t)(m.grp + k * g.ng) >= nlive) continue;
+                            soff = k * kgrp;
+                        } else {
+                            // this thread-group's k-th record of the stage
+                            uint32_t hgrp, flo, fhi;
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
+                                         : "r"(shdr + k * krec));
+                            // flag byte of this thread's row: 0 = not in this segment (or a padding lane), 1 = read 1,
+                            // 3 = read 2.  A row usually keeps its flag from group to group, so the cycle-table
+                            // addresses are kept ready for the last flag seen and only re-based when it changes.
+                            const uint32_t flag = prmt(flo, fhi, rowsel) & lanemask;
+                            if (flag != cur_flag) {
+                                if (!flag) continue;
+                                const uint32_t delta = ((flag >> 1) - (cur_flag >> 1)) * revoff;
+#pragma unroll
+                                for (int b = 0; b < 4; ++b) aeff[b] += delta;
+                                cur_flag = flag;
+                            }
+                        }
+                        tally_word(sdata + soff);
                     }
                 }
                 __syncwarp();

@@ -17,7 +17,10 @@
 namespace kbbq {
 
 constexpr int NQ = KBBQ_NQ;            // 43 quality rows (0..42)
-constexpr int MAX_THREADS = 1024;
+#ifndef KBBQ_CTA_THREADS
+#define KBBQ_CTA_THREADS 1024
+#endif
+constexpr int MAX_THREADS = KBBQ_CTA_THREADS;  // consumer + producer threads of a hot-kernel CTA (64 registers per thread at 1024)
 constexpr uint32_t H4 = 0x80808080u;   // high bit of every byte
 constexpr uint32_t ONE4 = 0x01010101u;
 

@@ -18,6 +18,7 @@
 // the device-pointer entry points of kbbq_b200.cu.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <memory>
 #include <mutex>
@@ -726,17 +727,29 @@ int kbbq_recalibrate_host_multi(const uint8_t *seq, const uint8_t *qual, const u
         if (rc == KBBQ_OK && failed.load()) rc = KBBQ_E_CUDA;   // another device failed: nothing to apply
         return rc;
     };
+    const bool trace = !env_flag_off("KBBQ_HOST_TRACE");   // where a call spends its time (stderr, device 0's worker)
+    const auto t_start = std::chrono::steady_clock::now();
+    auto stamp = [&](int i, const char *what) {
+        if (trace && i == 0)
+            fprintf(stderr, "[kbbq host] %-28s %8.2f ms\n", what,
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    };
     auto worker = [&](int i) {
         kbbq_session *s = S[i];
         const int64_t r0 = lo[i], n = hi[i] - lo[i];
         const uint16_t *rg_i = rg ? rg + r0 : nullptr;
         const uint8_t *sec_i = second ? second + r0 : nullptr;
         int rc = cudaSetDevice(s->device) == cudaSuccess ? KBBQ_OK : KBBQ_E_CUDA;
+        stamp(i, "sessions ready");
         if (rc == KBBQ_OK) rc = run_build_pass(s, seq + (size_t)r0 * L, qual + (size_t)r0 * L, corr + (size_t)r0 * L, rg_i, sec_i, n);
+        stamp(i, "build pass enqueued");
+        if (trace) { cudaStreamSynchronize(s->s_comp); stamp(i, "build pass done"); }
         rc = sum_tables(i, rc);
         if (rc == KBBQ_OK) rc = run_apply_pass(s, seq + (size_t)r0 * L, qual + (size_t)r0 * L, rg_i, sec_i, n, out_qual + (size_t)r0 * L);
+        stamp(i, "apply pass enqueued");
         if (rc == KBBQ_OK && i == 0) rc = fetch_results(s, tables_host, deltas_host);
         const int rc2 = session_sync(s, &sts[i]);
+        stamp(i, "all done");
         rcs[i] = rc ? rc : rc2;
     };
     if (n_dev == 1) {
