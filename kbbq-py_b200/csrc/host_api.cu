@@ -155,6 +155,23 @@ bool env_flag_off(const char *name) {   // unset or "0"
     return !e || atoi(e) == 0;
 }
 
+int usable_cpus() {
+    cpu_set_t set;
+    if (sched_getaffinity(0, sizeof(set), &set) == 0) return std::max(1, CPU_COUNT(&set));
+    return std::max(1, (int)std::thread::hardware_concurrency());
+}
+
+// The corrected reads cross PCIe as a 1-bit-per-base mismatch map made by the host cores (host_pack.cpp) when this
+// session has the cores for it: the comparison reads 2 B per base of host memory, and with fewer than 8 threads (an
+// 8-GPU box shares 32 cores, and its host memory, between 8 sessions) it takes longer than the bytes it saves
+// (B200 x 8: 389 ms per step with the map, 343 ms with the corrected reads as they are; 4 GPUs, 8 threads each: map).
+// KBBQ_HOST_NO_BITMAP=1 / KBBQ_HOST_BITMAP=1 force either.
+bool want_bitmap(int host_threads) {
+    if (!env_flag_off("KBBQ_HOST_NO_BITMAP")) return false;
+    if (!env_flag_off("KBBQ_HOST_BITMAP")) return true;
+    return (host_threads > 0 ? host_threads : usable_cpus()) >= 8;
+}
+
 // several read groups: chunks are rewritten into the segmented layout on the device (segment.cuh) unless the
 // shape has no shared-memory plan or the padding (32 R rows per chunk) would rival the chunk itself
 bool want_segmode(int L, int R, int minscore, int64_t C) {
@@ -169,7 +186,7 @@ int session_create(int device, int L, int R, int minscore, int64_t C, int64_t M,
     S->C = (C + 15) / 16 * 16;
     S->M = M;
     S->host_threads = host_threads;
-    S->use_bits = env_flag_off("KBBQ_HOST_NO_BITMAP");
+    S->use_bits = want_bitmap(host_threads);
     S->segmode = want_segmode(L, R, minscore, S->C);
     S->rowsC = S->segmode ? kbbq_segment_rows_bound(S->C, R) : S->C;
     KBBQ_CUDA(cudaStreamCreateWithFlags(&S->s_up, cudaStreamNonBlocking));
@@ -421,7 +438,7 @@ int cached_session(int slot, int device, int L, int R, int minscore, int64_t C, 
     const int64_t C16 = (C + 15) / 16 * 16;
     const int64_t nres = M ? (M + C16 - 1) / C16 : 0;
     if (s && s->device == device && s->L == L && s->R == R && s->minscore == minscore && s->C == C16 &&
-        (int64_t)s->res.size() >= nres && (nres > 0) == (s->M > 0) && s->use_bits == env_flag_off("KBBQ_HOST_NO_BITMAP") &&
+        (int64_t)s->res.size() >= nres && (nres > 0) == (s->M > 0) && s->use_bits == want_bitmap(host_threads) &&
         s->segmode == want_segmode(L, R, minscore, C16)) {
         s->host_threads = host_threads;
         KBBQ_TRY(session_reset(s));
@@ -659,12 +676,7 @@ int kbbq_recalibrate_host_multi(const uint8_t *seq, const uint8_t *qual, const u
 
     std::vector<std::unique_lock<std::mutex>> locks;
     for (int i = 0; i < n_dev; ++i) locks.emplace_back(g_cache[i].mu);
-    int hw = (int)std::thread::hardware_concurrency();
-    {
-        cpu_set_t set;
-        if (sched_getaffinity(0, sizeof(set), &set) == 0) hw = CPU_COUNT(&set);
-    }
-    const int host_threads = std::max(1, hw / n_dev);
+    const int host_threads = std::max(1, usable_cpus() / n_dev);
     const int64_t units = (N + 15) / 16;
     std::vector<kbbq_session *> S((size_t)n_dev, nullptr);
     std::vector<int64_t> lo((size_t)n_dev), hi((size_t)n_dev);

@@ -104,11 +104,28 @@ __global__ void marginals_rg_kernel(const long long *q_errs, const long long *q_
     meanq[rg] = mq;  // t == 0: nan -> int -> clip gives 0 in the reference
 }
 
+// s = hi + lo exactly (two_sum).  The value an x87 extended-precision add returns for it: rounded to a 64-bit
+// significand, ties to even, as a canonical (hi, lo) pair (hi = nearest double, lo = the rest), so that equal
+// fp80 values give equal pairs and a lexicographic compare orders them as the fp80 values.
+__device__ __forceinline__ dd round_to_x87(dd s) {
+    if (s.lo == 0.0 || isinf(s.hi) || isnan(s.hi)) return s;
+    int e;
+    frexp(s.hi, &e);
+    int eh = e - 1;  // floor(log2 |hi|)
+    // hi a power of two and lo of the other sign: the sum lies in the binade below, with half the quantum
+    if (fabs(s.hi) == ldexp(1.0, eh) && ((s.hi > 0.0) != (s.lo > 0.0))) eh -= 1;
+    const int qe = eh - 63;  // exponent of the last of 64 significand bits
+    // hi is a multiple of 2^11 quanta (even), so rounding the sum is rounding lo; rint = round half to even
+    const double lo_r = ldexp(rint(ldexp(s.lo, -qe)), qe);
+    const double h = __dadd_rn(s.hi, lo_r);
+    return {h, __dadd_rn(__dsub_rn(s.hi, h), lo_r)};
+}
+
 // ---- gatk_delta_q -------------------------------------------------------------------------------
 // posterior[c] = prior_dist[|c - prior|] + ((errs+1) ln p_c + (tot+1-errs) log1p(-p_c)); the
-// reference adds the fp64 log-likelihood to an x87 long-double prior, i.e. the sum is rounded to
-// 64 bits; here the sum is kept exact as (hi, lo) and compared lexicographically.  First maximum
-// wins (np.argmax).
+// reference adds the fp64 log-likelihood to an x87 long-double prior (kbbq/compare_reads.py:257-258), i.e.
+// the sum is rounded to a 64-bit significand: the exact sum (two_sum) is rounded the same way and the
+// candidates compared on that value.  First maximum wins (np.argmax).
 // `prior` is an integer quality, or (PRIOR = double: the read-group row of a recalibration report,
 // kbbq/gatk/bqsr.py:293-297) a real one: the reference truncates candidate - prior towards zero
 // before taking the absolute value (kbbq/compare_reads.py:245).  Returns the MAP candidate.
@@ -127,7 +144,7 @@ __device__ __forceinline__ int posterior_q_cell(PRIOR prior, long long errs, lon
         const double ll = __dadd_rn(a, b);
         double h, l;
         if (isinf(pr) || isinf(ll)) { h = -KBBQ_INF; l = 0.0; }
-        else { dd s = two_sum(pr, ll); h = s.hi; l = s.lo; }
+        else { dd s = round_to_x87(two_sum(pr, ll)); h = s.hi; l = s.lo; }
         if (!have || h > bh || (h == bh && l > bl)) { best = c; bh = h; bl = l; have = true; }
     }
     return best;

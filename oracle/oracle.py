@@ -109,6 +109,33 @@ def gatk_delta_q(prior_q, numerrs, numtotal):
     return out
 
 
+def delta_q_top2_gap(prior_q, numerrs, numtotal):
+    """Relative gap between the two best posteriors of every cell (long double): how close to a tie."""
+    prior_q, numerrs, numtotal = _i64(prior_q), _i64(numerrs), _i64(numtotal)
+    out = np.zeros(prior_q.shape, np.float64)
+    lib().oracle_delta_q_top2_gap(_p(prior_q), _p(numerrs), _p(numtotal), C.c_int64(prior_q.size), _p(out))
+    return out
+
+
+def near_tie_cells(n, seed, log10_lo=3.0, log10_hi=11.0):
+    """Cells of gatk_delta_q whose two best candidates are as close as integer counts allow: for a random prior, a
+    random adjacent candidate pair (c, c + 1) and a random failure count m, the error count that balances the two
+    posteriors.  -> (prior, errs, total).  A blind random grid never comes near a tie; these do (with m >= 1e10 a
+    few per million are exact ties of the 64-bit-significand sums)."""
+    _, lnp, ln1mp, prior = constants()
+    rng = np.random.default_rng(seed)
+    pq = rng.integers(0, 43, n)
+    c = rng.integers(1, 42, n)
+    m = (10 ** rng.uniform(log10_lo, log10_hi, n)).astype(np.int64)
+    d1, d2 = np.abs(c - pq), np.abs(c + 1 - pq)
+    ok = (d1 < 19) & (d2 < 19)   # both priors finite
+    pq, c, m, d1, d2 = pq[ok], c[ok], m[ok], d1[ok], d2[ok]
+    k = np.rint(-((prior[d1] - prior[d2]) + m * (ln1mp[c] - ln1mp[c + 1])) / (lnp[c] - lnp[c + 1])).astype(np.int64)
+    ok = k >= 1
+    pq, m, k = pq[ok], m[ok], k[ok]
+    return pq, k - 1, m + k - 2
+
+
 def get_delta_qs(meanq, rg_errs, rg_total, q_errs, q_total, pos_errs, pos_total, din_errs, din_total):
     R, _, L2 = pos_total.shape
     rgdq = np.zeros(R, np.int64)

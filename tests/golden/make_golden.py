@@ -105,6 +105,46 @@ def make_case(name, N, L, R, seed, paired=True, infer_rg=True, p_n=0.01, p_err=0
           "changed", float((outq != qual).mean()))
 
 
+def make_synth_case(name, seed, N, L, R):
+    """BASELINE-shaped case: the reads come from kbbq.synth (the numpy twin of the device generator bench.py and the
+    GPU tests use), so the .npz only keeps (seed, N, L, R), a digest of the inputs, the first-seen read-group
+    numbers and the reference's outputs; tests regenerate the same bytes."""
+    import hashlib
+    import importlib.util   # by path: the name `kbbq` is taken by the reference package here
+    spec = importlib.util.spec_from_file_location("kbbq_b200_synth", os.path.join(ROOT, "kbbq-py_b200", "kbbq", "synth.py"))
+    synth = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(synth)
+    seq, qual, corr, rgk, second = synth.synth_reads(seed, 0, N, L, R)
+    infer_rg = R > 1
+    names = ["r%d/%d" % (i // 2, second[i] + 1) + ("_RG:Z:g%d" % rgk[i] if infer_rg else "") for i in range(N)]
+    seen = {}
+    rg = np.array([seen.setdefault(int(k), len(seen)) for k in rgk], dtype=np.uint16) if infer_rg else np.zeros(N, np.uint16)
+    nrg = max(1, len(seen))
+    with tempfile.TemporaryDirectory() as td:
+        fu, fc = os.path.join(td, "u.fq"), os.path.join(td, "c.fq")
+        with open(fu, "w") as hu, open(fc, "w") as hc:
+            for i in range(N):
+                q = (qual[i] + 33).tobytes().decode()
+                hu.write("@%s\n%s\n+\n%s\n" % (names[i], seq[i].tobytes().decode(), q))
+                hc.write("@%s\n%s\n+\n%s\n" % (names[i], corr[i].tobytes().decode(), q))
+        tables = rc.fastq_to_covariate_arrays((fu, fc), infer_rg=infer_rg)
+        dqs = ab.get_delta_qs(*tables)
+        buf = io.StringIO()
+        with contextlib.redirect_stdout(buf):
+            rc.recalibrate_fastq((fu, fc), infer_rg=infer_rg)
+    lines = buf.getvalue().split("\n")
+    outq = np.array([[ord(ch) - 33 for ch in lines[4 * i + 3]] for i in range(N)], dtype=np.int16)
+    assert all(lines[4 * i] == "@" + names[i] for i in range(N)) and outq.min() >= 0 and outq.max() < 256
+    digest = hashlib.sha256(seq.tobytes() + qual.tobytes() + corr.tobytes() + rgk.tobytes() + second.tobytes()).hexdigest()
+    keys = ("meanq", "rg_errs", "rg_total", "q_errs", "q_total", "pos_errs", "pos_total",
+            "dinuc_errs", "dinuc_total")
+    out = dict(seed=seed, N=N, L=L, R=nrg, R_synth=R, infer_rg=infer_rg, input_sha256=np.array(digest), rg=rg,
+               outq=outq.astype(np.uint8), rgdq=dqs[0], qdq=dqs[1], posdq=dqs[2], dindq=dqs[3])
+    out.update({k: np.asarray(v, dtype=np.int64) for k, v in zip(keys, tables)})
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "N", N, "L", L, "R", nrg, "meanq", tables[0], "changed", float((outq != qual).mean()))
+
+
 def delta_grid(seed=7, n=24000):
     rng = np.random.default_rng(seed)
     prior = rng.integers(0, 43, size=n)
@@ -142,5 +182,9 @@ if __name__ == "__main__":
     make_case("tails_r2_second", N=300, L=40, R=2, seed=13, qmode="illumina", all_second=True, lowq_reads=9)
     make_case("odd_len_unpaired", N=257, L=33, R=4, seed=14, paired=False)
     make_case("tiny_r2", N=24, L=17, R=2, seed=15)
+    if "--no-synth" not in sys.argv:   # the BASELINE shapes (configs 2, 3, 4), ~1 minute each
+        make_synth_case("c2_l150_r1", 1002, 5000, 150, 1)
+        make_synth_case("c3_l150_r8", 1003, 5000, 150, 8)
+        make_synth_case("c4_l250_r32", 1004, 4000, 250, 32)
     delta_grid()
     scalar_kats()

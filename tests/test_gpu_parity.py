@@ -109,6 +109,20 @@ def test_golden_cases_device_api(torch_cuda, golden_case, path):
     assert np.array_equal(out.astype(np.int16), g["outq"])
 
 
+@pytest.mark.parametrize("path", [1, 2, SEGMENTED])
+def test_baseline_shaped_goldens_device_api(torch_cuda, synth_golden_case, path):
+    """The reference's own outputs at the BASELINE shapes (L = 150 / 250, R = 1 / 8 / 32)."""
+    g = synth_golden_case
+    L, R = int(g["L"]), int(g["R"])
+    run = _run_segmented if path == SEGMENTED else (lambda *a: _run_device(*a, path))
+    tables, deltas, out = run(torch_cuda, g["seq"], g["qual"], g["corr"], g["rg"], g["second"], L, R)
+    for got, key in zip(tables, TABLE_KEYS):
+        assert np.array_equal(got, g[key]), key
+    for got, key in zip(deltas, DELTA_KEYS):
+        assert np.array_equal(got, g[key]), key
+    assert np.array_equal(out.astype(np.int16), g["outq"])
+
+
 def test_golden_cases_python_api(golden_case, tmp_path, capfd):
     """The reference's own entry points, same signatures, fed the same FASTQ files."""
     from kbbq import recalibrate
@@ -153,6 +167,27 @@ def test_delta_grid_matches_reference():
     g = load_case("delta_grid")
     dq = compare_reads.gatk_delta_q(g["prior"], g["errs"], g["total"])
     assert np.array_equal(dq, g["dq"])
+
+
+def test_near_ties_kernel_equals_long_double(torch_cuda, oracle_mod):
+    """Tie-breaking of gatk_delta_q (kbbq/compare_reads.py:257-258: fp64 log-likelihood + long-double prior, first
+    maximum wins).  (1) the reference's own answers on constructed near-tie cells; (2) a search of ~1e7 constructed
+    cells with 1e10 .. 1e11 observations, where the 64-bit-significand sums of the two best candidates are EQUAL a few
+    times per million: the kernel (exact sum rounded to a 64-bit significand) must agree with C long double on all."""
+    from kbbq import _native
+    g = load_case("delta_near_ties")
+    got = _native.delta_q_host(g["prior"].astype(np.int64), g["errs"], g["total"])
+    assert np.array_equal(got, g["dq"].astype(np.int64))
+    ties = close = 0
+    for seed in range(5):
+        pq, errs, tot = oracle_mod.near_tie_cells(3_000_000, 100 + seed, 10.0, 11.0)
+        want = oracle_mod.gatk_delta_q(pq, errs, tot)
+        got = _native.delta_q_host(pq, errs, tot)
+        assert np.array_equal(got, want), np.nonzero(got != want)[0][:5]
+        gap = oracle_mod.delta_q_top2_gap(pq, errs, tot)
+        ties += int((gap == 0).sum())
+        close += int((gap < 2.0 ** -60).sum())
+    assert close >= 20 and ties >= 10, (close, ties)   # the sample does exercise ties
 
 
 def test_device_synth_equals_numpy_twin(torch_cuda):
