@@ -58,7 +58,12 @@ def recalibrate_host_distributed(seq, qual, corr, rg, second, L, R, out, session
     n = seq.shape[0] if seq.ndim == 2 else seq.size // L
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     if session is None:
-        session = _native.Session(L, R, minscore, chunk_reads=0, resident_reads=max(n, 1), device=dev.index)
+        # this rank's share of the host threads (one node: every rank of the group runs on this host)
+        import os
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        threads = max(1, len(os.sched_getaffinity(0)) // max(1, min(world, torch.cuda.device_count())))
+        session = _native.Session(L, R, minscore, chunk_reads=0, resident_reads=max(n, 1), device=dev.index,
+                                  host_threads=threads)
     else:
         session.reset()
     C = session.chunk_reads
