@@ -50,6 +50,7 @@ extern "C" {
 #define KBBQ_E_NAME_RG (-9)       /* --infer-rg: the second '_' field does not start with RG (AssertionError) */
 #define KBBQ_E_NAME_MISMATCH (-10) /* corrected read's name does not start with the read's (AssertionError) */
 #define KBBQ_E_PEER (-11)          /* multi-GPU entry points: a device cannot reach a peer's memory */
+#define KBBQ_E_UNSUPPORTED (-12)   /* kbbq_recalibrate_fastq: a case for the chunked driver (files of different length, or larger than the device) */
 
 /* bits of the device status word */
 #define KBBQ_FLAG_QUAL_RANGE 1 /* a quality > 42: IndexError in the reference */
@@ -245,6 +246,19 @@ int kbbq_recalibrate_host_multi(const uint8_t *seq, const uint8_t *qual, const u
                                 int minscore, uint8_t *out_qual, int64_t *tables_host,
                                 int64_t *deltas_host, int *status_out, const int *devices, int n_dev);
 
+/*
+ * FASTQ files in, recalibrated FASTQ out -- recalibrate.recalibrate_fastq (kbbq/recalibrate.py:123-156) as one call:
+ * both files are indexed side by side, names checked and read groups inferred (kbbq_fastq_*), then the reads go
+ * through a session in chunks: a chunk is tokenised into pinned memory while the previous one crosses PCIe and is
+ * added to the tables; after the model step a chunk is applied and copied back while the previous one is formatted
+ * straight into the (mapped) output file.  out_fd: where the text goes (stdout's descriptor; a pipe works, a regular
+ * file is mapped).  Returns KBBQ_E_UNSUPPORTED, having written nothing, when the files hold different numbers of
+ * reads (the reference's zip() semantics) or do not fit the device at once: the chunked driver of
+ * kbbq-py_b200/kbbq/recalibrate.py handles those.  *n_reads / *n_rg / *status_out as the other entry points.
+ */
+int kbbq_recalibrate_fastq(const char *reads_path, const char *corrected_path, int infer_rg, int minscore, int out_fd,
+                           int device, int threads, int64_t *n_reads, int *n_rg, int *status_out);
+
 /* The whole-path entry points keep their sessions (device buffers, streams) between calls: allocating several
  * GB per call costs far more than the kernels.  This frees what is cached for `device`. */
 int kbbq_host_release(int device);
@@ -348,7 +362,8 @@ int kbbq_plan_info(int L, int R, int minscore, int arrays, int max_smem, int *ou
  * (kbbq/recalibrate.py:56-57,92,141-142), fastq_infer_rg / fastq_infer_secondinpair
  * (kbbq/compare_reads.py:304-318, first-seen numbering kbbq/recalibrate.py:59-64), the name check of
  * find_corrected_sites (kbbq/recalibrate.py:17) and the FASTQ print (kbbq/recalibrate.py:152-156).
- * Host pointers only, no CUDA.  `threads` <= 0: all hardware threads.  4-line records; .gz by suffix.
+ * Host pointers only, no CUDA.  `threads` <= 0: all hardware threads.  4-line records (blank lines at the end are
+ * ignored); gzip by its magic bytes; pipes are read into memory.
  */
 typedef struct kbbq_fastq kbbq_fastq;
 int kbbq_fastq_open(const char *path, int threads, kbbq_fastq **out);
@@ -369,6 +384,10 @@ int kbbq_fastq_check_names(const kbbq_fastq *uncorr, const kbbq_fastq *corr, int
                            int64_t *first_bad);
 /* '@' name '\n' seq '\n+\n' (out_qual + 33) '\n' for reads [first, first + n); out_qual u8[n*L] */
 int kbbq_fastq_write(int fd, const kbbq_fastq *f, int64_t first, int64_t n, const uint8_t *out_qual, int threads);
+/* the same records formatted into memory: *bytes = their total length; dst must hold exactly that many */
+int kbbq_fastq_format_size(const kbbq_fastq *f, int64_t first, int64_t n, int threads, int64_t *bytes);
+int kbbq_fastq_format(const kbbq_fastq *f, int64_t first, int64_t n, const uint8_t *out_qual, char *dst,
+                      int64_t dst_bytes, int threads);
 
 /*
  * Host helper of the host-buffer entry points: bit (i mod 32) of bits[i / 32] = (seq[i] != corr[i]),

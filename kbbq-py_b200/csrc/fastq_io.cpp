@@ -16,6 +16,7 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -92,21 +93,30 @@ inline const char *name_end(const char *h0, const char *h1) {
 
 int build_index(kbbq_fastq *f, int threads) {
     const char *d = f->data;
-    const size_t len = f->len;
+    size_t len = f->len;
+    // blank lines at the end of the file are not records (pysam ignores them)
+    while (len >= 2 && d[len - 1] == '\n' && (d[len - 2] == '\n' || (d[len - 2] == '\r' && len >= 3 && d[len - 3] == '\n'))) {
+        len -= d[len - 2] == '\r' ? 2 : 1;
+    }
+    while (len > 0 && len == 1 && (d[0] == '\n' || d[0] == '\r')) len = 0;
+    f->len = len;
     if (len == 0) { f->n = 0; f->L = 0; f->rec.assign(1, 0); return KBBQ_OK; }
     const int T = n_threads(threads, (int64_t)(len >> 20) + 1);
     std::vector<int64_t> lines(T + 1, 0);
     auto lo = [&](int t) { return len * (size_t)t / (size_t)T; };
+    // one scan: every thread notes where the newlines of its share are; the line numbers follow from a prefix sum
+    std::vector<std::vector<int64_t>> nls(T);
     parallel_for(T, [&](int t) {
-        int64_t c = 0;
+        std::vector<int64_t> &v = nls[t];
         const char *p = d + lo(t), *e = d + lo(t + 1);
+        v.reserve((size_t)(e - p) / 64 + 16);
         while (p < e) {
             const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
             if (!nl) break;
-            ++c;
+            v.push_back((int64_t)(nl - d));
             p = nl + 1;
         }
-        lines[t + 1] = c;
+        lines[t + 1] = (int64_t)v.size();
     });
     for (int t = 0; t < T; ++t) lines[t + 1] += lines[t];
     int64_t total = lines[T] + (d[len - 1] != '\n' ? 1 : 0);  // last line without a newline
@@ -116,15 +126,12 @@ int build_index(kbbq_fastq *f, int threads) {
     // line k starts after the k-th newline; record i starts at line 4 i
     f->rec[0] = 0;
     parallel_for(T, [&](int t) {
-        int64_t k = lines[t];  // newlines before this chunk
-        const char *p = d + lo(t), *e = d + lo(t + 1);
-        while (p < e) {
-            const char *nl = (const char *)memchr(p, '\n', (size_t)(e - p));
-            if (!nl) break;
+        int64_t k = lines[t];  // newlines before this share
+        for (const int64_t pos : nls[t]) {
             ++k;  // the line after this newline has index k
-            if ((k & 3) == 0 && k / 4 < f->n) f->rec[(size_t)(k / 4)] = (int64_t)(nl + 1 - d);
-            p = nl + 1;
+            if ((k & 3) == 0 && k / 4 < f->n) f->rec[(size_t)(k / 4)] = pos + 1;
         }
+        std::vector<int64_t>().swap(nls[t]);
     });
     // uniform length?
     const Rec r0 = parse_record(d + f->rec[0], d + f->rec[1]);
@@ -134,8 +141,16 @@ int build_index(kbbq_fastq *f, int threads) {
     std::vector<int> state(T2, 0);  // 1 = format error, 2 = ragged
     parallel_for(T2, [&](int t) {
         const int64_t a = f->n * t / T2, b = f->n * (t + 1) / T2;
+        const int64_t L0 = f->L;
         for (int64_t i = a; i < b; ++i) {
-            const Rec r = parse_record(d + f->rec[(size_t)i], d + f->rec[(size_t)i + 1]);
+            const char *p = d + f->rec[(size_t)i], *e = d + f->rec[(size_t)i + 1];
+            // the usual record: header line, then exactly L bases, "+", L qualities, LF line ends -- checked at fixed
+            // offsets without scanning the two long lines again
+            const char *h1 = (const char *)memchr(p, '\n', (size_t)(e - p));
+            if (h1 && *p == '@' && e - h1 == 2 * L0 + 5 && h1[L0 + 1] == '\n' && h1[L0 + 2] == '+' && h1[L0 + 3] == '\n' &&
+                e[-1] == '\n' && !memchr(h1 + 1, '\r', 1) && h1[L0] != '\r')
+                continue;
+            const Rec r = parse_record(p, e);
             if (!r.ok || (r.s1 - r.s0) != (r.q1 - r.q0)) { state[t] |= 1; return; }
             if ((int)(r.s1 - r.s0) != f->L) state[t] |= 2;
         }
@@ -167,10 +182,37 @@ int kbbq_fastq_open_mem(const void *data, size_t len, int threads, kbbq_fastq **
     return KBBQ_OK;
 }
 
+// everything a descriptor yields (pipes, process substitution, files that cannot be mapped)
+static int read_all(int fd, std::vector<char> &buf) {
+    size_t used = 0;
+    for (;;) {
+        if (buf.size() - used < (1u << 22)) buf.resize(std::max<size_t>(buf.size() * 2, 1u << 24));
+        const ssize_t got = read(fd, buf.data() + used, buf.size() - used);
+        if (got < 0) return KBBQ_E_IO;
+        if (got == 0) break;
+        used += (size_t)got;
+    }
+    buf.resize(used);
+    return KBBQ_OK;
+}
+
 int kbbq_fastq_open(const char *path, int threads, kbbq_fastq **out) {
     if (!path || !out) return KBBQ_E_ARG;
     kbbq_fastq *f = new kbbq_fastq;
-    if (ends_with(path, ".gz")) {
+    // gzip by its magic bytes (pysam's FastxFile does not look at the suffix either); a pipe cannot be sniffed
+    // without consuming it, so there the suffix decides
+    bool gz = ends_with(path, ".gz");
+    {
+        const int fd = open(path, O_RDONLY);
+        if (fd < 0) { delete f; return KBBQ_E_IO; }
+        struct stat st;
+        if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode)) {
+            unsigned char magic[2] = {0, 0};
+            gz = pread(fd, magic, 2, 0) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+        }
+        close(fd);
+    }
+    if (gz) {
         gzFile g = gzopen(path, "rb");
         if (!g) { delete f; return KBBQ_E_IO; }
         gzbuffer(g, 1 << 20);
@@ -192,14 +234,18 @@ int kbbq_fastq_open(const char *path, int threads, kbbq_fastq **out) {
         if (fd < 0) { delete f; return KBBQ_E_IO; }
         struct stat st;
         if (fstat(fd, &st) != 0) { close(fd); delete f; return KBBQ_E_IO; }
-        if (st.st_size > 0) {
-            void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
-            if (m == MAP_FAILED) { close(fd); delete f; return KBBQ_E_IO; }
+        void *m = MAP_FAILED;
+        if (S_ISREG(st.st_mode) && st.st_size > 0) m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+        if (m != MAP_FAILED) {
             madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
             f->map = m;
             f->map_len = (size_t)st.st_size;
             f->data = (const char *)m;
             f->len = (size_t)st.st_size;
+        } else if (!S_ISREG(st.st_mode) || st.st_size > 0) {   // a pipe, or a file that cannot be mapped
+            if (read_all(fd, f->owned) != KBBQ_OK) { close(fd); delete f; return KBBQ_E_IO; }
+            f->data = f->owned.data();
+            f->len = f->owned.size();
         }
         close(fd);
     }
@@ -219,7 +265,7 @@ int64_t kbbq_fastq_num_reads(const kbbq_fastq *f) { return f ? f->n : -1; }
 int kbbq_fastq_read_len(const kbbq_fastq *f) { return f ? f->L : -1; }
 
 int kbbq_fastq_pack(const kbbq_fastq *f, int64_t first, int64_t n, uint8_t *seq, uint8_t *qual, int threads) {
-    if (!f || first < 0 || n < 0 || first + n > f->n || (n && (!seq || !qual))) return KBBQ_E_ARG;
+    if (!f || first < 0 || n < 0 || first + n > f->n || (n && !seq)) return KBBQ_E_ARG;   // qual may be NULL (bases only)
     if (f->L < 0) return KBBQ_E_RAGGED;
     const int L = f->L;
     const int T = n_threads(threads, n);
@@ -238,6 +284,7 @@ int kbbq_fastq_pack(const kbbq_fastq *f, int64_t first, int64_t n, uint8_t *seq,
                 q0 = r.q0;
             }
             memcpy(seq + (size_t)i * L, s0, (size_t)L);
+            if (!qual) continue;
             const uint8_t *__restrict q = (const uint8_t *)q0;
             uint8_t *__restrict o = qual + (size_t)i * L;
             unsigned m = 0xFF;
@@ -358,6 +405,75 @@ int kbbq_fastq_check_names(const kbbq_fastq *uncorr, const kbbq_fastq *corr, int
     return KBBQ_OK;
 }
 
+int kbbq_fastq_format_size(const kbbq_fastq *f, int64_t first, int64_t n, int threads, int64_t *bytes) {
+    if (!f || first < 0 || n < 0 || first + n > f->n || !bytes) return KBBQ_E_ARG;
+    if (f->L < 0) return KBBQ_E_RAGGED;
+    const int L = f->L;
+    const int T = n_threads(threads, (n >> 12) + 1);
+    std::vector<int64_t> part(T, 0);
+    parallel_for(T, [&](int t) {  // names vary, the rest is 2 L + 6 per record
+        const int64_t a = n * t / T, b = n * (t + 1) / T;
+        int64_t sum = 0;
+        for (int64_t i = a; i < b; ++i) {
+            const char *h0 = f->data + f->rec[(size_t)(first + i)] + 1;
+            const char *h1 = line_end(h0, f->data + f->rec[(size_t)(first + i) + 1]);
+            sum += (int64_t)(name_end(h0, h1) - h0) + 2 * (int64_t)L + 6;
+        }
+        part[t] = sum;
+    });
+    *bytes = 0;
+    for (int64_t v : part) *bytes += v;
+    return KBBQ_OK;
+}
+
+// one record: '@' name '\n' seq '\n+\n' (q + 33) '\n'; returns the byte after it
+static inline char *format_record(const kbbq_fastq *f, size_t ri, const uint8_t *__restrict q, int L, char *__restrict w) {
+    const char *p = f->data + f->rec[ri], *e = f->data + f->rec[ri + 1];
+    const char *h0 = p + 1, *h1 = (const char *)memchr(p, '\n', (size_t)(e - p)), *s0;
+    if (h1 && e - h1 >= 2 * (int64_t)L + 4 && h1[-1] != '\r') {
+        s0 = h1 + 1;   // LF line ends: the bases follow the header line (the index checked the record)
+    } else {
+        const Rec r = parse_record(p, e);
+        h0 = r.h0; h1 = r.h1; s0 = r.s0;
+    }
+    const size_t nl = (size_t)(name_end(h0, h1) - h0);
+    *w++ = '@';
+    memcpy(w, h0, nl); w += nl;   // the comment is dropped (kbbq/recalibrate.py:153)
+    *w++ = '\n';
+    memcpy(w, s0, (size_t)L); w += L;
+    *w++ = '\n'; *w++ = '+'; *w++ = '\n';
+    for (int c = 0; c < L; ++c) w[c] = (char)(q[c] + 33);
+    w[L] = '\n';
+    return w + L + 1;
+}
+
+int kbbq_fastq_format(const kbbq_fastq *f, int64_t first, int64_t n, const uint8_t *out_qual, char *dst, int64_t dst_bytes,
+                      int threads) {
+    if (!f || first < 0 || n < 0 || first + n > f->n || (n && (!out_qual || !dst))) return KBBQ_E_ARG;
+    if (f->L < 0) return KBBQ_E_RAGGED;
+    const int L = f->L;
+    const int T = n_threads(threads, (n >> 12) + 1);
+    std::vector<int64_t> bytes(T + 1, 0);
+    parallel_for(T, [&](int t) {
+        const int64_t a = n * t / T, b = n * (t + 1) / T;
+        int64_t sum = 0;
+        for (int64_t i = a; i < b; ++i) {
+            const char *h0 = f->data + f->rec[(size_t)(first + i)] + 1;
+            const char *h1 = line_end(h0, f->data + f->rec[(size_t)(first + i) + 1]);
+            sum += (int64_t)(name_end(h0, h1) - h0) + 2 * (int64_t)L + 6;
+        }
+        bytes[t + 1] = sum;
+    });
+    for (int t = 0; t < T; ++t) bytes[t + 1] += bytes[t];
+    if (bytes[T] != dst_bytes) return KBBQ_E_ARG;
+    parallel_for(T, [&](int t) {
+        const int64_t a = n * t / T, b = n * (t + 1) / T;
+        char *w = dst + bytes[t];
+        for (int64_t i = a; i < b; ++i) w = format_record(f, (size_t)(first + i), out_qual + (size_t)i * L, L, w);
+    });
+    return KBBQ_OK;
+}
+
 int kbbq_fastq_write(int fd, const kbbq_fastq *f, int64_t first, int64_t n, const uint8_t *out_qual, int threads) {
     if (!f || fd < 0 || first < 0 || n < 0 || first + n > f->n || (n && !out_qual)) return KBBQ_E_ARG;
     if (f->L < 0) return KBBQ_E_RAGGED;
@@ -366,10 +482,40 @@ int kbbq_fastq_write(int fd, const kbbq_fastq *f, int64_t first, int64_t n, cons
     const int64_t wave = 1 << 15;  // reads per thread and wave: bounds the formatting buffers
     std::vector<std::vector<char>> buf(T);
 
-    // A seekable descriptor (a file, not a pipe, not O_APPEND): every thread formats its own contiguous
-    // share of the reads and writes it at its own offset, so the copy into the page cache is parallel too.
+    // A regular file (stdout redirected, not a pipe, not O_APPEND): the records are formatted straight into a shared
+    // mapping of the output file, every thread its own contiguous share.  write() / pwrite() on ONE file serialise
+    // on the inode lock however many threads call them (3 - 4 GB/s into a tmpfs); page faults on a mapping do not.
+    // The descriptor is usually write-only (shell redirection), so the file is reopened read-write through /proc.
     const off_t pos0 = lseek(fd, 0, SEEK_CUR);
     const int fl = fcntl(fd, F_GETFL);
+    struct stat st;
+    if (pos0 >= 0 && fl >= 0 && !(fl & O_APPEND) && T > 1 && n > 0 && fstat(fd, &st) == 0 && S_ISREG(st.st_mode) &&
+        !getenv("KBBQ_FASTQ_NO_MMAP")) {
+        int64_t total = 0;
+        int rc = kbbq_fastq_format_size(f, first, n, threads, &total);
+        if (rc) return rc;
+        char link[64];
+        snprintf(link, sizeof(link), "/proc/self/fd/%d", fd);
+        const int rw = open(link, O_RDWR);
+        if (rw >= 0) {
+            const long page = sysconf(_SC_PAGESIZE);
+            const off_t base = pos0 / page * page;
+            const size_t span = (size_t)(pos0 - base) + (size_t)total;
+            void *m = MAP_FAILED;
+            if (ftruncate(rw, pos0 + (off_t)total) == 0) m = mmap(nullptr, span, PROT_READ | PROT_WRITE, MAP_SHARED, rw, base);
+            close(rw);
+            if (m != MAP_FAILED) {
+                rc = kbbq_fastq_format(f, first, n, out_qual, (char *)m + (pos0 - base), total, threads);
+                munmap(m, span);
+                if (rc) return rc;
+                if (lseek(fd, pos0 + (off_t)total, SEEK_SET) < 0) return KBBQ_E_IO;
+                return KBBQ_OK;
+            }
+        }
+    }
+
+    // A seekable descriptor that cannot be mapped: every thread formats its own contiguous share of the reads and
+    // writes it at its own offset.
     if (pos0 >= 0 && fl >= 0 && !(fl & O_APPEND) && T > 1) {
         std::vector<int64_t> bytes(T + 1, 0);
         parallel_for(T, [&](int t) {  // size of every share: names vary, the rest is 2 L + 6 per record
@@ -390,23 +536,15 @@ int kbbq_fastq_write(int fd, const kbbq_fastq *f, int64_t first, int64_t n, cons
             std::vector<char> &o = buf[t];
             for (int64_t c0 = a; c0 < b; c0 += 4096) {
                 const int64_t c1 = std::min(b, c0 + 4096);
-                o.clear();
+                int64_t need = 0;
                 for (int64_t i = c0; i < c1; ++i) {
-                    const size_t ri = (size_t)(first + i);
-                    const Rec r = parse_record(f->data + f->rec[ri], f->data + f->rec[ri + 1]);
-                    const size_t nl = (size_t)(name_end(r.h0, r.h1) - r.h0);
-                    const size_t used = o.size();
-                    o.resize(used + nl + 2 * (size_t)L + 6);
-                    char *w = o.data() + used;
-                    *w++ = '@';
-                    memcpy(w, r.h0, nl); w += nl;
-                    *w++ = '\n';
-                    memcpy(w, r.s0, (size_t)L); w += L;
-                    *w++ = '\n'; *w++ = '+'; *w++ = '\n';
-                    const uint8_t *__restrict q = out_qual + (size_t)i * L;
-                    for (int c = 0; c < L; ++c) w[c] = (char)(q[c] + 33);
-                    w[L] = '\n';
+                    const char *h0 = f->data + f->rec[(size_t)(first + i)] + 1;
+                    const char *h1 = line_end(h0, f->data + f->rec[(size_t)(first + i) + 1]);
+                    need += (int64_t)(name_end(h0, h1) - h0) + 2 * (int64_t)L + 6;
                 }
+                o.resize((size_t)need);
+                char *w = o.data();
+                for (int64_t i = c0; i < c1; ++i) w = format_record(f, (size_t)(first + i), out_qual + (size_t)i * L, L, w);
                 const char *p = o.data();
                 size_t left = o.size();
                 while (left) {

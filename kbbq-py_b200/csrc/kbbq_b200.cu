@@ -168,6 +168,7 @@ const char *kbbq_strerror(int code) {
     case KBBQ_E_NAME_RG: return "read-group field does not start with RG";
     case KBBQ_E_NAME_MISMATCH: return "corrected read name does not start with the read name";
     case KBBQ_E_PEER: return "multi-GPU: peer access between the devices is not available";
+    case KBBQ_E_UNSUPPORTED: return "not handled by this entry point (use the chunked driver)";
     default: return "unknown error";
     }
 }

@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(HERE, "libkbbq_b200.so")
 NQ = 43
 FLAG_QUAL_RANGE, FLAG_BAD_BASE, FLAG_RG_RANGE, FLAG_SEGMENTS = 1, 2, 4, 8
 E_DATA = -4
+E_UNSUPPORTED = -12
 
 _lib = None
 
@@ -34,6 +35,7 @@ SIGNATURES = {
     "kbbq_apply": (_i, [_vp] * 4 + [_i64, _i, _i, _i] + [_vp] * 5 + [_i, _i, _vp, _vp, _sz, _vp, _i, _vp]),
     "kbbq_recalibrate_host": (_i, [_vp] * 5 + [_i64, _i, _i, _i] + [_vp] * 3 + [C.POINTER(_i), _i]),
     "kbbq_recalibrate_host_multi": (_i, [_vp] * 5 + [_i64, _i, _i, _i] + [_vp] * 3 + [C.POINTER(_i), C.POINTER(_i), _i]),
+    "kbbq_recalibrate_fastq": (_i, [C.c_char_p, C.c_char_p, _i, _i, _i, _i, _i, C.POINTER(_i64), C.POINTER(_i), C.POINTER(_i)]),
     "kbbq_host_release": (_i, [_i]),
     "kbbq_session_create": (_i, [_i, _i, _i, _i, _i64, _i64, _i, C.POINTER(_vp)]),
     "kbbq_session_destroy": (None, [_vp]),
@@ -76,6 +78,8 @@ SIGNATURES = {
     "kbbq_fastq_rg_key": (_i, [_vp, _i, C.POINTER(C.c_char_p), C.POINTER(_i)]),
     "kbbq_fastq_check_names": (_i, [_vp, _vp, _i64, _i, C.POINTER(_i64)]),
     "kbbq_fastq_write": (_i, [_i, _vp, _i64, _i64, _vp, _i]),
+    "kbbq_fastq_format_size": (_i, [_vp, _i64, _i64, _i, C.POINTER(_i64)]),
+    "kbbq_fastq_format": (_i, [_vp, _i64, _i64, _vp, _vp, _i64, _i]),
     "kbbq_host_mismatch_bits": (_i, [_vp, _vp, _i64, _vp, _i]),
     "kbbq_expand_mismatch_bits": (_i, [_vp, _vp, _i64, _vp, _vp]),
     "kbbq_plan_info": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i)]),

@@ -137,6 +137,21 @@ def recalibrate_fastq(fastq, infer_rg=False, devices=None):
         batch_reads = STREAM_BATCH_READS
     if batch_reads > 0:
         return _recalibrate_fastq_streamed(fastq, infer_rg, batch_reads, devices)
+    devs = _native.device_list(devices)
+    fd = _stdout_fd()
+    if fd is not None and len(devs) == 1:
+        # the whole path in native code: tokenise, upload, build, model, apply, download, format -- pipelined per chunk
+        import ctypes as C
+        from . import fastx
+        n, nrg, st = C.c_int64(0), C.c_int(0), C.c_int(0)
+        rc = _native.lib().kbbq_recalibrate_fastq(str(fastq[0]).encode(), str(fastq[1]).encode(), 1 if infer_rg else 0, 6, fd,
+                                                  devs[0], 0, C.byref(n), C.byref(nrg), C.byref(st))
+        if rc == 0:
+            return
+        if rc != _native.E_UNSUPPORTED:
+            if rc == _native.E_DATA:
+                _native.check(rc, st.value)
+            fastx._check(rc, str(fastq[0]))
     batch = ReadBatch.from_fastq(fastq, infer_rg)
     if batch.N == 0:
         return

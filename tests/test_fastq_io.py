@@ -157,3 +157,78 @@ def test_write_to_pipe_append_and_offset_agree(tmp_path):
     t.join()
     os.close(r)
     assert got[0] == body
+
+
+def test_open_is_tolerant_like_pysam(tmp_path):
+    """Blank lines at the end of the file, gzip without the .gz suffix, a named pipe instead of a file."""
+    import shutil
+    import threading
+    rng = np.random.default_rng(7)
+    recs = _random_records(rng, 301, 25)
+    plain = tmp_path / "x.fq"
+    _write(plain, recs)
+    want = fastx.NativeFastq(plain, threads=3)
+    ws, wq = want.pack()
+    with open(plain, "rb") as fh:
+        body = fh.read()
+    for tail in (b"\n", b"\n\n\n", b"\r\n"):
+        p = tmp_path / "blank.fq"
+        p.write_bytes(body + tail)
+        f = fastx.NativeFastq(p, threads=3)
+        assert f.N == want.N and f.L == want.L
+        s, q = f.pack()
+        assert np.array_equal(s, ws) and np.array_equal(q, wq) and f.name(f.N - 1) == want.name(want.N - 1)
+        f.close()
+    gz = tmp_path / "x.fq.gz"
+    _write(gz, recs)
+    shutil.copy(gz, tmp_path / "disguised.fastq")   # gzip bytes, no .gz suffix
+    f = fastx.NativeFastq(tmp_path / "disguised.fastq", threads=2)
+    s, q = f.pack()
+    assert np.array_equal(s, ws) and np.array_equal(q, wq)
+    f.close()
+    fifo = tmp_path / "pipe.fq"
+    os.mkfifo(fifo)
+    feeder = threading.Thread(target=lambda: open(fifo, "wb").write(body))
+    feeder.start()
+    f = fastx.NativeFastq(fifo, threads=2)
+    feeder.join()
+    s, q = f.pack()
+    assert f.N == want.N and np.array_equal(s, ws) and np.array_equal(q, wq)
+    f.close()
+    want.close()
+
+
+@pytest.mark.parametrize("flags", [os.O_WRONLY, os.O_RDWR])
+def test_writer_mapped_equals_plain(tmp_path, monkeypatch, flags):
+    """The writer maps the output file (reopened read-write through /proc when the descriptor is write-only, as a
+    shell redirection is) and must produce the bytes of the pwrite path; text already in the file is kept."""
+    rng = np.random.default_rng(8)
+    recs = _random_records(rng, 20_011, 31)
+    path = tmp_path / "x.fq"
+    _write(path, recs)
+    f = fastx.NativeFastq(path, threads=6)
+    out = rng.integers(0, 60, size=(f.N, f.L)).astype(np.uint8)
+    texts = []
+    for no_mmap in ("", "1"):
+        if no_mmap:
+            monkeypatch.setenv("KBBQ_FASTQ_NO_MMAP", "1")
+        p = tmp_path / ("out%s.fq" % no_mmap)
+        fd = os.open(p, flags | os.O_CREAT | os.O_TRUNC, 0o600)
+        os.write(fd, b"# header line\n")
+        f.write(fd, out[:5000], 0, 5000)
+        f.write(fd, out[5000:], 5000, f.N - 5000)   # appends where the first call stopped
+        os.close(fd)
+        texts.append(p.read_bytes())
+    assert texts[0] == texts[1] and texts[0].startswith(b"# header line\n@r0/1")
+    lines = texts[0].decode().split("\n")
+    assert len(lines) == 1 + 4 * f.N + 1
+    assert lines[1 + 4 * 7 + 3] == "".join(chr(33 + int(v)) for v in out[7])
+    # the in-memory formatter is the same text
+    import ctypes as C
+    from kbbq import _native
+    nbytes = C.c_int64(0)
+    assert _native.lib().kbbq_fastq_format_size(f._h, 0, f.N, 4, C.byref(nbytes)) == 0
+    buf = np.empty(nbytes.value, np.uint8)
+    assert _native.lib().kbbq_fastq_format(f._h, 0, f.N, _native.ptr(out), _native.ptr(buf), nbytes.value, 4) == 0
+    assert buf.tobytes() == texts[0][len(b"# header line\n"):]
+    f.close()
