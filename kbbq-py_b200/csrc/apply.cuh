@@ -50,7 +50,7 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
     const StageLayout &sl = a.sl;
     const int nconsumers = g.threads;
     const uint32_t bar0 = pin(smem_u32(smem_raw + sl.bar_off));
-    const ThreadMap m = make_thread_map(g, t.sj);
+    const ThreadMap m = make_thread_map(g, t, UNI);
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
     const uint32_t din_base = pin(smem_addr(smem_raw + t.din_off) + (lane & (t.drep - 1)) * 4);
@@ -62,7 +62,7 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
     const uint32_t rowsel = m.row >= 0 ? (uint32_t)m.row : 0u;
     const uint32_t lanemask = pin(m.row >= 0 ? 0xFFu : 0u);
     const uint32_t rowmask = pin(m.rowmask);
-    bool live = true;
+    const bool live = m.row >= 0;
     const uint32_t kgrp = g.ng * g.gbytes;
     // how this thread's word is written back: whole (0), one aligned half (1, the usual partial
     // word: reads of even length start 2-byte aligned) or byte by byte (2)
@@ -81,7 +81,12 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
     uint32_t stage = 0, phase = 0;
     uint32_t qgood = 0xFFFFFFFFu;
 
-    int cur_rg = -1;
+    int cur_rg = -1, cur_sub = -1;
+    int hs0 = 0, hs1 = 1;   // half of the cycle axis each table slot holds (build.cuh)
+    if (UNI && !a.segmode) {
+        hs0 = (int)((uni_flo & 0xFFu) >> 1);
+        hs1 = (int)(((uni_flo >> 8) & 0xFFu) >> 1);
+    }
     for (int sub = 0; sub < a.nsub; ++sub) {
         uint32_t s_lo = a.seg[sub], s_hi = a.seg[sub + 1];
         if (s_hi <= lo) continue;
@@ -93,20 +98,24 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
 
         // stage this read group's folded tables; row 0 = "leave the quality alone": the dinuc table holds 0
         // there (invalid dinucs of any quality land on it), the cycle tables hold minscore - 1, the only
-        // quality that reaches row 0 with its byte selected
-        if (rg != cur_rg) {
+        // quality that reaches row 0 with its byte selected.  In a span of a segmented batch both slots hold
+        // the span's half of the cycle axis, so the tables are staged again whenever the span changes.
+        if (rg != cur_rg || (a.segmode && sub != cur_sub)) {
             cur_rg = rg;
+            cur_sub = sub;
+            if (a.segmode) hs0 = hs1 = sub & 1;
             consumer_sync(nconsumers);
             for (int i = threadIdx.x; i < apply_table_bytes(t) / 4; i += nconsumers)
                 reinterpret_cast<int *>(smem_raw)[i] = i * 4 < t.din_off && (i * 4) % t.revoff < t.rs ? g.minscore - 1 : 0;
             consumer_sync(nconsumers);
             const int L = g.L, L2 = 2 * g.L;
             const short *fc = a.fold_cyc + (size_t)rg * NQ * L2;
-            for (int i = threadIdx.x; i < (t.nrows - 1) * L2; i += nconsumers) {
-                const int r = i / L2 + 1, c2 = i - (r - 1) * L2;
-                const int half = c2 >= L, c = half ? L2 - 1 - c2 : c2;
-                int *p = reinterpret_cast<int *>(smem_raw + t.pos_off + half * t.revoff + r * t.rs) + ((c & 3) * t.sj + (c >> 2));
-                *p = fc[(size_t)(r + g.minscore - 1) * L2 + c2];
+            for (int i = threadIdx.x; i < 2 * (t.nrows - 1) * L; i += nconsumers) {
+                const int slot = i >= (t.nrows - 1) * L, j = i - slot * (t.nrows - 1) * L;
+                const int r = j / L + 1, c = j - (r - 1) * L;
+                const int half = slot ? hs1 : hs0;
+                int *p = reinterpret_cast<int *>(smem_raw + t.pos_off + slot * t.revoff + r * t.rs) + ((c & 3) * t.sj + (c >> 2));
+                *p = fc[(size_t)(r + g.minscore - 1) * L2 + (half ? L2 - 1 - c : c)];
             }
             const short *fd = a.fold_din + (size_t)rg * NQ * DIN_SLOTS;
             for (int i = threadIdx.x; i < (t.nrows - 1) * DIN_SLOTS * t.drep; i += nconsumers) {
@@ -115,16 +124,6 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
                 *p = fd[(r + g.minscore - 1) * DIN_SLOTS + s];
             }
             consumer_sync(nconsumers);
-        }
-        if (UNI) {  // the row flag is fixed for the whole span
-            const uint32_t f = (a.segmode ? ((sub & 1) ? 3u : 1u) : prmt(uni_flo, uni_fhi, rowsel)) & lanemask;
-            // moved by the difference to the last flag (as the work-list path does) and pinned: ptxas would otherwise
-            // keep the base addresses live, or redo a multiply-add per word, at the price of constant-bank reloads
-            const uint32_t delta = ((f >> 1) - (cur_flag >> 1)) * t.revoff;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) aeff[b] = pin(aeff[b] + delta);
-            cur_flag = f;
-            live = f != 0;
         }
 
         for (uint32_t first = s_lo; first < s_hi; first += ngs) {

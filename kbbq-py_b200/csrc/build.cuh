@@ -50,7 +50,7 @@ struct TableCfg {
     int nrows;        // 44 - minscore (row 0 = trash)
     int rs;           // cycle table: row stride in bytes, multiple of 128
     int sj;           // plane stride in words: cell of cycle c at word (c & 3) * sj + (c >> 2)
-    int revoff;       // bytes from the read-1 table to the read-2 table = nrows * rs
+    int revoff;       // bytes from the first cycle table (slot 0) to the second (slot 1) = nrows * rs
     int dq;           // dinuc table: row stride in bytes = 16 slots x drep replicas x 4
     int drep;         // replicas of the dinuc table (32: bank == lane; 16: lanes l and l + 16 share one)
     int pos_off, din_off;            // byte offsets from the start of dynamic shared memory
@@ -68,7 +68,7 @@ struct TableCfg {
 
 inline bool make_table_cfg(const Geom &g, int kps, int drep, TableCfg *t) {
     if (g.minscore < 1) return false;  // row 0 is the trash row
-    if (drep != 32 && drep != 16) return false;
+    if (drep != 32 && drep != 16 && drep != 8) return false;
     t->nrows = NQ + 1 - g.minscore;
     t->sj = (g.L + 3) / 4;
     t->rs = (16 * t->sj + 127) / 128 * 128;            // 4 planes x sj words, rounded to whole bank rows
@@ -149,7 +149,15 @@ struct ThreadMap {
     int cyc[4];          // cycle of each byte (-1: not owned)
 };
 
-__device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, int sj) {
+// by_parity: the uniform walk -- the table slot of a row is its parity inside the group (interleaved pairs: read 1 /
+// read 2; rows that are all the same mate: two replicas of one table, which halves the collisions of a warp that
+// holds the end of one row and the start of the next); the cell offsets then include the slot's table and never
+// move.  Otherwise the caller moves the addresses between the two tables as the row flags of the work list say.
+// (A layout of the second table with its planes shifted so that every warp touches 32 different banks -- 168
+// instead of 220 wavefronts per CTA and byte position for 150 bp -- was built and measured on B200: no
+// faster, and its larger rows cost the apply kernel a group per stage.  The cycle-table reductions are not what
+// the kernel waits for.)
+__device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, const TableCfg &tc, bool by_parity) {
     ThreadMap m;
     const int tid = threadIdx.x;
     m.grp = tid / g.lps;
@@ -159,16 +167,10 @@ __device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, int sj) {
 #pragma unroll
     for (int k = 0; k < MAX_G; ++k)
         if (k < g.G && t >= g.wstart[k] && t < g.wstart[k + 1]) { m.row = k; w = t - g.wstart[k]; }
-    if (m.grp >= g.ng) { m.grp = 0; m.row = -1; }  // padding lanes of the last warp
+    if (m.grp >= g.ng) m.row = -1;  // idle lanes behind the last thread-group
     m.rowmask = 0; m.toff = 0; m.selv = 0x4444u; m.seln = 0x4444u;
 #pragma unroll
     for (int b = 0; b < 4; ++b) { m.cell[b] = 0; m.cyc[b] = -1; }
-    if (m.row < 0) {
-        // padding lanes run along in full stages with nothing selected (trash rows only): spread them over the banks
-        // of the trash row instead of letting them collide on one cell
-#pragma unroll
-        for (int b = 0; b < 4; ++b) m.cell[b] = 4u * (uint32_t)(((tid & 31) + 32 * b) % (4 * sj));
-    }
     if (m.row >= 0) {
         const int a = (m.row * g.L) & 3;
         m.toff = m.row * g.L - a + 4 * w;
@@ -180,14 +182,16 @@ __device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, int sj) {
                 m.rowmask |= 0xFFu << (8 * b);
                 m.selv = (m.selv & ~(0xFu << (4 * b))) | ((8u | b) << (4 * b));
                 if (c != 0) m.seln = (m.seln & ~(0xFu << (4 * b))) | ((8u | b) << (4 * b));
-#ifdef KBBQ_EXPERIMENT_NOCONFLICT
-                m.cell[b] = 4u * ((tid & 31) + 32 * b);  // timing experiment only: every lane its own bank (wrong tables)
-#else
-                m.cell[b] = 4u * ((c & 3) * sj + (c >> 2));
-#endif
+                m.cell[b] = 4u * (uint32_t)((c & 3) * tc.sj + (c >> 2)) + (by_parity ? (uint32_t)((m.row & 1) * tc.revoff) : 0u);
             }
         }
+    } else {
+        // Idle lanes (the tail of the last warp) run along in full stages with nothing selected and tally into the
+        // trash row: spread them over its banks instead of letting them collide on one cell.
+#pragma unroll
+        for (int b = 0; b < 4; ++b) m.cell[b] = 4u * (uint32_t)(((tid & 31) + 32 * b) % (tc.rs / 4));
     }
+    if (m.grp >= g.ng) { m.grp = 0; }
     return m;
 }
 
@@ -220,23 +224,26 @@ __device__ __forceinline__ void fold_din_replicas(const BuildArgs &a, unsigned c
     }
 }
 
-// Flush the cycle table of this CTA into the global int64 tables of read group rg and clear it.
-__device__ __forceinline__ void flush_pos_table(const BuildArgs &a, unsigned char *smem_raw, int rg, int nconsumers) {
+// Flush both cycle tables of this CTA into the global int64 tables of read group rg and clear them.  hs[s] says which
+// half of the cycle axis slot s holds: read 1 (0) or read 2 (1); both slots may hold the same half (single-end reads,
+// a span of a segmented batch), the global reductions simply add up.
+__device__ __forceinline__ void flush_pos_table(const BuildArgs &a, unsigned char *smem_raw, int rg, int nconsumers, int hs0, int hs1) {
     const Geom &g = a.g;
     const TableCfg &t = a.t;
     const int L = g.L, L2 = 2 * g.L;
     unsigned long long *gpe = a.pos_errs + (size_t)rg * NQ * L2, *gpt = a.pos_total + (size_t)rg * NQ * L2;
-    const int per_half = (t.nrows - 1) * L;
-    for (int i = threadIdx.x; i < 2 * per_half; i += nconsumers) {
-        const int half = i >= per_half, j = i - half * per_half;
+    const int per_slot = (t.nrows - 1) * L;
+    for (int i = threadIdx.x; i < 2 * per_slot; i += nconsumers) {
+        const int slot = i >= per_slot, j = i - slot * per_slot;
         const int r = j / L + 1, c = j - (r - 1) * L;
-        unsigned int *p = reinterpret_cast<unsigned int *>(smem_raw + t.pos_off + half * t.revoff + r * t.rs) +
+        unsigned int *p = reinterpret_cast<unsigned int *>(smem_raw + t.pos_off + slot * t.revoff + r * t.rs) +
                           ((c & 3) * t.sj + (c >> 2));
         const unsigned int v = *p;
         if (v) {
             *p = 0;
             const unsigned int tot = v % ERR_UNIT, er = v / ERR_UNIT;
             // row r holds quality r + minscore - 1; read-2 cycles count from the end of the axis
+            const int half = slot ? hs1 : hs0;
             const size_t o = (size_t)(r + g.minscore - 1) * L2 + (half ? L2 - 1 - c : c);
             atomicAdd(gpt + o, (unsigned long long)tot);
             if (er) atomicAdd(gpe + o, (unsigned long long)er);
@@ -256,11 +263,13 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
     const StageLayout &sl = a.sl;
     const int nconsumers = g.threads;
     const uint32_t bar0 = pin(smem_u32(smem_raw + sl.bar_off));
-    const ThreadMap m = make_thread_map(g, t.sj);
+    const ThreadMap m = make_thread_map(g, t, UNI);
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
     const uint32_t din_base = pin(smem_addr(smem_raw + t.din_off) + (lane & (t.drep - 1)) * 4);
-    uint32_t aeff[4];  // shared address of row 0 of the read-1 (cur_flag 1) or read-2 (3) cycle table at this thread's cycles
+    // shared address of row 0 of this thread's cycles: fixed (its slot's table) in the uniform walk, moved between the
+    // read-1 (cur_flag 1) and read-2 (3) table by the work-list walk
+    uint32_t aeff[4];
 #pragma unroll
     for (int b = 0; b < 4; ++b) aeff[b] = pos_base + m.cell[b];
     uint32_t cur_flag = 1;
@@ -268,7 +277,7 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
     const uint32_t rowsel = m.row >= 0 ? (uint32_t)m.row : 0u;  // prmt selector: flag byte of this thread's row
     const uint32_t lanemask = pin(m.row >= 0 ? 0xFFu : 0u);     // padding lanes never see a live row
     const uint32_t rowmask = pin(m.rowmask);
-    bool live = true;
+    const bool live = m.row >= 0;   // idle lanes skip partial stages (in full ones they run along, see make_thread_map)
     // UNI: group j of a stage starts at (misalignment of the stage's first group) + j * gbytes
     const uint32_t data0 = pin(smem_u32(smem_raw + sl.data_off) + m.toff + (UNI ? m.grp * g.gbytes : 0));
     const uint32_t hdr0 = pin(smem_u32(smem_raw + sl.hdr_off) + m.grp * 16);
@@ -286,15 +295,20 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
     // iterations (stages) and the dinuc replicas folded every fold_din, so that no total field can reach ERR_UNIT.
     // Both flush and fold leave the tables zero (the trash row is never read), so they double as the reset between
     // read groups.
-    int cur_rg = -1;
+    int cur_rg = -1, cur_sub = -1;
+    int hs0 = 0, hs1 = 1;   // half of the cycle axis each table slot holds
     uint32_t since_pos = 0, since_din = 0;
     auto flush_all = [&](int rg) {
         consumer_sync(nconsumers);
-        flush_pos_table(a, smem_raw, rg, nconsumers);
+        flush_pos_table(a, smem_raw, rg, nconsumers, hs0, hs1);
         fold_din_replicas(a, smem_raw, rg, nconsumers);
         consumer_sync(nconsumers);
         since_pos = since_din = 0;
     };
+    if (UNI && !a.segmode) {   // one read group: slot s holds what the flag of row s says (rows of equal parity agree)
+        hs0 = (int)((uni_flo & 0xFFu) >> 1);
+        hs1 = (int)(((uni_flo >> 8) & 0xFFu) >> 1);
+    }
 
     for (int sub = 0; sub < a.nsub; ++sub) {
         uint32_t s_lo = a.seg[sub], s_hi = a.seg[sub + 1];
@@ -303,27 +317,18 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
         if (s_lo < lo) s_lo = lo;
         if (s_hi > hi) s_hi = hi;
         if (s_lo >= s_hi) continue;
-        // a segmented batch lists (read group, read 1) and (read group, read 2) spans in turn
+        // a segmented batch lists (read group, read 1) and (read group, read 2) spans in turn; inside a span both
+        // table slots count the same half of the cycle axis, so the tables are flushed whenever the span changes
         const int rg = a.segmode ? sub >> 1 : sub;
-        if (rg != cur_rg) {
-            if (cur_rg >= 0) flush_all(cur_rg);
-            cur_rg = rg;
-        }
-        if (UNI) {  // the row flag is fixed for the whole span: re-base the cycle-table addresses once
-            const uint32_t f = (a.segmode ? ((sub & 1) ? 3u : 1u) : prmt(uni_flo, uni_fhi, rowsel)) & lanemask;
-            // moved by the difference to the last flag (as the work-list path does) and pinned: ptxas would otherwise
-            // keep the base addresses live, or redo a multiply-add per word, at the price of constant-bank reloads
-            const uint32_t delta = ((f >> 1) - (cur_flag >> 1)) * t.revoff;
-#pragma unroll
-            for (int b = 0; b < 4; ++b) aeff[b] = pin(aeff[b] + delta);
-            cur_flag = f;
-            live = f != 0;
-        }
+        if (cur_rg >= 0 && (rg != cur_rg || (a.segmode && sub != cur_sub))) flush_all(cur_rg);
+        cur_rg = rg;
+        cur_sub = sub;
+        if (a.segmode) hs0 = hs1 = sub & 1;
 
         for (uint32_t first = s_lo; first < s_hi;) {
             if (since_pos >= (uint32_t)t.flush_pos || since_din >= (uint32_t)t.fold_din) {
                 consumer_sync(nconsumers);
-                if (since_pos >= (uint32_t)t.flush_pos) { flush_pos_table(a, smem_raw, rg, nconsumers); since_pos = 0; }
+                if (since_pos >= (uint32_t)t.flush_pos) { flush_pos_table(a, smem_raw, rg, nconsumers, hs0, hs1); since_pos = 0; }
                 if (since_din >= (uint32_t)t.fold_din) { fold_din_replicas(a, smem_raw, rg, nconsumers); since_din = 0; }
                 consumer_sync(nconsumers);
             }

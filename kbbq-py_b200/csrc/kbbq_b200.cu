@@ -63,11 +63,13 @@ static bool misaligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)
 // Measured on 10M x 150 bp: build kps 1 / drep 32 1.51 ms, kps 2 / drep 32 1.24 ms, kps 4 / drep 16 1.30 ms.
 static bool plan_smem(const Geom &g, int narr, int max_smem, TableCfg *tc, StageLayout *sl) {
     const char *e = getenv("KBBQ_KPS");  // tuning / test hooks
-    const int kmax = e ? std::max(1, std::min(4, atoi(e))) : 4;
+    const int kmax = e ? std::max(1, std::min(8, atoi(e))) : 4;
     const char *d = getenv("KBBQ_DREP");
     const int dmax = d ? atoi(d) : 32;
     const char *w = getenv("KBBQ_MIN_STAGES");
     const int want = w ? std::max(2, std::min(8, atoi(w))) : 2;
+    const char *ms = getenv("KBBQ_MAX_STAGES");
+    const int smax = ms ? std::max(want, std::min(MAX_STAGES, atoi(ms))) : MAX_STAGES;
     // Measured (tools/kps_sweep.sh and the shape runs in DESIGN.md): more groups per barrier round win
     // -- four groups x two stages beats two x four by 5 % in the 150 bp build -- as long as the stages
     // behind the one being consumed hold the bandwidth-delay product of an SM (~30 B/clk x ~1400 clk);
@@ -76,12 +78,13 @@ static bool plan_smem(const Geom &g, int narr, int max_smem, TableCfg *tc, Stage
     const int in_flight_min = 40000;
     for (int pass = 0; pass < 2; ++pass) {          // pass 1: nothing holds the product; take what fits
         for (int kmin = 2; kmin >= 1; --kmin) {
-            for (int drep = 32; drep >= 16; drep >>= 1) {
+            for (int drep = 32; drep >= 8; drep >>= 1) {
+                if (drep == 8 && dmax > 8) continue;   // 8 replicas only on request
                 if (drep > dmax) continue;
                 for (int k = kmax; k >= kmin; --k) {
                     if (g.nprod > 1 && g.ng * k > 32) continue;  // one producer lane per group of a stage
                     if (!make_table_cfg(g, k, drep, tc)) return false;
-                    for (int s = MAX_STAGES; s >= want; --s) {
+                    for (int s = smax; s >= want; --s) {
                         // several producer warps take the iterations round-robin: a stage must always be
                         // refilled by the same warp (its waits are only one phase deep), so the ring
                         // depth has to be a multiple of their number
@@ -122,6 +125,10 @@ static int launch_build_kps(const BuildArgs &a, int grid, size_t smem, cudaStrea
 }
 static int launch_build_smem(const BuildArgs &a, int grid, size_t smem, cudaStream_t st) {
     switch (a.sl.kps) {
+    case 8: return launch_build_kps<8>(a, grid, smem, st);
+    case 7: return launch_build_kps<7>(a, grid, smem, st);
+    case 6: return launch_build_kps<6>(a, grid, smem, st);
+    case 5: return launch_build_kps<5>(a, grid, smem, st);
     case 4: return launch_build_kps<4>(a, grid, smem, st);
     case 3: return launch_build_kps<3>(a, grid, smem, st);
     case 2: return launch_build_kps<2>(a, grid, smem, st);
@@ -139,6 +146,10 @@ static int launch_apply_kps(const ApplyArgs &a, int grid, size_t smem, cudaStrea
 }
 static int launch_apply_smem(const ApplyArgs &a, int grid, size_t smem, cudaStream_t st) {
     switch (a.sl.kps) {
+    case 8: return launch_apply_kps<8>(a, grid, smem, st);
+    case 7: return launch_apply_kps<7>(a, grid, smem, st);
+    case 6: return launch_apply_kps<6>(a, grid, smem, st);
+    case 5: return launch_apply_kps<5>(a, grid, smem, st);
     case 4: return launch_apply_kps<4>(a, grid, smem, st);
     case 3: return launch_apply_kps<3>(a, grid, smem, st);
     case 2: return launch_apply_kps<2>(a, grid, smem, st);

@@ -102,6 +102,9 @@ __global__ void prep_uniform_kernel(PrepArgs a) {
     unsigned int exist0, sec0;
     identity_rows(a, 0, exist0, sec0, false);
     bool differs = exist0 != (1u << a.G) - 1u;
+    // the uniform walk keeps one cycle table per row parity (build.cuh: banked layout): rows of equal parity must be
+    // the same mate
+    for (int k = 2; k < a.G; ++k) differs |= ((sec0 >> k) & 1u) != ((sec0 >> (k & 1)) & 1u);
     for (long long grp = t0; grp < a.ngroups; grp += stride) {  // a few thousand threads, coalesced byte loads
         unsigned int exist, sec;
         identity_rows(a, grp, exist, sec, true);
