@@ -3,9 +3,10 @@
 
     python tools/sass_listing.py profiles/r1_sass
 
-writes <prefix>_<kernel>.txt (instructions only, encodings stripped) for the instantiations config 2
-runs (build_smem_kernel<2,true>, apply_smem_kernel<4>) and the several-read-group ones
-(build<1,true>, apply<2>), plus <prefix>_summary.txt with a mnemonic histogram of each: the lines to
+writes <prefix>_<kernel>.txt (instructions only, encodings stripped) for the instantiations the BASELINE configs
+run -- 150 bp, one read group or a segmented batch: build_smem_kernel<4,true>, apply_smem_kernel<4>; 250 bp:
+build<2,true>, apply<3>; the work-list walk of rows in read order with several read groups: build<1,true>,
+apply<2> -- plus <prefix>_summary.txt with a mnemonic histogram of each: the lines to
 look for are UBLKCP (TMA bulk copy), SYNCS (mbarrier), ATOMS / REDS (shared-memory reductions), IDP
 (4-way byte dot product), PRMT, LDS, STG.
 """
@@ -18,8 +19,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "kbbq-py_b200", "kbbq", "libkbbq_b200.so")
 WANT = {
-    "_ZN4kbbq17build_smem_kernelILi2ELb1EEEvNS_9BuildArgsE": "build_smem_kernel_kps2",
+    "_ZN4kbbq17build_smem_kernelILi4ELb1EEEvNS_9BuildArgsE": "build_smem_kernel_kps4",
     "_ZN4kbbq17apply_smem_kernelILi4EEEvNS_9ApplyArgsE": "apply_smem_kernel_kps4",
+    "_ZN4kbbq17build_smem_kernelILi2ELb1EEEvNS_9BuildArgsE": "build_smem_kernel_kps2",
+    "_ZN4kbbq17apply_smem_kernelILi3EEEvNS_9ApplyArgsE": "apply_smem_kernel_kps3",
     "_ZN4kbbq17build_smem_kernelILi1ELb1EEEvNS_9BuildArgsE": "build_smem_kernel_kps1",
     "_ZN4kbbq17apply_smem_kernelILi2EEEvNS_9ApplyArgsE": "apply_smem_kernel_kps2",
 }
