@@ -119,10 +119,16 @@ def _recalibrate_fastq_streamed(fastq, infer_rg, batch_reads, devices=None):
 
 
 def _fastq_size(path):
-    """Size of a regular file; 0 for anything else (pipes, process substitution)."""
+    """Size of the FASTQ text of a regular file (a gzip file is taken at four times its size: the streaming decision
+    is about the inflated reads); 0 for anything else (pipes, process substitution)."""
     import os
     try:
-        return os.path.getsize(path) if os.path.isfile(path) else 0
+        if not os.path.isfile(path):
+            return 0
+        size = os.path.getsize(path)
+        with open(path, "rb") as fh:
+            gz = fh.read(2) == b"\x1f\x8b"
+        return 4 * size if gz else size
     except OSError:
         return 0
 

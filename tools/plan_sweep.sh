@@ -3,21 +3,17 @@
 # ring depth (KBBQ_MIN_STAGES .. KBBQ_MAX_STAGES).  bash tools/plan_sweep.sh R L N
 LIB=kbbq-py_b200/kbbq/libkbbq_b200.so
 R=$1; RL=$2; N=$3
-echo "default plan:"; python tools/ab_kernels.py $LIB -- $R $RL $N | tail -1
+echo "default plan: $(python tools/ab_kernels.py $LIB -- $R $RL $N | tail -1)"
 while read k d smin smax; do
   echo "kps $k drep $d stages $smin..$smax: $(KBBQ_KPS=$k KBBQ_DREP=$d KBBQ_MIN_STAGES=$smin KBBQ_MAX_STAGES=$smax python tools/ab_kernels.py $LIB -- $R $RL $N | tail -1)"
 done <<CFG
 4 32 2 2
-4 16 2 2
-4 16 3 3
-5 16 2 2
-6 16 2 2
-6 16 3 3
-8 16 2 2
-6 8 2 2
-6 8 3 3
-8 8 2 2
-8 8 3 3
-4 8 4 4
 3 32 3 3
+3 32 2 2
+2 32 4 4
+2 32 5 5
+2 32 3 3
+1 32 8 8
+4 32 3 3
+3 32 4 4
 CFG
