@@ -73,7 +73,7 @@ class Workload:
 def resolve_workload(args, world):
     """The workload of this run: an explicit shape, else config 2 on one GPU and config 3's shard on several."""
     explicit = args.reads is not None or args.read_len is not None or args.read_groups is not None
-    base = CONFIGS[2 if world == 1 else 3]
+    base = CONFIGS[2 if world == 1 and args.scaling == "weak" else 3]   # strong scaling is config 3 at any N
     if args.stream_batch > 0 and not explicit:
         base = CONFIGS[5]
     N = args.reads if args.reads is not None else base["reads"]

@@ -102,10 +102,42 @@ __global__ void prep_uniform_kernel(PrepArgs a) {
     unsigned int exist0, sec0;
     identity_rows(a, 0, exist0, sec0, false);
     bool differs = exist0 != (1u << a.G) - 1u;
-    // the uniform walk keeps one cycle table per row parity (build.cuh: banked layout): rows of equal parity must be
-    // the same mate
+    // the uniform walk keeps one cycle table per row parity (build.cuh: make_thread_map): rows of equal parity must
+    // be the same mate
     for (int k = 2; k < a.G; ++k) differs |= ((sec0 >> k) & 1u) != ((sec0 >> (k & 1)) & 1u);
-    for (long long grp = t0; grp < a.ngroups; grp += stride) {  // a few thousand threads, coalesced byte loads
+    // Whole groups of a power-of-two G repeat every 16 rows: compare 16 mate flags (and 8 read-group numbers) per
+    // load against the pattern of group 0 instead of walking the rows one byte at a time.
+    const bool wide = (a.G & (a.G - 1)) == 0 && a.G <= 16 && (!a.second || ((uintptr_t)a.second & 15u) == 0) &&
+                      (!a.rg || ((uintptr_t)a.rg & 15u) == 0);
+    long long done_groups = 0;
+    if (wide) {
+        const long long chunks = a.N / 16;   // rows [0, 16 * chunks)
+        uint4 pat;
+        {
+            unsigned int v[4];
+            for (int j = 0; j < 4; ++j) {
+                v[j] = 0;
+                for (int k = 0; k < 4; ++k) v[j] |= ((sec0 >> ((4 * j + k) % a.G)) & 1u) << (8 * k);
+            }
+            pat = make_uint4(v[0], v[1], v[2], v[3]);
+        }
+        for (long long c = t0; c < chunks; c += stride) {
+            if (a.second) {
+                const uint4 s = reinterpret_cast<const uint4 *>(a.second)[c];
+                // second[] holds any non-zero value for "read 2": normalise to 0 / 1 per byte
+                auto norm = [](unsigned int x) { return ((x | ((x | 0x80808080u) - 0x01010101u)) >> 7) & 0x01010101u; };
+                differs |= norm(s.x) != pat.x || norm(s.y) != pat.y || norm(s.z) != pat.z || norm(s.w) != pat.w;
+            } else {
+                differs |= sec0 != 0;
+            }
+            if (a.rg) {
+                const uint4 r0 = reinterpret_cast<const uint4 *>(a.rg)[2 * c], r1 = reinterpret_cast<const uint4 *>(a.rg)[2 * c + 1];
+                if (r0.x | r0.y | r0.z | r0.w | r1.x | r1.y | r1.z | r1.w) { differs = true; atomicOr(a.status, KBBQ_FLAG_RG_RANGE); }
+            }
+        }
+        done_groups = chunks * 16 / a.G;
+    }
+    for (long long grp = done_groups + t0; grp < a.ngroups; grp += stride) {  // the rest (or every group), row by row
         unsigned int exist, sec;
         identity_rows(a, grp, exist, sec, true);
         differs |= exist != exist0 || sec != sec0;
