@@ -359,6 +359,46 @@ def test_full_size_properties(torch_cuda, case):
     rec.check_status()
 
 
+PACKED_COUNTER_CASES = [
+    # (L, N, R): short reads of ONE quality -- every read hits the same row of the cycle table at every cycle, so a
+    # CTA's slice (N / 148 reads) puts far more than 65 024 hits into single shared-memory cells between segments
+    (16, 20_000_000, 1),
+    (8, 24_000_000, 2),
+    (24, 12_000_000, 1),
+]
+
+
+@pytest.mark.parametrize("case", PACKED_COUNTER_CASES, ids=["l%d_n%dm_r%d" % (c[0], c[1] // 1_000_000, c[2]) for c in PACKED_COUNTER_CASES])
+def test_packed_counters_do_not_carry(torch_cuda, oracle_mod, case):
+    """The shared-memory counters pack total + 65025 * errors in one u32 (build.cuh): the cycle table has to be
+    flushed, and the dinucleotide replicas folded, before any total field reaches 65025 -- whatever the read
+    length.  Constant qualities on tens of millions of short reads reach that regime (for L < 29 the fold period
+    used to exceed the flush period, and a chunk was only bounded by the former)."""
+    torch = torch_cuda
+    from kbbq.device import DeviceRecalibrator
+    L, N, R = case
+    rng = np.random.default_rng(L)
+    seq = np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, (N, L), dtype=np.uint8)]
+    qual = np.full((N, L), 30, np.uint8)
+    corr = seq.copy()
+    corr[rng.random((N, L)) < 0.02] = ord("A")      # ~1.5 % mismatches
+    rg = (np.arange(N) // 2 % R).astype(np.uint16) if R > 1 else None
+    second = (np.arange(N) & 1).astype(np.uint8)
+    want = oracle_mod.covariate_arrays(seq, qual, corr, rg if rg is not None else np.zeros(N, np.uint16), second, L, R)[5:]
+    s, q, c, g, sec = _dev(torch, seq, qual, corr, rg, second)
+    rec = DeviceRecalibrator(L, R, max_reads=N)
+    rec.build(s, q, c, g, sec, path=1)
+    got = rec.covariate_arrays()[5:]
+    for a, b, key in zip(got, want, TABLE_KEYS[5:]):
+        assert np.array_equal(a, b), (key, "read order")
+    if _segmented_ok(L, R):
+        rec.reset()
+        rec.build_segmented(rec.segment(s, q, c, g, sec))
+        for a, b, key in zip(rec.covariate_arrays()[5:], want, TABLE_KEYS[5:]):
+            assert np.array_equal(a, b), (key, "segmented")
+    rec.check_status()
+
+
 def test_random_shapes_vs_oracle(torch_cuda, oracle_mod):
     """Seeded sweep over read lengths (every alignment class, the generic-kernel range L > 288 included),
     read-group counts, batch sizes that leave partial groups, unpaired reads and N-rich data; path 0 is
