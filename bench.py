@@ -523,22 +523,26 @@ def measure_e2e(args, wl, dev, world, rank, local, barrier, first_read):
     rec.check_status()
     if not torch.equal(h_out.to(dev), want):
         raise SystemExit("bench.py: host-buffer path and device path disagree")
-    # the library sends the corrected reads as a mismatch bit map when the session has >= 8 host threads
+    # what the library actually copied (counted by its sessions from the copies they issued) and in which form
     cpus = len(os.sched_getaffinity(0))
-    bits = os.environ.get("KBBQ_HOST_NO_BITMAP", "0") in ("", "0") and \
-        (os.environ.get("KBBQ_HOST_BITMAP", "0") not in ("", "0") or cpus // max(1, world) >= 8)
-    h2d = 2 * n * L + ((n * L + 31) // 32 * 4 if bits else n * L) + n + (2 * n if R > 1 else 0)
+    mode = int(lib.kbbq_host_pack_mode(max(1, cpus // max(1, world))))
     if world > 1 and state["s"] is not None:
-        counted, _ = state["s"].traffic()   # counted by the session from the copies it issued
-        bits = counted < 3 * n * L
-        h2d = counted
+        h2d, _ = state["s"].traffic()
         state["s"].close()
+    else:
+        up = C.c_int64(0)
+        _native.check(lib.kbbq_host_last_traffic(local, C.byref(up), None))
+        h2d = up.value
+    transport = {0: "reads, qualities and corrected reads cross PCIe as they are",
+                 1: "corrected reads cross PCIe as a 1-bit mismatch map made by the host cores",
+                 2: "reads + corrected reads cross PCIe as 4 bits per base (base code | mismatch) packed by the host "
+                    "cores while the copy engine moves the qualities"}[mode]
     links = link_rates(dev, barrier, world)
     ideal = h2d / (links["h2d_gbs_per_gpu"] * 1e9) + n * L / (links["d2h_gbs_per_gpu"] * 1e9)
     return {"value": world * n * L * ke / dt, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": n * L,
             "host_input_bytes_per_step": 3 * n * L + n + (2 * n if R > 1 else 0), "ms_per_step": 1e3 * dt / ke,
             "steps": ke, "ms_all_steps": [1e3 * x for x in times], "statistic": "median step", "reads_per_gpu": n, "api": api +
-            ("; corrected reads cross PCIe as a 1-bit mismatch map" if bits else "") +
+            "; " + transport +
             ("; chunks segmented by read group on the device" if R > 1 else ""),
             "link": links, "frac_of_link": ideal / (dt / ke),
             "frac_of_link_note": "(h2d_bytes / measured H2D rate + d2h_bytes / measured D2H rate) / step time: upload and "

@@ -262,6 +262,11 @@ int kbbq_recalibrate_fastq(const char *reads_path, const char *corrected_path, i
 /* The whole-path entry points keep their sessions (device buffers, streams) between calls: allocating several
  * GB per call costs far more than the kernels.  This frees what is cached for `device`. */
 int kbbq_host_release(int device);
+/* What the last whole-path call on `device` moved over PCIe (bytes of the copies it issued), and the form the
+ * reads take on the way up for a session with that many host threads (<= 0: all): 0 = seq + qual + corrected as
+ * they are, 1 = seq + qual + 1-bit mismatch map, 2 = qual + 4 bits per base (kbbq_host_pack_nibbles). */
+int kbbq_host_last_traffic(int device, int64_t *h2d_bytes, int64_t *d2h_bytes);
+int kbbq_host_pack_mode(int host_threads);
 
 /*
  * Sessions: the two passes of kbbq/recalibrate.py:123-156 on one device, fed chunk by chunk from host memory
@@ -400,6 +405,20 @@ int kbbq_host_mismatch_bits(const uint8_t *seq, const uint8_t *corr, int64_t n, 
  * where the corrected read did -- all kbbq_build looks at.  seq_dev / corr_dev 16-byte aligned. */
 int kbbq_expand_mismatch_bits(const uint8_t *seq_dev, const uint32_t *bits_dev, int64_t n, uint8_t *corr_dev,
                               void *stream);
+
+/*
+ * The same idea one step further, used by the host-buffer entry points when the host has the cores for it:
+ * packed[i / 2] holds, for bases 2k (low nibble) and 2k + 1 (high nibble), (base >> 1) & 7 -- A 0, C 1, T 2, G 3,
+ * N 7 -- with bit 3 set where seq[i] != corr[i] (find_corrected_sites, kbbq/recalibrate.py:13-20): the reads and
+ * the corrected reads cross PCIe as 0.5 byte per base and only the qualities travel as they are.  *bad_base = 1
+ * if a byte of seq is none of ACGTN (the reference's TypeError, kbbq/compare_reads.py:289-302; the device never
+ * sees the byte, so the check happens here).  packed holds ceil(n / 2) bytes.
+ */
+int kbbq_host_pack_nibbles(const uint8_t *seq, const uint8_t *corr, int64_t n, uint8_t *packed, int threads,
+                           int *bad_base);
+/* The device side: seq_dev from the base codes, corr_dev = a byte array that differs from seq_dev exactly where
+ * bit 3 of the nibble is set.  All three pointers 16-byte aligned. */
+int kbbq_expand_nibbles(const uint8_t *packed_dev, int64_t n, uint8_t *seq_dev, uint8_t *corr_dev, void *stream);
 
 /* Number of kernel launches this library has issued since load (bench.py's gpu_launches). */
 int64_t kbbq_launch_count(void);

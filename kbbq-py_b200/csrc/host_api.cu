@@ -87,10 +87,12 @@ __global__ void sum_tables_kernel(PeerTables p, int n, long long *out, size_t el
     }
 }
 
+enum { PACK_NONE = 0, PACK_BITS = 1, PACK_NIBBLES = 2 };
+
 struct UpSlot {   // one upload in flight: the chunk as the host has it (read order)
     uint8_t *seq = nullptr, *qual = nullptr, *corr = nullptr, *sec = nullptr;
     uint16_t *rg = nullptr;
-    uint32_t *bits = nullptr;
+    uint32_t *bits = nullptr;     // PACK_BITS: 1 bit per base; PACK_NIBBLES: 4 bits per base
     // streaming sessions with several read groups: the segmented copy of the chunk
     uint8_t *sseq = nullptr, *squal = nullptr, *scorr = nullptr;
     uint32_t *seg = nullptr, *dest = nullptr;
@@ -117,7 +119,9 @@ struct kbbq_session {
     int64_t C = 0;          // reads per chunk (capacity)
     int64_t M = 0;          // reads that can stay resident (0: streaming session)
     int64_t rowsC = 0;      // rows of a chunk in the segmented layout
-    bool segmode = false, use_bits = true;
+    bool segmode = false;
+    int pack = PACK_NIBBLES;   // how the reads and the corrected reads cross PCIe (PACK_*)
+    int host_status = 0;       // KBBQ_FLAG_* found by the host-side packer
     int host_threads = 0;
     void *base = nullptr;
     size_t cap = 0;
@@ -165,15 +169,22 @@ int usable_cpus() {
     return std::max(1, (int)std::thread::hardware_concurrency());
 }
 
-// The corrected reads cross PCIe as a 1-bit-per-base mismatch map made by the host cores (host_pack.cpp) when this
-// session has the cores for it: the comparison reads 2 B per base of host memory, and with fewer than 8 threads (an
-// 8-GPU box shares 32 cores, and its host memory, between 8 sessions) it takes longer than the bytes it saves
-// (B200 x 8: 389 ms per step with the map, 343 ms with the corrected reads as they are; 4 GPUs, 8 threads each: map).
-// KBBQ_HOST_NO_BITMAP=1 / KBBQ_HOST_BITMAP=1 force either.
-bool want_bitmap(int host_threads) {
-    if (!env_flag_off("KBBQ_HOST_NO_BITMAP")) return false;
-    if (!env_flag_off("KBBQ_HOST_BITMAP")) return true;
-    return (host_threads > 0 ? host_threads : usable_cpus()) >= 8;
+// What crosses PCIe in pass 1, per base (the reference only ever compares the corrected reads with the reads,
+// find_corrected_sites, kbbq/recalibrate.py:13-20):
+//   PACK_NIBBLES  qual as it is + 4 bits (base code | mismatch) made by the host cores while the copy engine moves
+//                 the qualities (host_pack.cpp): 1.5 B instead of 3;
+//   PACK_BITS     seq + qual as they are + a 1-bit mismatch map: 2.125 B;
+//   PACK_NONE     seq + qual + corrected reads: 3 B, no host work.
+// Packing reads 2 B per base of host memory, so it only pays when this session has the cores for it: with fewer
+// than 8 threads (an 8-GPU box shares 32 cores, and its host memory, between 8 sessions) it takes longer than the
+// bytes it saves (B200 x 8: 389 ms per step with the bit map, 343 ms with the corrected reads as they are; 4 GPUs,
+// 8 threads each: map).  KBBQ_HOST_NO_BITMAP=1 forces PACK_NONE, KBBQ_HOST_BITMAP=1 packing whatever the core
+// count, KBBQ_HOST_NO_NIBBLES=1 the bit map instead of the nibbles.
+int pack_mode(int host_threads) {
+    if (!env_flag_off("KBBQ_HOST_NO_BITMAP")) return PACK_NONE;
+    const int packed = env_flag_off("KBBQ_HOST_NO_NIBBLES") ? PACK_NIBBLES : PACK_BITS;
+    if (!env_flag_off("KBBQ_HOST_BITMAP")) return packed;
+    return (host_threads > 0 ? host_threads : usable_cpus()) >= 8 ? packed : PACK_NONE;
 }
 
 // several read groups: chunks are rewritten into the segmented layout on the device (segment.cuh) unless the
@@ -190,7 +201,7 @@ int session_create(int device, int L, int R, int minscore, int64_t C, int64_t M,
     S->C = (C + 15) / 16 * 16;
     S->M = M;
     S->host_threads = host_threads;
-    S->use_bits = want_bitmap(host_threads);
+    S->pack = pack_mode(host_threads);
     S->segmode = want_segmode(L, R, minscore, S->C);
     S->rowsC = S->segmode ? kbbq_segment_rows_bound(S->C, R) : S->C;
     KBBQ_CUDA(cudaStreamCreateWithFlags(&S->s_up, cudaStreamNonBlocking));
@@ -209,7 +220,8 @@ int session_create(int device, int L, int R, int minscore, int64_t C, int64_t M,
     const size_t nmodel = carve_model(nullptr, L, R).elems;
     KBBQ_TRY(kbbq_workspace_bytes(S->rowsC, L, R, &S->ws_bytes));
     const size_t cb = (size_t)S->C * L + 16, rb = (size_t)S->rowsC * L + 16;
-    const size_t bits_words = ((size_t)S->C * L + 31) / 32 + 4;
+    // words of the packed form of a chunk: 1 bit or 4 bits per base
+    const size_t bits_words = S->pack == PACK_NIBBLES ? ((size_t)S->C * L + 7) / 8 + 4 : ((size_t)S->C * L + 31) / 32 + 4;
     const size_t seg_elems = (size_t)kbbq_segment_table_elems(R);
     const int64_t nres = M ? (M + S->C - 1) / S->C : 0;
     const bool seg = S->segmode, stream_seg = seg && nres == 0;
@@ -229,7 +241,7 @@ int session_create(int device, int L, int R, int minscore, int64_t C, int64_t M,
             u.rg = staged ? c.take<uint16_t>((size_t)S->C + 8) : nullptr;
             u.sec = staged ? c.take<uint8_t>((size_t)S->C + 16) : nullptr;
             u.corr = c.take<uint8_t>(cb);
-            u.bits = S->use_bits ? c.take<uint32_t>(bits_words) : nullptr;
+            u.bits = S->pack ? c.take<uint32_t>(bits_words) : nullptr;
             u.scorr = seg ? c.take<uint8_t>(rb) : nullptr;
             u.sseq = stream_seg ? c.take<uint8_t>(rb) : nullptr;
             u.squal = stream_seg ? c.take<uint8_t>(rb) : nullptr;
@@ -254,7 +266,7 @@ int session_create(int device, int L, int R, int minscore, int64_t C, int64_t M,
         }
     }
     S->mp = carve_model(S->d_model, L, R);
-    if (S->use_bits) {
+    if (S->pack) {
         KBBQ_CUDA(cudaHostAlloc(&S->pinned, 2 * bits_words * 4, cudaHostAllocDefault));
         S->up[0].h_bits = (uint32_t *)S->pinned;
         S->up[1].h_bits = (uint32_t *)S->pinned + bits_words;
@@ -273,6 +285,7 @@ int session_reset(kbbq_session *S) {
     KBBQ_CUDA(cudaMemsetAsync(S->d_tab, 0, S->ntab * 8, S->s_comp));
     KBBQ_CUDA(cudaMemsetAsync(S->d_status, 0, sizeof(int), S->s_comp));
     S->built = S->applied = 0;
+    S->host_status = 0;
     S->summed = false;
     S->h2d_bytes = S->d2h_bytes = 0;
     for (auto &r : S->res) r.n = 0;
@@ -282,41 +295,73 @@ int session_reset(kbbq_session *S) {
 int upload_reads(kbbq_session *S, const uint8_t *seq, const uint8_t *qual, const uint16_t *rg, const uint8_t *second,
                  int64_t n, uint8_t *d_seq, uint8_t *d_qual, uint16_t *d_rg, uint8_t *d_sec) {
     const size_t nb = (size_t)n * S->L;
-    KBBQ_CUDA(cudaMemcpyAsync(d_seq, seq, nb, cudaMemcpyHostToDevice, S->s_up));
+    if (seq) { KBBQ_CUDA(cudaMemcpyAsync(d_seq, seq, nb, cudaMemcpyHostToDevice, S->s_up)); S->h2d_bytes += (int64_t)nb; }
     KBBQ_CUDA(cudaMemcpyAsync(d_qual, qual, nb, cudaMemcpyHostToDevice, S->s_up));
-    S->h2d_bytes += 2 * (int64_t)nb;
+    S->h2d_bytes += (int64_t)nb;
     if (rg) { KBBQ_CUDA(cudaMemcpyAsync(d_rg, rg, (size_t)n * 2, cudaMemcpyHostToDevice, S->s_up)); S->h2d_bytes += 2 * n; }
     if (second) { KBBQ_CUDA(cudaMemcpyAsync(d_sec, second, (size_t)n, cudaMemcpyHostToDevice, S->s_up)); S->h2d_bytes += n; }
     return KBBQ_OK;
 }
 
-// Pass 1 of one chunk, asynchronous: nothing here waits for the device except for the reuse of the pinned
-// bit-map slot (two chunks back).  keep: the chunk stays in HBM for kbbq_session_apply_resident.
-int build_chunk_async(kbbq_session *S, const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,
-                      const uint8_t *second, int64_t n, bool keep) {
-    if (n < 0 || n > S->C) return KBBQ_E_ARG;
-    if (n == 0) return KBBQ_OK;
-    if (!seq || !qual || !corr) return KBBQ_E_ARG;
-    const int64_t k = S->built;
-    if (keep && k >= (int64_t)S->res.size()) return KBBQ_E_ARG;
-    S->built++;
-    UpSlot &u = S->up[k & 1];
-    Resident *r = keep ? &S->res[(size_t)k] : nullptr;
+// Where chunk k of pass 1 lives on the device.  keep: it stays in HBM for kbbq_session_apply_resident; a plain
+// (one read group) resident chunk is uploaded / expanded straight into its place, no staging copy.
+struct ChunkPlace {
+    UpSlot *u;
+    Resident *r;
+    uint8_t *d_seq, *d_qual, *d_sec;
+    uint16_t *d_rg;
+};
+ChunkPlace chunk_place(kbbq_session *S, int64_t k, bool keep, bool has_rg, bool has_second) {
+    ChunkPlace p;
+    p.u = &S->up[k & 1];
+    p.r = keep ? &S->res[(size_t)k] : nullptr;
+    const bool direct = keep && !S->segmode;
+    p.d_seq = direct ? p.r->seq : p.u->seq;
+    p.d_qual = direct ? p.r->qual : p.u->qual;
+    p.d_rg = has_rg ? (direct ? p.r->rg : p.u->rg) : nullptr;
+    p.d_sec = has_second ? (direct ? p.r->sec : p.u->sec) : nullptr;
+    return p;
+}
+
+bool chunk_args_ok(const kbbq_session *S, int64_t k, int64_t n, bool keep) {
+    return n > 0 && n <= S->C && (!keep || k < (int64_t)S->res.size());
+}
+
+// Pass 1 of chunk k, first half: enqueue the copies that come straight from the caller's memory (the qualities,
+// read groups and mate flags; the reads too unless they travel as nibbles).  Nothing waits for the device.
+int build_chunk_upload(kbbq_session *S, int64_t k, const uint8_t *seq, const uint8_t *qual, const uint16_t *rg,
+                       const uint8_t *second, int64_t n, bool keep) {
+    if (!chunk_args_ok(S, k, n, keep) || !seq || !qual) return KBBQ_E_ARG;
+    const ChunkPlace p = chunk_place(S, k, keep, rg != nullptr, second != nullptr);
+    KBBQ_CUDA(cudaStreamWaitEvent(S->s_up, p.u->consumed, 0));   // the slot's previous chunk has been built
+    return upload_reads(S, S->pack == PACK_NIBBLES ? nullptr : seq, qual, rg, second, n, p.d_seq, p.d_qual, p.d_rg, p.d_sec);
+}
+
+// Second half: the host cores pack (seq, corrected) of the chunk while the copy engine is busy with what
+// build_chunk_upload queued (of this chunk and, in run_build_pass, of the next one too), the packed form follows,
+// and the compute stream expands it, segments the rows when there are several read groups, and builds.  The only
+// wait is for the pinned packing slot (two chunks back).
+int build_chunk_finish(kbbq_session *S, int64_t k, const uint8_t *seq, const uint8_t *corr, bool has_rg, bool has_second,
+                       int64_t n, bool keep) {
+    if (!chunk_args_ok(S, k, n, keep) || !seq || !corr) return KBBQ_E_ARG;
+    const ChunkPlace p = chunk_place(S, k, keep, has_rg, has_second);
+    UpSlot &u = *p.u;
+    Resident *r = p.r;
     const int L = S->L, R = S->R;
     const size_t nb = (size_t)n * L;
-    const bool direct = keep && !S->segmode;   // plain resident chunk: uploaded into its place
-    uint8_t *d_seq = direct ? r->seq : u.seq, *d_qual = direct ? r->qual : u.qual;
-    uint16_t *d_rg = rg ? (direct ? r->rg : u.rg) : nullptr;
-    uint8_t *d_sec = second ? (direct ? r->sec : u.sec) : nullptr;
     if (r) r->n = n;
-
-    KBBQ_CUDA(cudaStreamWaitEvent(S->s_up, u.consumed, 0));   // the slot's previous chunk has been built
-    KBBQ_TRY(upload_reads(S, seq, qual, rg, second, n, d_seq, d_qual, d_rg, d_sec));
-    if (S->use_bits) {
-        // the host cores compare while the copy engine moves seq and qual of this chunk (host_pack.cpp)
-        KBBQ_CUDA(cudaEventSynchronize(u.uploaded));           // the pinned map of two chunks back is on the device
-        KBBQ_TRY(kbbq_host_mismatch_bits(seq, corr, (int64_t)nb, u.h_bits, S->host_threads));
-        const size_t bb = ((nb + 31) / 32) * 4;
+    if (S->pack) {
+        KBBQ_CUDA(cudaEventSynchronize(u.uploaded));           // the slot's packed chunk of two chunks back is on the device
+        size_t bb;
+        if (S->pack == PACK_NIBBLES) {
+            int bad = 0;
+            KBBQ_TRY(kbbq_host_pack_nibbles(seq, corr, (int64_t)nb, (uint8_t *)u.h_bits, S->host_threads, &bad));
+            if (bad) S->host_status |= KBBQ_FLAG_BAD_BASE;
+            bb = (nb + 1) / 2;
+        } else {
+            KBBQ_TRY(kbbq_host_mismatch_bits(seq, corr, (int64_t)nb, u.h_bits, S->host_threads));
+            bb = ((nb + 31) / 32) * 4;
+        }
         KBBQ_CUDA(cudaMemcpyAsync(u.bits, u.h_bits, bb, cudaMemcpyHostToDevice, S->s_up));
         S->h2d_bytes += (int64_t)bb;
     } else {
@@ -325,25 +370,39 @@ int build_chunk_async(kbbq_session *S, const uint8_t *seq, const uint8_t *qual, 
     }
     KBBQ_CUDA(cudaEventRecord(u.uploaded, S->s_up));
     KBBQ_CUDA(cudaStreamWaitEvent(S->s_comp, u.uploaded, 0));
-    if (S->use_bits) KBBQ_TRY(kbbq_expand_mismatch_bits(d_seq, u.bits, (int64_t)nb, u.corr, S->s_comp));
+    if (S->pack == PACK_NIBBLES) KBBQ_TRY(kbbq_expand_nibbles((const uint8_t *)u.bits, (int64_t)nb, p.d_seq, u.corr, S->s_comp));
+    else if (S->pack == PACK_BITS) KBBQ_TRY(kbbq_expand_mismatch_bits(p.d_seq, u.bits, (int64_t)nb, u.corr, S->s_comp));
     const size_t npos = (size_t)R * NQ * 2 * L, ndin = (size_t)R * NQ * 16;
     int64_t *pe = S->d_tab, *pt = pe + npos, *de = pt + npos, *dt = de + ndin;
     if (S->segmode) {
         uint32_t *seg = keep ? r->seg : u.seg, *dest = keep ? r->dest : u.dest;
         uint8_t *sseq = keep ? r->seq : u.sseq, *squal = keep ? r->qual : u.squal;
-        KBBQ_TRY(kbbq_segment_plan(d_rg, d_sec, n, R, seg, dest, S->d_status, S->s_comp));
-        KBBQ_TRY(kbbq_segment_rows(d_seq, dest, n, L, sseq, S->s_comp));
-        KBBQ_TRY(kbbq_segment_rows(d_qual, dest, n, L, squal, S->s_comp));
+        KBBQ_TRY(kbbq_segment_plan(p.d_rg, p.d_sec, n, R, seg, dest, S->d_status, S->s_comp));
+        KBBQ_TRY(kbbq_segment_rows(p.d_seq, dest, n, L, sseq, S->s_comp));
+        KBBQ_TRY(kbbq_segment_rows(p.d_qual, dest, n, L, squal, S->s_comp));
         KBBQ_TRY(kbbq_segment_rows(u.corr, dest, n, L, u.scorr, S->s_comp));
         KBBQ_TRY(kbbq_segment_pad(seg, R, L, sseq, squal, u.scorr, S->s_comp));
         KBBQ_TRY(kbbq_build_segmented(sseq, squal, u.scorr, seg, S->rowsC, L, R, S->minscore, pe, pt, de, dt, S->d_ws,
                                       S->ws_bytes, S->d_status, S->s_comp));
     } else {
-        KBBQ_TRY(kbbq_build(d_seq, d_qual, u.corr, d_rg, d_sec, n, L, R, S->minscore, pe, pt, de, dt, S->d_ws, S->ws_bytes,
+        KBBQ_TRY(kbbq_build(p.d_seq, p.d_qual, u.corr, p.d_rg, p.d_sec, n, L, R, S->minscore, pe, pt, de, dt, S->d_ws, S->ws_bytes,
                             S->d_status, 0, S->s_comp));
     }
     KBBQ_CUDA(cudaEventRecord(u.consumed, S->s_comp));
     return KBBQ_OK;
+}
+
+// Pass 1 of one chunk in one go.
+int build_chunk_async(kbbq_session *S, const uint8_t *seq, const uint8_t *qual, const uint8_t *corr, const uint16_t *rg,
+                      const uint8_t *second, int64_t n, bool keep) {
+    if (n < 0 || n > S->C) return KBBQ_E_ARG;
+    if (n == 0) return KBBQ_OK;
+    if (!seq || !qual || !corr) return KBBQ_E_ARG;
+    const int64_t k = S->built;
+    if (keep && k >= (int64_t)S->res.size()) return KBBQ_E_ARG;
+    S->built++;
+    KBBQ_TRY(build_chunk_upload(S, k, seq, qual, rg, second, n, keep));
+    return build_chunk_finish(S, k, seq, corr, rg != nullptr, second != nullptr, n, keep);
 }
 
 int model_async(kbbq_session *S) {
@@ -423,6 +482,7 @@ int session_sync(kbbq_session *S, int *status_out) {
     KBBQ_CUDA(cudaStreamSynchronize(S->s_comp));
     KBBQ_CUDA(cudaStreamSynchronize(S->s_down));
     KBBQ_CUDA(cudaMemcpy(&st, S->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    st |= S->host_status;
     if (status_out) *status_out = st;
     return st ? KBBQ_E_DATA : KBBQ_OK;
 }
@@ -442,7 +502,7 @@ int cached_session(int slot, int device, int L, int R, int minscore, int64_t C, 
     const int64_t C16 = (C + 15) / 16 * 16;
     const int64_t nres = M ? (M + C16 - 1) / C16 : 0;
     if (s && s->device == device && s->L == L && s->R == R && s->minscore == minscore && s->C == C16 &&
-        (int64_t)s->res.size() >= nres && (nres > 0) == (s->M > 0) && s->use_bits == want_bitmap(host_threads) &&
+        (int64_t)s->res.size() >= nres && (nres > 0) == (s->M > 0) && s->pack == pack_mode(host_threads) &&
         s->segmode == want_segmode(L, R, minscore, C16)) {
         s->host_threads = host_threads;
         KBBQ_TRY(session_reset(s));
@@ -474,11 +534,20 @@ int run_build_pass(kbbq_session *S, const uint8_t *seq, const uint8_t *qual, con
                    const uint8_t *second, int64_t N) {
     const int L = S->L;
     const int64_t C = S->C, nchunks = N ? (N + C - 1) / C : 0;
+    const bool keep = S->M > 0;
+    auto upload = [&](int64_t k) {
+        const int64_t r0 = k * C, n = std::min(C, N - r0);
+        return build_chunk_upload(S, k, seq + (size_t)r0 * L, qual + (size_t)r0 * L, rg ? rg + r0 : nullptr,
+                                  second ? second + r0 : nullptr, n, keep);
+    };
+    // the direct copies of chunk k + 1 are queued before chunk k is packed: the copy engine never waits for the cores
+    if (nchunks) KBBQ_TRY(upload(0));
     for (int64_t k = 0; k < nchunks; ++k) {
         const int64_t r0 = k * C, n = std::min(C, N - r0);
-        KBBQ_TRY(build_chunk_async(S, seq + (size_t)r0 * L, qual + (size_t)r0 * L, corr + (size_t)r0 * L, rg ? rg + r0 : nullptr,
-                                   second ? second + r0 : nullptr, n, S->M > 0));
+        if (k + 1 < nchunks) KBBQ_TRY(upload(k + 1));
+        KBBQ_TRY(build_chunk_finish(S, k, seq + (size_t)r0 * L, corr + (size_t)r0 * L, rg != nullptr, second != nullptr, n, keep));
     }
+    S->built = nchunks;
     return KBBQ_OK;
 }
 
@@ -627,6 +696,20 @@ int kbbq_session_traffic(const kbbq_session *s, int64_t *h2d_bytes, int64_t *d2h
     if (!s) return KBBQ_E_ARG;
     if (h2d_bytes) *h2d_bytes = s->h2d_bytes;
     if (d2h_bytes) *d2h_bytes = s->d2h_bytes;
+    return KBBQ_OK;
+}
+
+int kbbq_host_pack_mode(int host_threads) { return pack_mode(host_threads); }
+
+int kbbq_host_last_traffic(int device, int64_t *h2d_bytes, int64_t *d2h_bytes) {
+    if (device < 0) return KBBQ_E_ARG;
+    int64_t up = 0, down = 0;
+    for (auto &c : g_cache) {
+        std::lock_guard<std::mutex> lock(c.mu);
+        if (c.s && c.s->device == device) { up += c.s->h2d_bytes; down += c.s->d2h_bytes; }
+    }
+    if (h2d_bytes) *h2d_bytes = up;
+    if (d2h_bytes) *d2h_bytes = down;
     return KBBQ_OK;
 }
 
@@ -820,6 +903,7 @@ int kbbq_recalibrate_fastq(const char *reads_path, const char *corrected_path, i
         if (k == 0) {   // bad input raises before anything is printed, as the reference's first pass does
             int st = 0;
             KBBQ_CUDA(cudaMemcpy(&st, S->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+            st |= S->host_status;
             if (st) { if (status_out) *status_out = st; return KBBQ_E_DATA; }
         }
         const int64_t bytes = off[(size_t)k + 1] - off[(size_t)k];

@@ -82,6 +82,10 @@ SIGNATURES = {
     "kbbq_fastq_format": (_i, [_vp, _i64, _i64, _vp, _vp, _i64, _i]),
     "kbbq_host_mismatch_bits": (_i, [_vp, _vp, _i64, _vp, _i]),
     "kbbq_expand_mismatch_bits": (_i, [_vp, _vp, _i64, _vp, _vp]),
+    "kbbq_host_last_traffic": (_i, [_i, C.POINTER(_i64), C.POINTER(_i64)]),
+    "kbbq_host_pack_mode": (_i, [_i]),
+    "kbbq_host_pack_nibbles": (_i, [_vp, _vp, _i64, _vp, _i, _vp]),
+    "kbbq_expand_nibbles": (_i, [_vp, _i64, _vp, _vp, _vp]),
     "kbbq_plan_info": (_i, [_i, _i, _i, _i, _i, C.POINTER(_i)]),
     "kbbq_segment_rows_bound": (_i64, [_i64, _i]),
     "kbbq_segment_table_elems": (_i64, [_i]),

@@ -238,18 +238,27 @@ def test_synthetic_configs_vs_oracle(torch_cuda, oracle_mod, case):
         assert np.array_equal(out.astype(np.int16), want_o), (path, splits)
 
 
-@pytest.mark.parametrize("bitmap", ["1", "0"])
+def _set_transport(monkeypatch, transport):
+    monkeypatch.setenv("KBBQ_HOST_BITMAP", "1")   # pack whatever the core count of the box
+    monkeypatch.setenv("KBBQ_HOST_NO_BITMAP", "1" if transport == "plain" else "0")
+    monkeypatch.setenv("KBBQ_HOST_NO_NIBBLES", "1" if transport == "bits" else "0")
+
+
+@pytest.mark.parametrize("transport", ["nibbles", "bits", "plain"])
 @pytest.mark.parametrize("streaming", ["0", "1"])
-def test_host_buffer_entry_point_chunked(oracle_mod, monkeypatch, streaming, bitmap):
-    """kbbq_recalibrate_host with several chunks, resident and two-pass streaming modes, the corrected
-    reads crossing PCIe as a mismatch bit map (default) or as they are."""
+@pytest.mark.parametrize("R", [4, 1])
+def test_host_buffer_entry_point_chunked(oracle_mod, monkeypatch, streaming, transport, R):
+    """kbbq_recalibrate_host with several chunks, resident and two-pass streaming modes, one and several read
+    groups; the reads and the corrected reads crossing PCIe as 4 bits per base (default), the corrected reads as
+    a mismatch bit map, or everything as it is."""
     from kbbq import _native, synth
-    N, L, R = 50_003, 151, 4   # odd sizes: the last chunk's bit map ends inside a word
+    N, L = 50_003, 151   # odd sizes: the last chunk's packed form ends inside a byte / word
     seq, qual, corr, rg, second = synth.synth_reads(11, 0, N, L, R)
     corr[::7, 3] = ord("N")    # corrected bases outside ACGT only have to differ
+    seq[::11, 5] = ord("N")
     monkeypatch.setenv("KBBQ_HOST_CHUNK_READS", "7000")
     monkeypatch.setenv("KBBQ_HOST_FORCE_STREAMING", streaming)
-    monkeypatch.setenv("KBBQ_HOST_NO_BITMAP", "0" if bitmap == "1" else "1")
+    _set_transport(monkeypatch, transport)
     out, tabs, dqs = _native.recalibrate_host(seq, qual, corr, rg, second, L, R, want_tables=True)
     want_t = oracle_mod.covariate_arrays(seq, qual, corr, rg, second, L, R)
     want_d = oracle_mod.get_delta_qs(*want_t)
@@ -260,6 +269,57 @@ def test_host_buffer_entry_point_chunked(oracle_mod, monkeypatch, streaming, bit
     for got, want in zip(dqs[1:], want_d):
         assert np.array_equal(got, want)
     assert np.array_equal(out.astype(np.int16), want_o)
+
+
+def test_expand_nibbles_kernel(torch_cuda):
+    """kbbq_expand_nibbles: the device side of kbbq_host_pack_nibbles -- seq comes back byte for byte, corr differs
+    from it exactly where the corrected read did."""
+    torch = torch_cuda
+    import ctypes as C
+    from kbbq import _native
+    lib = _native.lib()
+    rng = np.random.default_rng(12)
+    alphabet = np.frombuffer(b"ACGTN", np.uint8)
+    for n in (1, 31, 32, 33, 8192 * 3 + 7, 1_000_001):
+        seq = alphabet[rng.integers(0, 5, size=n)]
+        corr = seq.copy()
+        flip = rng.random(n) < 0.1
+        corr[flip] = alphabet[rng.integers(0, 5, size=int(flip.sum()))]
+        packed = np.zeros((n + 1) // 2, np.uint8)
+        bad = C.c_int(0)
+        assert lib.kbbq_host_pack_nibbles(_native.ptr(seq), _native.ptr(corr), n, _native.ptr(packed), 0, C.byref(bad)) == 0
+        d_packed = torch.from_numpy(packed).cuda()
+        d_seq = torch.full((n + 64,), 255, dtype=torch.uint8, device="cuda")
+        d_corr = torch.full((n + 64,), 255, dtype=torch.uint8, device="cuda")
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        _native.check(lib.kbbq_expand_nibbles(C.c_void_p(d_packed.data_ptr()), n, C.c_void_p(d_seq.data_ptr()),
+                                              C.c_void_p(d_corr.data_ptr()), st))
+        got_s, got_c = d_seq.cpu().numpy(), d_corr.cpu().numpy()
+        assert np.array_equal(got_s[:n], seq)
+        assert np.array_equal(got_c[:n] != got_s[:n], corr != seq)
+        assert np.all(got_s[n:] == 255) and np.all(got_c[n:] == 255)   # nothing written past the end
+
+
+@pytest.mark.parametrize("transport", ["nibbles", "bits", "plain"])
+def test_host_entry_point_input_errors(monkeypatch, transport):
+    """A base outside ACGTN -> TypeError, a quality above 42 -> IndexError through kbbq_recalibrate_host, whichever
+    form the reads cross PCIe in (with nibbles the base check happens on the host: the device never sees the byte)."""
+    from kbbq import _native, synth
+    N, L, R = 20_000, 100, 2
+    seq, qual, corr, rg, second = synth.synth_reads(21, 0, N, L, R)
+    monkeypatch.setenv("KBBQ_HOST_CHUNK_READS", "6000")
+    _set_transport(monkeypatch, transport)
+    for bad_byte in (ord("X"), ord("a"), ord("O"), 0):
+        s2 = seq.copy()
+        s2[13_333, 77] = bad_byte
+        with pytest.raises(TypeError):
+            _native.recalibrate_host(s2, qual, corr, rg, second, L, R)
+    q2 = qual.copy()
+    q2[19_999, 99] = 43
+    with pytest.raises(IndexError):
+        _native.recalibrate_host(seq, q2, corr, rg, second, L, R)
+    out = _native.recalibrate_host(seq, qual, corr, rg, second, L, R)   # the session recovers
+    assert out.shape == (N, L)
 
 
 def test_input_errors_raise_like_the_reference(torch_cuda):

@@ -164,3 +164,45 @@ def test_host_mismatch_bits_matches_numpy():
             got = bits[:(n + 31) // 32].view(np.uint8)[:want.size]
             assert np.array_equal(got, want), (n, threads)
             assert bits[(n + 31) // 32] == 0xDEADBEEF  # nothing written past the map
+
+
+def test_host_pack_nibbles_matches_numpy():
+    """kbbq_host_pack_nibbles (csrc/host_pack.cpp): 4 bits per base = (base >> 1) & 7 | mismatch << 3, two bases
+    per byte (even base in the low nibble); a byte outside ACGTN is reported, as the reference's TypeError is."""
+    import ctypes as C
+    from kbbq import _native
+    lib = _native.lib()
+    rng = np.random.default_rng(4)
+    alphabet = np.frombuffer(b"ACGTN", np.uint8)
+    for n in (0, 1, 2, 63, 64, 65, 2048 * 64 * 3 + 21, 1_000_003):
+        seq = alphabet[rng.integers(0, 5, size=n)]
+        corr = seq.copy()
+        flip = rng.random(n) < 0.05
+        corr[flip] = alphabet[rng.integers(0, 5, size=int(flip.sum()))]   # some of them equal again
+        for offset in (0, 1):   # destination 32-byte aligned (streaming stores) or not
+            buf = np.full((n + 1) // 2 + 33, 0xAB, np.uint8)
+            start = (-buf.ctypes.data) % 32 + offset
+            packed = buf[start:start + (n + 1) // 2 + 1]
+            for threads in (1, 0):
+                bad = C.c_int(-1)
+                assert lib.kbbq_host_pack_nibbles(_native.ptr(seq), _native.ptr(corr), n, _native.ptr(packed), threads, C.byref(bad)) == 0
+                assert bad.value == 0
+                nib = ((seq >> 1) & 7) | ((seq != corr).astype(np.uint8) << 3)
+                if n & 1:
+                    nib = np.append(nib, np.uint8(0))
+                want = nib[0::2] | (nib[1::2] << 4)
+                assert np.array_equal(packed[:(n + 1) // 2], want), (n, threads, offset)
+                assert packed[(n + 1) // 2] == 0xAB  # nothing written past the packed bases
+    # every byte value that is not one of ACGTN is reported, wherever it sits
+    n = 2048 * 64 * 2 + 5
+    seq = alphabet[rng.integers(0, 5, size=n)]
+    packed = np.zeros((n + 1) // 2, np.uint8)
+    for value in list(range(0, 256, 7)) + [ord("a"), ord("c"), ord("B"), ord("O"), ord("U"), 0x4F, 0xC1]:
+        if value in b"ACGTN":
+            continue
+        for pos in (0, 70, n // 2, n - 1):
+            s2 = seq.copy()
+            s2[pos] = value
+            bad = C.c_int(0)
+            assert lib.kbbq_host_pack_nibbles(_native.ptr(s2), _native.ptr(seq), n, _native.ptr(packed), 0, C.byref(bad)) == 0
+            assert bad.value == 1, (value, pos)

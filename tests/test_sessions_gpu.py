@@ -57,7 +57,7 @@ def test_session_chunks(oracle_mod, R, L, resident):
                   tabs[2 * npos:2 * npos + ndin].reshape(R, 43, 16), tabs[2 * npos + ndin:].reshape(R, 43, 16))
             _check(out, tt, dqs, want)
             h2d, d2h = s.traffic()
-            assert d2h == N * L and h2d > 2 * N * L
+            assert d2h == N * L and h2d > N * L   # qualities as they are + at least 4 bits per base for the reads
 
 
 def test_session_tables_add_up(oracle_mod):
