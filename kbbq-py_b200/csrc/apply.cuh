@@ -172,7 +172,12 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
                 const uint32_t res = (sum4 & vm8) | (qw & ~vm8);
                 // group base + this thread's offset inside the group (64-bit multiply-add, one instruction)
                 const unsigned long long dst = outp + (unsigned long long)hgrp * gbytes;
-                // three independent, predicated stores (the mode is a per-thread constant; no branch in the usual cases)
+                if (UNI) {
+                    // uniform walk: a live thread owns its whole word (make_thread_map) -- one predicated store
+                    if (st32) asm volatile("st.global.u32 [%0], %1;" ::"l"(dst), "r"(res) : "memory");
+                    return;
+                }
+                // work-list walk: a word that straddles two rows has two owners -- whole word, one aligned half, or bytes
                 if (st32) asm volatile("st.global.u32 [%0], %1;" ::"l"(dst), "r"(res) : "memory");
                 if (st16) asm volatile("st.global.u16 [%0], %1;" ::"l"(dst), "h"((unsigned short)(res >> wshift)) : "memory");
                 if (st8) {

@@ -171,7 +171,27 @@ __device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, const TableC
     m.rowmask = 0; m.toff = 0; m.selv = 0x4444u; m.seln = 0x4444u;
 #pragma unroll
     for (int b = 0; b < 4; ++b) { m.cell[b] = 0; m.cyc[b] = -1; }
-    if (m.row >= 0) {
+    if (by_parity) {
+        // Uniform walk: every row of a group is tallied and the table of a byte follows from the parity of its row, so
+        // nothing ties a thread to ONE row: lane t of the thread-group owns all four bytes of word t of the group,
+        // whichever rows they belong to (a word that straddles two reads has one owner instead of two half-owners; the
+        // lanes behind the last word idle).  Every live thread then writes whole aligned words in the apply kernel.
+        const int nwords = g.gbytes >> 2;
+        m.row = (t < nwords && m.grp < g.ng) ? (4 * t) / g.L : -1;
+        if (m.row >= 0) {
+            m.toff = 4 * t;
+            m.rowmask = 0xFFFFFFFFu;
+            m.selv = 0xBA98u;
+            m.seln = 0xBA98u;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int j = 4 * t + b, k = j / g.L, c = j - k * g.L;
+                m.cyc[b] = c;
+                if (c == 0) m.seln = (m.seln & ~(0xFu << (4 * b))) | (0x4u << (4 * b));
+                m.cell[b] = 4u * (uint32_t)((c & 3) * tc.sj + (c >> 2)) + (uint32_t)((k & 1) * tc.revoff);
+            }
+        }
+    } else if (m.row >= 0) {
         const int a = (m.row * g.L) & 3;
         m.toff = m.row * g.L - a + 4 * w;
 #pragma unroll
@@ -182,10 +202,11 @@ __device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, const TableC
                 m.rowmask |= 0xFFu << (8 * b);
                 m.selv = (m.selv & ~(0xFu << (4 * b))) | ((8u | b) << (4 * b));
                 if (c != 0) m.seln = (m.seln & ~(0xFu << (4 * b))) | ((8u | b) << (4 * b));
-                m.cell[b] = 4u * (uint32_t)((c & 3) * tc.sj + (c >> 2)) + (by_parity ? (uint32_t)((m.row & 1) * tc.revoff) : 0u);
+                m.cell[b] = 4u * (uint32_t)((c & 3) * tc.sj + (c >> 2));
             }
         }
-    } else {
+    }
+    if (m.row < 0) {
         // Idle lanes (the tail of the last warp) run along in full stages with nothing selected and tally into the
         // trash row: spread them over its banks instead of letting them collide on one cell.
 #pragma unroll

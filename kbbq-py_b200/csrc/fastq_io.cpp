@@ -91,6 +91,90 @@ inline const char *name_end(const char *h0, const char *h1) {
     return p;
 }
 
+// The usual file: every record is "@header LF, L bases LF, + LF, L qualities LF".  Once L is known from the first
+// record only the header lines have to be scanned: a record that starts at p ends at (end of its header) + 2 L + 5,
+// and the three line ends in between sit at fixed offsets.  Every thread finds the first record of its share of the
+// bytes (a line that starts with '@' and passes the fixed-offset checks: a quality line that starts with '@' fails
+// them, its "+" would have to be the first base of the next record), walks its records, and the walks have to meet:
+// thread t must stop exactly where thread t + 1 started.  Anything unusual (CR LF, reads of different lengths,
+// multi-line records, a malformed record) -> false, and build_index falls back to the general scan below, which
+// also produces the error codes.
+bool index_uniform_records(kbbq_fastq *f, int threads) {
+    const char *d = f->data;
+    const size_t len = f->len;
+    if (len < 8 || d[0] != '@') return false;
+    const char *end = d + len;
+    const char *h1 = (const char *)memchr(d, '\n', len);
+    if (!h1) return false;
+    const char *s1 = (const char *)memchr(h1 + 1, '\n', (size_t)(end - h1 - 1));
+    if (!s1) return false;
+    const int64_t L = s1 - h1 - 1;
+    if (L < 1) return false;
+    // p -> a record?  *next = start of the following record
+    auto record_at = [&](const char *p, const char **next) -> bool {
+        if (p >= end || *p != '@') return false;
+        const char *h = (const char *)memchr(p, '\n', (size_t)(end - p));
+        if (!h || h[-1] == '\r') return false;
+        const char *last = h + 2 * L + 4;   // the LF behind the qualities (or the end of a file without one)
+        if (last > end) return false;
+        if (h[L + 1] != '\n' || h[L + 2] != '+' || h[L + 3] != '\n' || h[L] == '\r') return false;
+        if (last < end && *last != '\n') return false;
+        if (last == end && end[-1] == '\n') return false;   // a short last record
+        *next = last < end ? last + 1 : end;
+        return true;
+    };
+    const int T = n_threads(threads, (int64_t)(len >> 20) + 1);
+    std::vector<std::vector<int64_t>> starts(T);
+    std::vector<const char *> first(T, nullptr), stop(T, nullptr);
+    std::vector<int> bad(T, 0);
+    parallel_for(T, [&](int t) {
+        const char *lo = d + len * (size_t)t / (size_t)T, *hi = d + len * (size_t)(t + 1) / (size_t)T;
+        const char *p = lo, *next = nullptr;
+        if (t > 0) {   // first line start in [lo, hi) that is a record
+            p = nullptr;
+            const char *q = lo - 1;
+            // a record is at most one header + 2 L + 5 bytes away; give up (empty share) at hi
+            while (q < hi) {
+                const char *nl = (const char *)memchr(q, '\n', (size_t)(hi - q));
+                if (!nl || nl + 1 >= hi) break;
+                if (nl[1] == '@' && record_at(nl + 1, &next)) { p = nl + 1; break; }
+                q = nl + 1;
+            }
+            if (!p) { first[t] = stop[t] = nullptr; return; }   // no record starts in this share
+        }
+        first[t] = p;
+        std::vector<int64_t> &v = starts[t];
+        v.reserve((size_t)(hi - p) / (size_t)(2 * L + 8) + 16);
+        while (p < hi) {
+            if (!record_at(p, &next)) { bad[t] = 1; return; }
+            v.push_back((int64_t)(p - d));
+            p = next;
+        }
+        stop[t] = p;
+    });
+    // the walks must meet
+    const char *expect = d;
+    int64_t n = 0;
+    for (int t = 0; t < T; ++t) {
+        if (bad[t]) return false;
+        if (!first[t]) continue;
+        if (first[t] != expect) return false;
+        expect = stop[t];
+        n += (int64_t)starts[t].size();
+    }
+    if (expect != end || n == 0) return false;
+    f->n = n;
+    f->L = (int)L;
+    f->rec.resize((size_t)n + 1);
+    std::vector<int64_t> base(T + 1, 0);
+    for (int t = 0; t < T; ++t) base[t + 1] = base[t] + (int64_t)starts[t].size();
+    parallel_for(T, [&](int t) {
+        if (!starts[t].empty()) memcpy(f->rec.data() + base[t], starts[t].data(), starts[t].size() * sizeof(int64_t));
+    });
+    f->rec[(size_t)n] = (int64_t)len;
+    return true;
+}
+
 int build_index(kbbq_fastq *f, int threads) {
     const char *d = f->data;
     size_t len = f->len;
@@ -101,6 +185,7 @@ int build_index(kbbq_fastq *f, int threads) {
     while (len > 0 && len == 1 && (d[0] == '\n' || d[0] == '\r')) len = 0;
     f->len = len;
     if (len == 0) { f->n = 0; f->L = 0; f->rec.assign(1, 0); return KBBQ_OK; }
+    if (!getenv("KBBQ_FASTQ_GENERAL_INDEX") && index_uniform_records(f, threads)) return KBBQ_OK;
     const int T = n_threads(threads, (int64_t)(len >> 20) + 1);
     std::vector<int64_t> lines(T + 1, 0);
     auto lo = [&](int t) { return len * (size_t)t / (size_t)T; };

@@ -193,7 +193,8 @@ bool want_segmode(int L, int R, int minscore, int64_t C) {
     return R > 1 && kbbq_segmented_supported(L, R, minscore) && (int64_t)32 * R * 8 <= C && env_flag_off("KBBQ_HOST_NO_SEGMENT");
 }
 
-int session_create(int device, int L, int R, int minscore, int64_t C, int64_t M, int host_threads, kbbq_session **out) {
+// pack < 0: the transport follows from the host threads this session has (pack_mode)
+int session_create(int device, int L, int R, int minscore, int64_t C, int64_t M, int host_threads, int pack, kbbq_session **out) {
     if (device < 0 || L < 1 || R < 1 || R > 65535 || C < 1 || M < 0 || !out) return KBBQ_E_ARG;
     KBBQ_CUDA(cudaSetDevice(device));
     std::unique_ptr<kbbq_session> S(new kbbq_session);
@@ -201,7 +202,7 @@ int session_create(int device, int L, int R, int minscore, int64_t C, int64_t M,
     S->C = (C + 15) / 16 * 16;
     S->M = M;
     S->host_threads = host_threads;
-    S->pack = pack_mode(host_threads);
+    S->pack = pack < 0 ? pack_mode(host_threads) : pack;
     S->segmode = want_segmode(L, R, minscore, S->C);
     S->rowsC = S->segmode ? kbbq_segment_rows_bound(S->C, R) : S->C;
     KBBQ_CUDA(cudaStreamCreateWithFlags(&S->s_up, cudaStreamNonBlocking));
@@ -495,14 +496,14 @@ struct CacheSlot {
 };
 CacheSlot g_cache[MAX_DEVICES];
 
-int cached_session(int slot, int device, int L, int R, int minscore, int64_t C, int64_t M, int host_threads,
+int cached_session(int slot, int device, int L, int R, int minscore, int64_t C, int64_t M, int host_threads, int pack,
                    kbbq_session **out) {
     CacheSlot &c = g_cache[slot];
     kbbq_session *s = c.s.get();
     const int64_t C16 = (C + 15) / 16 * 16;
     const int64_t nres = M ? (M + C16 - 1) / C16 : 0;
     if (s && s->device == device && s->L == L && s->R == R && s->minscore == minscore && s->C == C16 &&
-        (int64_t)s->res.size() >= nres && (nres > 0) == (s->M > 0) && s->pack == pack_mode(host_threads) &&
+        (int64_t)s->res.size() >= nres && (nres > 0) == (s->M > 0) && s->pack == (pack < 0 ? pack_mode(host_threads) : pack) &&
         s->segmode == want_segmode(L, R, minscore, C16)) {
         s->host_threads = host_threads;
         KBBQ_TRY(session_reset(s));
@@ -511,7 +512,7 @@ int cached_session(int slot, int device, int L, int R, int minscore, int64_t C, 
     }
     c.s.reset();
     kbbq_session *fresh = nullptr;
-    KBBQ_TRY(session_create(device, L, R, minscore, C, M, host_threads, &fresh));
+    KBBQ_TRY(session_create(device, L, R, minscore, C, M, host_threads, pack, &fresh));
     c.s.reset(fresh);
     *out = fresh;
     return KBBQ_OK;
@@ -595,7 +596,7 @@ extern "C" {
 int kbbq_session_create(int device, int L, int R, int minscore, int64_t chunk_reads, int64_t resident_reads_cap,
                         int host_threads, kbbq_session **out) {
     if (chunk_reads <= 0) chunk_reads = default_chunk_reads(L > 0 ? L : 1);
-    return session_create(device, L, R, minscore, chunk_reads, resident_reads_cap, host_threads, out);
+    return session_create(device, L, R, minscore, chunk_reads, resident_reads_cap, host_threads, -1, out);
 }
 
 void kbbq_session_destroy(kbbq_session *s) { delete s; }
@@ -741,16 +742,25 @@ PinnedCache g_pinned;
 
 struct FastqPair {
     kbbq_fastq *reads = nullptr, *corr = nullptr;
-    ~FastqPair() { kbbq_fastq_close(reads); kbbq_fastq_close(corr); }
+    // unmapping two large files and freeing their indices takes milliseconds nobody has to wait for
+    ~FastqPair() {
+        kbbq_fastq *a = reads, *b = corr;
+        if (!a && !b) return;
+        try { std::thread([a, b] { kbbq_fastq_close(a); kbbq_fastq_close(b); }).detach(); }
+        catch (...) { kbbq_fastq_close(a); kbbq_fastq_close(b); }
+    }
 };
 
 struct OutputMap {   // the output file mapped read-write (fastq_io.cpp: kbbq_fastq_write), or a buffer + write()
-    int fd = -1;
-    off_t pos0 = 0, base = 0;
+    int fd = -1, rw = -1;
+    off_t pos0 = 0, base = 0, size0 = 0;
     char *map = nullptr;
     size_t span = 0;
     int64_t total = 0;
+    bool finished = false;
     std::vector<char> buf;
+    std::thread ahead;
+    std::atomic<bool> stop{false};
     int open_for(int out_fd, int64_t bytes) {
         fd = out_fd;
         total = bytes;
@@ -761,16 +771,31 @@ struct OutputMap {   // the output file mapped read-write (fastq_io.cpp: kbbq_fa
             !getenv("KBBQ_FASTQ_NO_MMAP")) {
             char link[64];
             snprintf(link, sizeof(link), "/proc/self/fd/%d", fd);
-            const int rw = open(link, O_RDWR);
+            rw = open(link, O_RDWR);
             if (rw >= 0) {
                 const long page = sysconf(_SC_PAGESIZE);
+                size0 = st.st_size;
                 base = pos0 / page * page;
                 span = (size_t)(pos0 - base) + (size_t)bytes;
                 void *m = MAP_FAILED;
                 if (ftruncate(rw, pos0 + (off_t)bytes) == 0) m = mmap(nullptr, span, PROT_READ | PROT_WRITE, MAP_SHARED, rw, base);
-                close(rw);
                 if (m != MAP_FAILED) map = (char *)m;
+                else { if (ftruncate(rw, size0)) {} close(rw); rw = -1; }
             }
+        }
+        // A new file's pages are instantiated one fault at a time, and adding a page to the file is serialised per
+        // file (~8 GB/s into a tmpfs however many threads write).  One background thread allocates the blocks ahead
+        // of the formatting threads with fallocate -- no zeroing, no mapping -- while the reads are still being
+        // tokenised and built; the faults behind it only zero and map.  (Pre-faulting with MADV_POPULATE_WRITE,
+        // which zeroes and maps as well, was measured slower than plain faults.)  KBBQ_FASTQ_NO_FALLOCATE=1: off.
+        if (map && !getenv("KBBQ_FASTQ_NO_FALLOCATE")) {
+            ahead = std::thread([this] {
+                const off_t slice = (off_t)32 << 20;
+                for (off_t o = 0; o < (off_t)total && !stop.load(std::memory_order_relaxed); o += slice) {
+                    const off_t n = std::min<off_t>(slice, (off_t)total - o);
+                    if (fallocate(rw, 0, pos0 + o, n) != 0) break;   // not supported here: plain faults do the work
+                }
+            });
         }
         return KBBQ_OK;
     }
@@ -791,15 +816,33 @@ struct OutputMap {   // the output file mapped read-write (fastq_io.cpp: kbbq_fa
         }
         return KBBQ_OK;
     }
+    void join_ahead() {
+        stop.store(true);
+        if (ahead.joinable()) ahead.join();
+    }
     int finish() {
+        join_ahead();
+        finished = true;
         if (map) {
-            munmap(map, span);
+            // the text is in the page cache whether or not this process still maps it: tearing the mapping down
+            // (one page-table entry per 4 KB) is left to a thread nobody waits for
+            char *m = map;
+            const size_t len = span;
             map = nullptr;
+            try { std::thread([m, len] { munmap(m, len); }).detach(); }
+            catch (...) { munmap(m, len); }
             if (lseek(fd, pos0 + (off_t)total, SEEK_SET) < 0) return KBBQ_E_IO;
         }
         return KBBQ_OK;
     }
-    ~OutputMap() { if (map) munmap(map, span); }
+    ~OutputMap() {
+        join_ahead();
+        if (map) munmap(map, span);
+        // an error before the end: nothing has been printed as far as the caller is concerned (the reference raises
+        // in its first pass, before any output), so the file gets its size back
+        if (rw >= 0 && !finished && ftruncate(rw, size0)) {}
+        if (rw >= 0) close(rw);
+    }
 };
 
 }  // namespace
@@ -836,6 +879,23 @@ int kbbq_recalibrate_fastq(const char *reads_path, const char *corrected_path, i
     if (L < 0 || kbbq_fastq_read_len(fq.corr) != L) return KBBQ_E_RAGGED;
     if (L < 1) return KBBQ_E_FORMAT;
 
+    int64_t C = 262144;
+    if (const char *e = getenv("KBBQ_FASTQ_CHUNK_READS")) C = std::max<int64_t>(16, atoll(e));
+    C = std::min<int64_t>((C + 15) / 16 * 16, (n + 15) / 16 * 16);
+    const int64_t nchunks = (n + C - 1) / C;
+    // where every chunk's text goes.  The output is sized, mapped and its blocks allocated (by a background thread)
+    // before anything else: the later that starts, the more of it is left for pass 2 to wait for.  Every error
+    // return below gives the file its size back (~OutputMap).
+    std::vector<int64_t> off((size_t)nchunks + 1, 0);
+    for (int64_t k = 0; k < nchunks; ++k) {
+        int64_t b = 0;
+        KBBQ_TRY(kbbq_fastq_format_size(fq.reads, k * C, std::min(C, n - k * C), T, &b));
+        off[(size_t)k + 1] = off[(size_t)k] + b;
+    }
+    OutputMap out;
+    KBBQ_TRY(out.open_for(out_fd, off[(size_t)nchunks]));
+    stamp("output sized and mapped");
+
     std::vector<uint16_t> rg((size_t)n);
     std::vector<uint8_t> second((size_t)n);
     int R = 1;
@@ -851,16 +911,14 @@ int kbbq_recalibrate_fastq(const char *reads_path, const char *corrected_path, i
     if (n_rg_out) *n_rg_out = R;
     stamp("names checked, groups inferred");
 
-    int64_t C = 262144;
-    if (const char *e = getenv("KBBQ_FASTQ_CHUNK_READS")) C = std::max<int64_t>(16, atoll(e));
-    C = std::min<int64_t>((C + 15) / 16 * 16, (n + 15) / 16 * 16);
-    const int64_t nchunks = (n + C - 1) / C;
     KBBQ_CUDA(cudaSetDevice(device));
     std::unique_lock<std::mutex> cache_lock(g_cache[0].mu);
     size_t ours = g_cache[0].s && g_cache[0].s->device == device ? g_cache[0].s->cap : 0;
     if (resident_reads(device, n, L, R, C, ours) == 0) return KBBQ_E_UNSUPPORTED;   // larger than the device: chunked driver
     kbbq_session *S = nullptr;
-    KBBQ_TRY(cached_session(0, device, L, R, minscore, C, n, T, &S));
+    // every core is busy tokenising and the copy engine has time to spare (3 B per base at 55 GB/s against 10 GB/s
+    // of FASTQ text): the chunks cross PCIe as they are, no packing pass (KBBQ_FASTQ_PACK=1: as the host-buffer path)
+    KBBQ_TRY(cached_session(0, device, L, R, minscore, C, n, T, env_flag_off("KBBQ_FASTQ_PACK") ? PACK_NONE : -1, &S));
     const size_t cb = (size_t)C * L;
     std::lock_guard<std::mutex> pin_lock(g_pinned.mu);
     KBBQ_TRY(g_pinned.ensure(8 * cb));
@@ -868,21 +926,6 @@ int kbbq_recalibrate_fastq(const char *reads_path, const char *corrected_path, i
     uint8_t *h_seq[2] = {pin, pin + cb}, *h_qual[2] = {pin + 2 * cb, pin + 3 * cb}, *h_corr[2] = {pin + 4 * cb, pin + 5 * cb},
             *h_out[2] = {pin + 6 * cb, pin + 7 * cb};
     stamp("session and staging ready");
-
-    // where every chunk's text goes
-    std::vector<int64_t> off((size_t)nchunks + 1, 0);
-    for (int64_t k = 0; k < nchunks; ++k) {
-        int64_t b = 0;
-        KBBQ_TRY(kbbq_fastq_format_size(fq.reads, k * C, std::min(C, n - k * C), T, &b));
-        off[(size_t)k + 1] = off[(size_t)k] + b;
-    }
-    OutputMap out;
-    KBBQ_TRY(out.open_for(out_fd, off[(size_t)nchunks]));
-    stamp("output sized and mapped");
-    // (A new file's pages are instantiated one fault at a time under the mapping's lock, ~8 GB/s into a tmpfs however
-    // many threads write.  Pre-faulting with MADV_POPULATE_WRITE -- every formatting thread its own share, or one
-    // background thread running ahead during pass 1 -- was measured slower than plain faults: 245 -> 283 ms and
-    // 225 -> 252 ms for 2 M x 150 bp.)
 
     // pass 1: tokenise a chunk into a pinned slot while the previous one is on its way to the device
     for (int64_t k = 0; k < nchunks; ++k) {
@@ -979,7 +1022,7 @@ int kbbq_recalibrate_host_multi(const uint8_t *seq, const uint8_t *qual, const u
         size_t ours = 0;
         for (int j = 0; j < n_dev; ++j)
             if (g_cache[j].s && g_cache[j].s->device == devices[i]) ours += j == i ? g_cache[j].s->cap : 0;
-        KBBQ_TRY(cached_session(i, devices[i], L, R, minscore, C, resident_reads(devices[i], n, L, R, C, ours), host_threads, &S[i]));
+        KBBQ_TRY(cached_session(i, devices[i], L, R, minscore, C, resident_reads(devices[i], n, L, R, C, ours), host_threads, -1, &S[i]));
     }
 
     std::vector<int> rcs((size_t)n_dev, KBBQ_OK), sts((size_t)n_dev, 0);

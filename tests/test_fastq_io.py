@@ -232,3 +232,49 @@ def test_writer_mapped_equals_plain(tmp_path, monkeypatch, flags):
     assert _native.lib().kbbq_fastq_format(f._h, 0, f.N, _native.ptr(out), _native.ptr(buf), nbytes.value, 4) == 0
     assert buf.tobytes() == texts[0][len(b"# header line\n"):]
     f.close()
+
+
+@pytest.mark.parametrize("final", [True, False])
+def test_uniform_record_index_equals_general_scan(tmp_path, monkeypatch, final):
+    """The header-only index of uniform files (every thread finds the first record of its share of the bytes and
+    the walks have to meet) against the general newline scan, on a file built to mislead the search for a record
+    start: most quality lines begin with '@', and headers are exactly as long as a read, so that a quality line
+    taken for a header finds a line end where it expects one."""
+    rng = np.random.default_rng(17)
+    L, n = 23, 120_000   # ~6 MB: several threads take part
+    bases = np.frombuffer(b"ACGTN", np.uint8)[rng.integers(0, 5, (n, L))]
+    quals = rng.integers(35, 74, (n, L)).astype(np.uint8)
+    quals[rng.random(n) < 0.8, 0] = ord("@")
+    quals[rng.random(n) < 0.3, :] = ord("@")
+    lines = []
+    for i in range(n):
+        name = ("r%d/%d" % (i // 2, 1 + (i & 1))).ljust(L - 1, "x") if i % 3 else "r%d/%d" % (i // 2, 1 + (i & 1))
+        lines.append(b"@" + name.encode() + b"\n" + bases[i].tobytes() + b"\n+\n" + quals[i].tobytes())
+    text = b"\n".join(lines) + (b"\n" if final else b"")
+    p = tmp_path / "tricky.fq"
+    p.write_bytes(text)
+    got = {}
+    for general in ("", "1"):
+        if general:
+            monkeypatch.setenv("KBBQ_FASTQ_GENERAL_INDEX", "1")
+        for threads in (1, 7):
+            f = fastx.NativeFastq(p, threads=threads)
+            assert f.N == n and f.L == L
+            seq, qual = f.pack()
+            got[(general, threads)] = (seq, qual, [f.name(i) for i in (0, 1, n // 2, n - 2, n - 1)])
+            f.close()
+    ref = got[("1", 1)]
+    assert np.array_equal(ref[0], bases) and np.array_equal(ref[1], quals - 33)
+    for key, (seq, qual, names) in got.items():
+        assert np.array_equal(seq, ref[0]) and np.array_equal(qual, ref[1]) and names == ref[2], key
+    # one record in the middle a base short: both paths agree that the reads differ in length
+    bad = lines[:]
+    bad[n // 2] = bad[n // 2].replace(b"\n+\n", b"\n+\n", 1)[:len(bad[n // 2]) - 1]
+    seq_line = bad[n // 2].split(b"\n")
+    seq_line[1] = seq_line[1][:-1]
+    bad[n // 2] = b"\n".join(seq_line)
+    p.write_bytes(b"\n".join(bad) + b"\n")
+    monkeypatch.delenv("KBBQ_FASTQ_GENERAL_INDEX")
+    f = fastx.NativeFastq(p, threads=7)
+    assert f.N == n and f.L == -1
+    f.close()
