@@ -50,7 +50,7 @@ struct TableCfg {
     int nrows;        // 44 - minscore (row 0 = trash)
     int rs;           // cycle table: row stride in bytes, multiple of 128
     int sj;           // plane stride in words: cell of cycle c at word (c & 3) * sj + (c >> 2)
-    int revoff;       // bytes from the first cycle table (slot 0) to the second (slot 1) = nrows * rs
+    int revoff;       // bytes from the first cycle table (slot 0) to the second (slot 1) = nrows * rs + the bank displacement
     int dq;           // dinuc table: row stride in bytes = 16 slots x drep replicas x 4
     int drep;         // replicas of the dinuc table (32: bank == lane; 16: lanes l and l + 16 share one)
     int pos_off, din_off;            // byte offsets from the start of dynamic shared memory
@@ -66,6 +66,33 @@ struct TableCfg {
     uint32_t val16[2];  // {1 | 16 << 16, 256 | 4096 << 16}: packs the 3-bit codes of four bases into four selector nibbles
 };
 
+// Shared-memory wavefronts of one pass of the CTA's consumer warps over the cycle tables in the uniform walk (every
+// lane one access per byte position, rows -- i.e. addresses -- all different in the worst case): for every warp and
+// byte position the largest number of lanes that meet in one bank.  `shift` = words by which the second table is
+// displaced from a whole number of bank rows.  Thread-groups (76 lanes for a pair of 150 bp reads) are packed back to
+// back, so a warp holds the tail of one row or group and the head of the next, whose bank ranges overlap; the
+// displacement moves the overlap of the row-0 / row-1 transition.  Host side, a few 10 000 operations.
+inline int cycle_table_wavefronts(const Geom &g, int sj, int rs_words, int shift) {
+    const int nwords = g.gbytes >> 2;
+    int total = 0;
+    for (int warp = 0; warp < g.threads / 32; ++warp)
+        for (int b = 0; b < 4; ++b) {
+            int cnt[32] = {0}, worst = 0;
+            for (int lane = 0; lane < 32; ++lane) {
+                const int tid = warp * 32 + lane, grp = tid / g.lps, t = tid - grp * g.lps;
+                int cell;
+                if (grp >= g.ng || t >= nwords) cell = (lane + 32 * b) % rs_words;   // idle lanes: make_thread_map
+                else {
+                    const int j = 4 * t + b, k = j / g.L, c = j - k * g.L;
+                    cell = (c & 3) * sj + (c >> 2) + (k & 1) * shift;
+                }
+                worst = std::max(worst, ++cnt[cell & 31]);
+            }
+            total += worst;
+        }
+    return total;
+}
+
 inline bool make_table_cfg(const Geom &g, int kps, int drep, TableCfg *t) {
     if (g.minscore < 1) return false;  // row 0 is the trash row
     if (drep != 32 && drep != 16 && drep != 8) return false;
@@ -73,11 +100,22 @@ inline bool make_table_cfg(const Geom &g, int kps, int drep, TableCfg *t) {
     t->sj = (g.L + 3) / 4;
     t->rs = (16 * t->sj + 127) / 128 * 128;            // 4 planes x sj words, rounded to whole bank rows
     if (t->rs > 1152) return false;                      // L <= 288: longer reads take the generic kernels
-    t->revoff = t->nrows * t->rs;
+    // the second cycle table starts `shift` words past a whole number of bank rows: the displacement with the fewest
+    // modelled bank conflicts (150 bp: 17 words, 209 wavefronts per pass instead of 240; 124 would be conflict free)
+    int shift = 0;
+    if (const char *e = getenv("KBBQ_SLOT_SHIFT")) shift = std::max(0, std::min(31, atoi(e)));   // tuning hook
+    else {
+        int best = cycle_table_wavefronts(g, t->sj, t->rs / 4, 0);
+        for (int d = 1; d < 32; ++d) {
+            const int w = cycle_table_wavefronts(g, t->sj, t->rs / 4, d);
+            if (w < best) { best = w; shift = d; }
+        }
+    }
+    t->revoff = t->nrows * t->rs + 4 * shift;
     t->drep = drep;
     t->dq = DIN_SLOTS * drep * 4;
     t->pos_off = 0;
-    t->din_off = 2 * t->revoff;
+    t->din_off = (t->revoff + t->nrows * t->rs + 127) / 128 * 128;
     t->table_bytes = t->din_off + t->nrows * t->dq;
     // a cycle cell is hit at most once per (thread-group, row) and iteration; a dinuc replica cell
     // at most 4 times per thread of that lane id and iteration

@@ -16,6 +16,11 @@
 #include <zlib.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <cstdio>
 #include <cstdint>
 #include <cstdlib>
@@ -49,12 +54,92 @@ int n_threads(int want, int64_t work_items) {
     return t;
 }
 
+// Worker threads kept between calls: the FASTQ pipeline runs some forty short parallel loops per file pair, and
+// creating and joining sixteen threads for each costs more than some of the loops themselves.  Any number of callers
+// may run loops at the same time (both files are indexed at once): the pool grows to the demand of all running
+// loops, so a task never waits for a worker that is blocked in somebody else's loop.  The pool is never destroyed
+// (its threads end with the process) and is rebuilt in a forked child.
+class WorkerPool {
+public:
+    static WorkerPool &get() {
+        static WorkerPool *p = new WorkerPool;   // leaked on purpose
+        return *p;
+    }
+    // run f(1) .. f(n_tasks) on workers; the caller runs f(0) itself and then waits
+    template <class F> void run(int n_tasks, F &f) {
+        struct Join { std::mutex m; std::condition_variable c; int left; } j;
+        j.left = n_tasks;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            if (owner_ != getpid()) {   // forked: the parent's threads do not exist here
+                for (auto &w : workers_) w.release();
+                workers_.clear();
+                queue_.clear();
+                idle_ = 0;
+                owner_ = getpid();
+            }
+            for (int t = 1; t <= n_tasks; ++t)
+                queue_.emplace_back([&f, &j, t] {
+                    f(t);
+                    std::lock_guard<std::mutex> g(j.m);
+                    if (--j.left == 0) j.c.notify_one();
+                });
+            // every queued task gets a worker: idle ones first, new ones for the rest
+            const int need = (int)queue_.size() - idle_;
+            for (int i = 0; i < need && (int)workers_.size() < kMaxWorkers; ++i)
+                workers_.emplace_back(new std::thread([this] { loop(); }));
+        }
+        cv_.notify_all();
+        f(0);
+        // help with whatever is still queued (ours or not) instead of sleeping, then wait for our tasks in flight
+        for (;;) {
+            std::function<void()> task;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (queue_.empty()) break;
+                task = std::move(queue_.front());
+                queue_.pop_front();
+            }
+            task();
+        }
+        std::unique_lock<std::mutex> g(j.m);
+        j.c.wait(g, [&] { return j.left == 0; });
+    }
+
+private:
+    static constexpr int kMaxWorkers = 256;
+    void loop() {
+        for (;;) {
+            std::function<void()> task;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                ++idle_;
+                cv_.wait(lk, [&] { return !queue_.empty(); });
+                --idle_;
+                task = std::move(queue_.front());
+                queue_.pop_front();
+            }
+            task();
+        }
+    }
+    std::mutex mu_;
+    std::condition_variable cv_;
+    std::deque<std::function<void()>> queue_;
+    std::vector<std::unique_ptr<std::thread>> workers_;
+    int idle_ = 0;
+    pid_t owner_ = getpid();
+};
+
 template <class F> void parallel_for(int threads, F f) {  // f(thread index)
     if (threads <= 1) { f(0); return; }
-    std::vector<std::thread> pool;
-    pool.reserve(threads);
-    for (int t = 0; t < threads; ++t) pool.emplace_back(f, t);
-    for (auto &th : pool) th.join();
+    if (getenv("KBBQ_FASTQ_NO_POOL")) {   // a thread per index, as before the pool
+        std::vector<std::thread> pool;
+        pool.reserve(threads);
+        for (int t = 0; t < threads; ++t) pool.emplace_back(f, t);
+        for (auto &th : pool) th.join();
+        return;
+    }
+    WorkerPool::get().run(threads - 1, f);
 }
 
 inline const char *line_end(const char *p, const char *end) {

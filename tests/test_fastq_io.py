@@ -278,3 +278,39 @@ def test_uniform_record_index_equals_general_scan(tmp_path, monkeypatch, final):
     f = fastx.NativeFastq(p, threads=7)
     assert f.N == n and f.L == -1
     f.close()
+
+
+@pytest.mark.parametrize("pool", ["1", "0"])
+def test_parallel_loops_from_several_callers(tmp_path, monkeypatch, pool):
+    """The native loops share one pool of worker threads; several callers may be inside it at once (both FASTQ
+    files of a run are indexed at the same time).  Same results as a thread per index (KBBQ_FASTQ_NO_POOL)."""
+    import threading
+    if pool == "0":
+        monkeypatch.setenv("KBBQ_FASTQ_NO_POOL", "1")
+    rng = np.random.default_rng(23)
+    recs = _random_records(rng, 30_000, 60)
+    p = tmp_path / "x.fq"
+    _write(p, recs)
+    want_seq = np.array([list(r[2].encode()) for r in recs], np.uint8)
+    errors = []
+
+    def work(k):
+        try:
+            for rep in range(3):
+                f = fastx.NativeFastq(p, threads=2 + (k + rep) % 7)
+                assert f.N == len(recs) and f.L == 60
+                rg, second, keys = f.infer(True)
+                seq, qual = f.pack()
+                assert np.array_equal(seq, want_seq)
+                assert len(keys) == 5 and int(second.sum()) == len(recs) // 2
+                f.close()
+        except Exception as e:   # noqa: BLE001 -- reported by the main thread
+            errors.append(repr(e))
+
+    callers = [threading.Thread(target=work, args=(k,)) for k in range(6)]
+    for c in callers:
+        c.start()
+    for c in callers:
+        c.join(timeout=120)
+    assert not any(c.is_alive() for c in callers), "a caller is stuck in the worker pool"
+    assert errors == []
