@@ -359,46 +359,62 @@ def time_hot_path(hp, K, W, world, barrier, use_graph=True, sampler_factory=None
     launches = lib.kbbq_launch_count() - launches0
     eager_ms = parallel.max_over_ranks(t0.elapsed_time(t1), dev)
     graph_ms = None
+    eager_phases = None
     if use_graph:
         # the collective stays outside the captures (NCCL inside a capture hung on this pool): one graph up to the
         # build, the eager all-reduce, one graph from the model on
-        g1 = g2 = None
+        g1 = g2 = g3 = None
         try:
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
                 rec.tables.zero_()
                 hp.build()
             with torch.cuda.graph(g2):
                 rec.model()
+            with torch.cuda.graph(g3):
                 hp.apply()
             torch.cuda.synchronize()
         except Exception as exc:  # capture not possible: the eager figure stands
             sys.stderr.write("bench.py: CUDA graph capture failed (%r); reporting the eager loop\n" % (exc,))
-            g1 = g2 = None
+            g1 = g2 = g3 = None
 
-        def replay():
+        def replay(ev=None):
+            if ev:
+                ev[0].record()
             g1.replay()
+            if ev:
+                ev[1].record()
             rec.allreduce()
             g2.replay()
+            if ev:
+                ev[2].record()
+            g3.replay()
+            if ev:
+                ev[3].record()
 
         if parallel.max_over_ranks(0.0 if g1 is not None else 1.0, dev) == 0.0:   # every rank replays or none does
             for _ in range(W):
                 replay()
             barrier()
+            gevs = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(K)]
             t0.record()
-            for _ in range(K):
-                replay()
+            for k in range(K):
+                replay(gevs[k])
             t1.record()
             barrier()
             graph_ms = parallel.max_over_ranks(t0.elapsed_time(t1), dev)
             rec.check_status()
+            eager_phases = {"build_ms": statistics.mean(e[0].elapsed_time(e[1]) for e in evs),
+                            "model_ms": statistics.mean(e[1].elapsed_time(e[2]) for e in evs),
+                            "apply_ms": statistics.mean(e[2].elapsed_time(e[3]) for e in evs)}
+            evs = gevs   # the per-phase times reported are those of the loop `value` comes from
     clocks = sampler.stop() if sampler else None   # sampled over both timed loops
     rec.check_status()
     build_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
     model_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
     apply_ms = statistics.mean(e[2].elapsed_time(e[3]) for e in evs)
     return {"K": K, "W": W, "eager_ms": eager_ms, "graph_ms": graph_ms, "build_ms": build_ms, "model_ms": model_ms,
-            "apply_ms": apply_ms, "launches": int(launches), "clocks": clocks}
+            "apply_ms": apply_ms, "launches": int(launches), "clocks": clocks, "eager_phases": eager_phases}
 
 
 def kernel_table(t, bases, peak):
@@ -803,15 +819,19 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["gbs"], "peak": peak, "unit": "GB/s",
                      "frac": kernels[dom]["frac_of_peak"], "traffic": traffic["bytes"] if traffic else None,
                      "traffic_source": traffic, "peak_source": peak_src,
-                     "timing": "CUDA events on the launching stream around the kbbq_build* / kbbq_apply* call in the eager "
-                               "timed loop (includes the < 1 % pre-pass kernels)",
+                     "timing": "CUDA events on the launching stream around the build phase (table reset, pre-pass kernels "
+                               "< 1 %, kbbq_build*) and the apply phase of every step of the timed loop `value` comes "
+                               "from" + (" (graph replay: one graph per phase)" if t["graph_ms"] is not None else " (eager)"),
                      "build_plus_apply_gbs": combined, "build_plus_apply_frac": combined / peak},
         "kernels": kernels,
         "phase_ms": {"build": t["build_ms"], "allreduce+model": t["model_ms"], "apply": t["apply_ms"]},
         "launch": {"mode": "CUDA graph replay" if t["graph_ms"] is not None else "eager",
                    "eager_ms_per_step": t["eager_ms"] / K,
-                   "note": "`value` = the replayed step; `phase_ms`, `kernels` and `roofline` come from the eager loop, "
-                           "which carries the per-phase events"},
+                   "eager_phase_ms": ({"build": t["eager_phases"]["build_ms"], "allreduce+model": t["eager_phases"]["model_ms"],
+                                       "apply": t["eager_phases"]["apply_ms"]} if t.get("eager_phases") else None),
+                   "note": "`value`, `phase_ms`, `kernels` and `roofline` all come from the same timed loop: the step "
+                           "replayed from one CUDA graph per phase (build | model | apply) around the eager all-reduce; "
+                           "the eager launch loop is reported next to it"},
         "gpu_launches": t["launches"],
         "clocks": t["clocks"],
     })

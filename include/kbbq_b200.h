@@ -276,6 +276,10 @@ int kbbq_host_pack_mode(int host_threads);
  *                 host_threads = host threads for the mismatch map (<= 0: all)
  *   build_chunk   pass 1 of a chunk: upload + build, accumulating into the session's tables.  Returns once the
  *                 host buffers have been read (they may be reused); the build itself runs behind.
+ *   build_range   pass 1 of n reads that lie contiguously in host memory, cut into chunks by the session and
+ *                 pipelined across them: the copies of chunk k + 1 are queued before the host cores pack chunk k,
+ *                 which a chunk-by-chunk caller cannot do.  Chunks stay resident iff the session was created with
+ *                 resident_reads_cap > 0; they are numbered on from the chunks already built.
  *   tables / set_tables / tables_dev   the partial tables [pos_errs | pos_total | din_errs | din_total] for sums
  *                 over sessions or ranks (tables_dev: device pointer, element count and the session's compute
  *                 stream; call kbbq_session_flush before touching them from another stream)
@@ -295,6 +299,8 @@ int64_t kbbq_session_chunk_reads(const kbbq_session *s);
 int kbbq_session_reset(kbbq_session *s);
 int kbbq_session_build_chunk(kbbq_session *s, const uint8_t *seq, const uint8_t *qual, const uint8_t *corr,
                              const uint16_t *rg, const uint8_t *second, int64_t n, int keep_resident);
+int kbbq_session_build_range(kbbq_session *s, const uint8_t *seq, const uint8_t *qual, const uint8_t *corr,
+                             const uint16_t *rg, const uint8_t *second, int64_t n);
 int kbbq_session_tables(kbbq_session *s, int64_t *tables_host);
 int kbbq_session_set_tables(kbbq_session *s, const int64_t *tables_host);
 int kbbq_session_tables_dev(kbbq_session *s, int64_t **tables_dev, int64_t *elems, void **stream);

@@ -50,7 +50,7 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
     const StageLayout &sl = a.sl;
     const int nconsumers = g.threads;
     const uint32_t bar0 = pin(smem_u32(smem_raw + sl.bar_off));
-    const ThreadMap m = make_thread_map(g, t, UNI);
+    const ThreadMap m = make_thread_map(g, t, UNI, true);
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
     const uint32_t din_base = pin(smem_addr(smem_raw + t.din_off) + (lane & (t.drep - 1)) * 4);

@@ -72,7 +72,7 @@ struct TableCfg {
 // displaced from a whole number of bank rows.  Thread-groups (76 lanes for a pair of 150 bp reads) are packed back to
 // back, so a warp holds the tail of one row or group and the head of the next, whose bank ranges overlap; the
 // displacement moves the overlap of the row-0 / row-1 transition.  Host side, a few 10 000 operations.
-inline int cycle_table_wavefronts(const Geom &g, int sj, int rs_words, int shift) {
+inline int cycle_table_wavefronts(const Geom &g, int sj, int rs_words, int shift, bool word_owner) {
     const int nwords = g.gbytes >> 2;
     int total = 0;
     for (int warp = 0; warp < g.threads / 32; ++warp)
@@ -80,11 +80,18 @@ inline int cycle_table_wavefronts(const Geom &g, int sj, int rs_words, int shift
             int cnt[32] = {0}, worst = 0;
             for (int lane = 0; lane < 32; ++lane) {
                 const int tid = warp * 32 + lane, grp = tid / g.lps, t = tid - grp * g.lps;
-                int cell;
-                if (grp >= g.ng || t >= nwords) cell = (lane + 32 * b) % rs_words;   // idle lanes: make_thread_map
-                else {
-                    const int j = 4 * t + b, k = j / g.L, c = j - k * g.L;
-                    cell = (c & 3) * sj + (c >> 2) + (k & 1) * shift;
+                int cell = (lane + 32 * b) % rs_words;   // idle lanes: make_thread_map
+                if (grp < g.ng && word_owner) {          // lane t owns word t of the group
+                    if (t < nwords) {
+                        const int j = 4 * t + b, k = j / g.L, c = j - k * g.L;
+                        cell = (c & 3) * sj + (c >> 2) + (k & 1) * shift;
+                    }
+                } else if (grp < g.ng) {                 // lane t owns one (row, word); foreign bytes go to cell 0
+                    for (int k = 0; k < g.G; ++k)
+                        if (t >= g.wstart[k] && t < g.wstart[k + 1]) {
+                            const int c = 4 * (t - g.wstart[k]) + b - ((k * g.L) & 3);
+                            cell = c >= 0 && c < g.L ? (c & 3) * sj + (c >> 2) + (k & 1) * shift : 0;
+                        }
                 }
                 worst = std::max(worst, ++cnt[cell & 31]);
             }
@@ -93,7 +100,9 @@ inline int cycle_table_wavefronts(const Geom &g, int sj, int rs_words, int shift
     return total;
 }
 
-inline bool make_table_cfg(const Geom &g, int kps, int drep, TableCfg *t) {
+// word_owner: which ownership the uniform walk of this kernel uses (make_thread_map): the apply kernel lets a lane own
+// a whole word of its group, the build kernel one (row, word)
+inline bool make_table_cfg(const Geom &g, int kps, int drep, bool word_owner, TableCfg *t) {
     if (g.minscore < 1) return false;  // row 0 is the trash row
     if (drep != 32 && drep != 16 && drep != 8) return false;
     t->nrows = NQ + 1 - g.minscore;
@@ -101,13 +110,14 @@ inline bool make_table_cfg(const Geom &g, int kps, int drep, TableCfg *t) {
     t->rs = (16 * t->sj + 127) / 128 * 128;            // 4 planes x sj words, rounded to whole bank rows
     if (t->rs > 1152) return false;                      // L <= 288: longer reads take the generic kernels
     // the second cycle table starts `shift` words past a whole number of bank rows: the displacement with the fewest
-    // modelled bank conflicts (150 bp: 17 words, 209 wavefronts per pass instead of 240; 124 would be conflict free)
+    // modelled bank conflicts (150 bp: 17 words for the apply kernel, 209 wavefronts per pass instead of 240; 15 words
+    // for the build kernel, 202 instead of 236; 124 would be conflict free)
     int shift = 0;
     if (const char *e = getenv("KBBQ_SLOT_SHIFT")) shift = std::max(0, std::min(31, atoi(e)));   // tuning hook
     else {
-        int best = cycle_table_wavefronts(g, t->sj, t->rs / 4, 0);
+        int best = cycle_table_wavefronts(g, t->sj, t->rs / 4, 0, word_owner);
         for (int d = 1; d < 32; ++d) {
-            const int w = cycle_table_wavefronts(g, t->sj, t->rs / 4, d);
+            const int w = cycle_table_wavefronts(g, t->sj, t->rs / 4, d, word_owner);
             if (w < best) { best = w; shift = d; }
         }
     }
@@ -195,7 +205,7 @@ struct ThreadMap {
 // instead of 220 wavefronts per CTA and byte position for 150 bp -- was built and measured on B200: no
 // faster, and its larger rows cost the apply kernel a group per stage.  The cycle-table reductions are not what
 // the kernel waits for.)
-__device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, const TableCfg &tc, bool by_parity) {
+__device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, const TableCfg &tc, bool by_parity, bool word_owner) {
     ThreadMap m;
     const int tid = threadIdx.x;
     m.grp = tid / g.lps;
@@ -209,7 +219,7 @@ __device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, const TableC
     m.rowmask = 0; m.toff = 0; m.selv = 0x4444u; m.seln = 0x4444u;
 #pragma unroll
     for (int b = 0; b < 4; ++b) { m.cell[b] = 0; m.cyc[b] = -1; }
-    if (by_parity) {
+    if (by_parity && word_owner) {
         // Uniform walk: every row of a group is tallied and the table of a byte follows from the parity of its row, so
         // nothing ties a thread to ONE row: lane t of the thread-group owns all four bytes of word t of the group,
         // whichever rows they belong to (a word that straddles two reads has one owner instead of two half-owners; the
@@ -240,7 +250,7 @@ __device__ __forceinline__ ThreadMap make_thread_map(const Geom &g, const TableC
                 m.rowmask |= 0xFFu << (8 * b);
                 m.selv = (m.selv & ~(0xFu << (4 * b))) | ((8u | b) << (4 * b));
                 if (c != 0) m.seln = (m.seln & ~(0xFu << (4 * b))) | ((8u | b) << (4 * b));
-                m.cell[b] = 4u * (uint32_t)((c & 3) * tc.sj + (c >> 2));
+                m.cell[b] = 4u * (uint32_t)((c & 3) * tc.sj + (c >> 2)) + (by_parity ? (uint32_t)((m.row & 1) * tc.revoff) : 0u);
             }
         }
     }
@@ -322,7 +332,9 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
     const StageLayout &sl = a.sl;
     const int nconsumers = g.threads;
     const uint32_t bar0 = pin(smem_u32(smem_raw + sl.bar_off));
-    const ThreadMap m = make_thread_map(g, t, UNI);
+    // one (row, word) per lane in either walk: the build has no stores to simplify, and its reductions collide less
+    // this way (ncu, 10 M x 150 bp: 51.7 M conflict wavefronts against 72 M with whole-word owners)
+    const ThreadMap m = make_thread_map(g, t, UNI, false);
     const int lane = threadIdx.x & 31;
     const uint32_t pos_base = smem_addr(smem_raw + t.pos_off);
     const uint32_t din_base = pin(smem_addr(smem_raw + t.din_off) + (lane & (t.drep - 1)) * 4);

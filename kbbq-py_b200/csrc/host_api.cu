@@ -536,9 +536,11 @@ int run_build_pass(kbbq_session *S, const uint8_t *seq, const uint8_t *qual, con
     const int L = S->L;
     const int64_t C = S->C, nchunks = N ? (N + C - 1) / C : 0;
     const bool keep = S->M > 0;
+    const int64_t k0 = S->built;   // chunks already in the session (a range may follow single chunks or another range)
+    if (keep && k0 + nchunks > (int64_t)S->res.size()) return KBBQ_E_ARG;
     auto upload = [&](int64_t k) {
         const int64_t r0 = k * C, n = std::min(C, N - r0);
-        return build_chunk_upload(S, k, seq + (size_t)r0 * L, qual + (size_t)r0 * L, rg ? rg + r0 : nullptr,
+        return build_chunk_upload(S, k0 + k, seq + (size_t)r0 * L, qual + (size_t)r0 * L, rg ? rg + r0 : nullptr,
                                   second ? second + r0 : nullptr, n, keep);
     };
     // the direct copies of chunk k + 1 are queued before chunk k is packed: the copy engine never waits for the cores
@@ -546,9 +548,9 @@ int run_build_pass(kbbq_session *S, const uint8_t *seq, const uint8_t *qual, con
     for (int64_t k = 0; k < nchunks; ++k) {
         const int64_t r0 = k * C, n = std::min(C, N - r0);
         if (k + 1 < nchunks) KBBQ_TRY(upload(k + 1));
-        KBBQ_TRY(build_chunk_finish(S, k, seq + (size_t)r0 * L, corr + (size_t)r0 * L, rg != nullptr, second != nullptr, n, keep));
+        KBBQ_TRY(build_chunk_finish(S, k0 + k, seq + (size_t)r0 * L, corr + (size_t)r0 * L, rg != nullptr, second != nullptr, n, keep));
     }
-    S->built = nchunks;
+    S->built = k0 + nchunks;
     return KBBQ_OK;
 }
 
@@ -617,6 +619,16 @@ int kbbq_session_build_chunk(kbbq_session *s, const uint8_t *seq, const uint8_t 
     const int64_t k = s->built;
     KBBQ_TRY(build_chunk_async(s, seq, qual, corr, rg, second, n, keep_resident != 0));
     if (n > 0) KBBQ_CUDA(cudaEventSynchronize(s->up[k & 1].uploaded));   // the caller may reuse its buffers
+    return KBBQ_OK;
+}
+
+int kbbq_session_build_range(kbbq_session *s, const uint8_t *seq, const uint8_t *qual, const uint8_t *corr,
+                             const uint16_t *rg, const uint8_t *second, int64_t n) {
+    if (!s || n < 0 || (n > 0 && (!seq || !qual || !corr))) return KBBQ_E_ARG;
+    std::lock_guard<std::mutex> lock(s->mu);
+    KBBQ_CUDA(cudaSetDevice(s->device));
+    KBBQ_TRY(run_build_pass(s, seq, qual, corr, rg, second, n));
+    KBBQ_CUDA(cudaStreamSynchronize(s->s_up));   // the caller may reuse its buffers
     return KBBQ_OK;
 }
 

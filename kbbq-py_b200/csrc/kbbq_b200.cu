@@ -83,7 +83,7 @@ static bool plan_smem(const Geom &g, int narr, int max_smem, TableCfg *tc, Stage
                 if (drep > dmax) continue;
                 for (int k = kmax; k >= kmin; --k) {
                     if (g.nprod > 1 && g.ng * k > 32) continue;  // one producer lane per group of a stage
-                    if (!make_table_cfg(g, k, drep, tc)) return false;
+                    if (!make_table_cfg(g, k, drep, narr == 2, tc)) return false;   // narr 2: the apply kernel
                     for (int s = smax; s >= want; --s) {
                         // several producer warps take the iterations round-robin: a stage must always be
                         // refilled by the same warp (its waits are only one phase deep), so the ring

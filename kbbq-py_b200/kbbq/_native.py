@@ -42,6 +42,7 @@ SIGNATURES = {
     "kbbq_session_chunk_reads": (_i64, [_vp]),
     "kbbq_session_reset": (_i, [_vp]),
     "kbbq_session_build_chunk": (_i, [_vp] * 6 + [_i64, _i]),
+    "kbbq_session_build_range": (_i, [_vp] * 6 + [_i64]),
     "kbbq_session_tables": (_i, [_vp, _vp]),
     "kbbq_session_set_tables": (_i, [_vp, _vp]),
     "kbbq_session_tables_dev": (_i, [_vp, C.POINTER(_vp), C.POINTER(_i64), C.POINTER(_vp)]),
@@ -397,6 +398,16 @@ class Session:
         rg = None if rg is None else np.ascontiguousarray(rg, dtype=np.uint16)
         second = None if second is None else u8(second)
         check(lib().kbbq_session_build_chunk(self.h, ptr(seq), ptr(qual), ptr(corr), ptr(rg), ptr(second), n, int(keep)))
+
+    def build_range(self, seq, qual, corr, rg=None, second=None):
+        """Pass 1 of reads that lie contiguously in host memory: cut into chunks by the session and pipelined across
+        them (kbbq_session_build_range).  Returns the number of chunks added."""
+        seq, qual, corr = u8(seq).ravel(), u8(qual).ravel(), u8(corr).ravel()
+        n = seq.size // self.L
+        rg = None if rg is None else np.ascontiguousarray(rg, dtype=np.uint16)
+        second = None if second is None else u8(second)
+        check(lib().kbbq_session_build_range(self.h, ptr(seq), ptr(qual), ptr(corr), ptr(rg), ptr(second), n))
+        return -(-n // self.chunk_reads)
 
     def tables(self):
         t = np.zeros(self.ntab, np.int64)

@@ -68,10 +68,9 @@ def recalibrate_host_distributed(seq, qual, corr, rg, second, L, R, out, session
         session.reset()
     C = session.chunk_reads
     seq2, qual2, corr2 = seq.reshape(-1, L), qual.reshape(-1, L), corr.reshape(-1, L)
-    for lo in range(0, n, C):
-        hi = min(n, lo + C)
-        session.build_chunk(seq2[lo:hi], qual2[lo:hi], corr2[lo:hi], None if rg is None else rg[lo:hi],
-                            None if second is None else second[lo:hi], keep=True)
+    # pass 1 over the whole shard in one call: the session pipelines the chunks (the copies of chunk k + 1 are
+    # queued before the host cores pack chunk k)
+    session.build_range(seq2[:n], qual2[:n], corr2[:n], None if rg is None else rg[:n], None if second is None else second[:n])
     session.flush()                                # the partial tables are complete
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         t = session_tables_tensor(session, dev)

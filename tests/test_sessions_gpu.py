@@ -40,9 +40,13 @@ def test_session_chunks(oracle_mod, R, L, resident):
             if rep:
                 s.reset()
                 out.fill(255)
-            for lo in range(0, N, C):
-                hi = min(N, lo + C)
-                s.build_chunk(seq[lo:hi], qual[lo:hi], corr[lo:hi], rg[lo:hi], second[lo:hi], keep=resident)
+            if rep == 0:
+                for lo in range(0, N, C):
+                    hi = min(N, lo + C)
+                    s.build_chunk(seq[lo:hi], qual[lo:hi], corr[lo:hi], rg[lo:hi], second[lo:hi], keep=resident)
+            else:   # the same reads as one chunk on its own followed by a pipelined range (kbbq_session_build_range)
+                s.build_chunk(seq[:C], qual[:C], corr[:C], rg[:C], second[:C], keep=resident)
+                assert s.build_range(seq[C:], qual[C:], corr[C:], rg[C:], second[C:]) == -(-(N - C) // C)
             tabs = s.tables()
             dqs = s.model(want_deltas=True)
             for k, lo in enumerate(range(0, N, C)):
