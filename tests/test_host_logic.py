@@ -206,3 +206,31 @@ def test_host_pack_nibbles_matches_numpy():
             bad = C.c_int(0)
             assert lib.kbbq_host_pack_nibbles(_native.ptr(s2), _native.ptr(seq), n, _native.ptr(packed), 0, C.byref(bad)) == 0
             assert bad.value == 1, (value, pos)
+
+
+def test_shared_memory_plans_fit_for_every_read_length():
+    """kbbq_plan_info (host only): every read length the shared-memory kernels claim (4 .. 288) gets a plan that
+    fits the 227 KB of a B200 SM, whole warps of consumers + producer warps within 1024 threads, a ring of at least
+    two stages -- for one and for several read groups, build (3 arrays staged) and apply (2)."""
+    import ctypes as C
+    from kbbq import _native
+    lib = _native.lib()
+    out = (C.c_int * 10)()
+    planned = 0
+    for L in range(4, 300):
+        for R in (1, 8):
+            for arrays in (3, 2):
+                rc = lib.kbbq_plan_info(L, R, 6, arrays, 0, out)
+                if L > 288:
+                    assert rc != 0, (L, R, arrays)     # longer reads take the generic kernels
+                    continue
+                assert rc == 0, (L, R, arrays)
+                G, lanes, ng, threads, nprod, kps, stages, drep, total, table_bytes = list(out)
+                planned += 1
+                assert total <= 232448 and table_bytes < total, (L, R, arrays, total)
+                assert threads % 32 == 0 and threads + 32 * nprod <= 1024 and ng * lanes <= threads, (L, R, arrays)
+                assert (G * L) % 4 == 0 and 1 <= kps <= 8 and stages >= 2 and drep in (8, 16, 32), (L, R, arrays)
+                # two cycle tables of 44 - minscore rows each (row stride a multiple of 128 B covering L cycles)
+                rows, rs = 44 - 6, (4 * ((L + 3) // 4) * 4 + 127) // 128 * 128
+                assert table_bytes >= 2 * rows * rs + rows * 16 * drep * 4, (L, R, arrays)
+    assert planned == 285 * 4
