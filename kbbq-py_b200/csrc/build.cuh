@@ -356,7 +356,9 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
     const uint32_t stage_bytes = pin(sl.narr * sl.abytes), abytes = pin(sl.abytes), abytes2 = pin(2 * sl.abytes), hdr_stride = sl.ngs * 16, krec = g.ng * 16;
     const uint32_t nstages = pin(sl.stages), ngs = pin(sl.ngs);
     const uint32_t revoff = t.revoff, addq = t.addq;
-    const uint32_t one = pin(1u), lut_acgt = pin(0x47544341u);  // 'A' 'C' 'T' 'G' by 2-bit code
+    // base validation: the low three bits tell A (1), C (3), T (4), N (6), G (7) apart; 0, 2, 5 map to a byte that no
+    // byte with those low bits can equal
+    const uint32_t one = pin(1u), minus1 = pin(0xFFFFFFFFu), lut_lo = pin(0x43014101u), lut_hi = pin(0x474E0154u);
     uint32_t stage = 0, phase = 0;
     uint32_t qgood = 0xFFFFFFFFu, bbad = 0;
 
@@ -427,7 +429,9 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
                     asm volatile("ld.shared.u8 %0, [%1];" : "=r"(pb) : "r"(wa - 1));
 
                     // ---- quality -> row index, byte-parallel ----
-                    const uint32_t nu = ~(qw + 0x55555555u);    // bit 7 clear <=> q >= 43 (for q < 128)
+                    // bit 7 clear <=> q >= 43 (for q < 128): ~(qw + 0x55555555) = qw * -1 - 0x55555556, one IMAD on the FMA
+                    // pipe (the ALU pipe is the one the kernel stalls on)
+                    const uint32_t nu = add_fma(qw, minus1, 0xAAAAAAAAu);
                     const uint32_t w5 = qw + addq;              // bit 7 <=> q >= minscore - 1, low bits q - (minscore - 1)
                     qgood &= nu & ~qw;                          // bit 7 stays set while every quality is <= 42
                     const uint32_t vraw = w5 & nu & ~qw;        // bit 7 <=> minscore - 1 <= q <= 42
@@ -444,15 +448,15 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
                     const uint32_t x01 = prmt(d4, qd, 0x5140u), x23 = prmt(d4, qd, 0x7362u);
 
                     // ---- mismatch: 0xFF where the corrected base differs (bases are 7-bit) ----
-                    const uint32_t e8 = prmt((sw ^ cw) + 0x7F7F7F7Fu, 0u, 0xBA98u);
+                    const uint32_t e8 = prmt(add_fma(sw ^ cw, one, 0x7F7F7F7Fu), 0u, 0xBA98u);
 
                     if (VALIDATE) {
                         // rebuild each byte from its 3-bit code (bits 1-3) with an 8-entry byte LUT; any difference = bad
                         // base.  The four codes are gathered into the selector nibbles by two 16-bit x 8-bit dot products
                         // (weights 1, 16 and 256, 4096) on the FMA pipe instead of shift / or / permute on the ALU pipe.
-                        const uint32_t code3 = (sw >> 1) & 0x07070707u;
+                        const uint32_t code3 = sw & 0x07070707u;
                         const uint32_t sel = __dp2a_hi(t.val16[1], code3, __dp2a_lo(t.val16[0], code3, 0u));
-                        const uint32_t recon = prmt(lut_acgt, 0x4E000000u /* . . . N */, sel);  // raw PRMT: __byte_perm would mask the selector
+                        const uint32_t recon = prmt(lut_lo, lut_hi, sel);  // raw PRMT: __byte_perm would mask the selector
                         bbad |= recon ^ sw;  // foreign bytes are masked off at the end (ownership is per byte position)
                     }
 
