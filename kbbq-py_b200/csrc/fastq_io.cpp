@@ -169,6 +169,17 @@ inline Rec parse_record(const char *p, const char *end) {
     return r;
 }
 
+// only the header line of the record starting at p: [h0, h1) without '@' and line end.  What the name-only loops
+// (read-group inference, name check) need: parse_record would scan the two long lines of every record as well.
+struct Hdr { const char *h0, *h1; };
+inline Hdr parse_header(const char *p, const char *end) {
+    Hdr r;
+    r.h0 = p + 1;
+    r.h1 = line_end(p, end);
+    if (r.h1 > r.h0 && r.h1[-1] == '\r') --r.h1;
+    return r;
+}
+
 // name = header up to the first whitespace (pysam's FastxRecord.name)
 inline const char *name_end(const char *h0, const char *h1) {
     const char *p = h0;
@@ -472,7 +483,7 @@ int kbbq_fastq_pack(const kbbq_fastq *f, int64_t first, int64_t n, uint8_t *seq,
 
 int kbbq_fastq_name(const kbbq_fastq *f, int64_t i, const char **name, int *len) {
     if (!f || i < 0 || i >= f->n || !name || !len) return KBBQ_E_ARG;
-    const Rec r = parse_record(f->data + f->rec[(size_t)i], f->data + f->rec[(size_t)i + 1]);
+    const Hdr r = parse_header(f->data + f->rec[(size_t)i], f->data + f->rec[(size_t)i + 1]);
     *name = r.h0;
     *len = (int)(name_end(r.h0, r.h1) - r.h0);
     return KBBQ_OK;
@@ -489,7 +500,9 @@ int kbbq_fastq_infer(kbbq_fastq *f, int infer_rg, uint16_t *rg, uint8_t *second,
         const int64_t a = n * t / T, b = n * (t + 1) / T;
         std::unordered_map<std::string, uint32_t> seen;
         for (int64_t i = a; i < b; ++i) {
-            const Rec r = parse_record(f->data + f->rec[(size_t)i], f->data + f->rec[(size_t)i + 1]);
+            // one header line per ~2 L bytes of file: the loop waits for memory, not for the scan -- fetch ahead
+            if (i + 16 < b) __builtin_prefetch(f->data + f->rec[(size_t)i + 16]);
+            const Hdr r = parse_header(f->data + f->rec[(size_t)i], f->data + f->rec[(size_t)i + 1]);
             const char *h1 = name_end(r.h0, r.h1);
             // first '_' field: second in pair <=> it ends in "/2" (kbbq/compare_reads.py:304-306)
             const char *u = (const char *)memchr(r.h0, '_', (size_t)(h1 - r.h0));
@@ -561,8 +574,12 @@ int kbbq_fastq_check_names(const kbbq_fastq *uncorr, const kbbq_fastq *corr, int
     parallel_for(T, [&](int t) {
         const int64_t a = n * t / T, b = n * (t + 1) / T;
         for (int64_t i = a; i < b; ++i) {
-            const Rec u = parse_record(uncorr->data + uncorr->rec[(size_t)i], uncorr->data + uncorr->rec[(size_t)i + 1]);
-            const Rec c = parse_record(corr->data + corr->rec[(size_t)i], corr->data + corr->rec[(size_t)i + 1]);
+            if (i + 16 < b) {
+                __builtin_prefetch(uncorr->data + uncorr->rec[(size_t)i + 16]);
+                __builtin_prefetch(corr->data + corr->rec[(size_t)i + 16]);
+            }
+            const Hdr u = parse_header(uncorr->data + uncorr->rec[(size_t)i], uncorr->data + uncorr->rec[(size_t)i + 1]);
+            const Hdr c = parse_header(corr->data + corr->rec[(size_t)i], corr->data + corr->rec[(size_t)i + 1]);
             const size_t ul = (size_t)(name_end(u.h0, u.h1) - u.h0), cl = (size_t)(name_end(c.h0, c.h1) - c.h0);
             if (cl < ul || memcmp(u.h0, c.h0, ul) != 0) { bad[t] = i; return; }  // corr.name.startswith(uncorr.name)
         }
