@@ -54,7 +54,9 @@ extern char g_last_cuda_error[256];
 // aligned 32-bit words; ONE THREAD OWNS ONE (row, word) of every group its thread-group processes,
 // so the cycles of its 4 bytes -- and therefore its shared-memory table offsets -- are fixed for
 // the whole kernel, and all its bytes belong to one read (one read group, one `second` flag).
-// Words that straddle two rows are loaded by both neighbours; each uses only its own bytes.
+// Words that straddle two rows are loaded by both neighbours; each uses only its own bytes.  (The apply kernel's
+// uniform walk lets a lane own the whole word instead -- the table of a byte is then the parity of its row, a
+// per-byte constant as well -- so that every lane stores whole words: make_thread_map, build.cuh.)
 // A thread-group is the sum W_k lanes of one group; thread-groups are packed back to back over the
 // CTA's consumer threads (a warp may hold lanes of two thread-groups -- everything a lane needs is a
 // per-thread constant), so only the last warp has padding lanes.  G (<= 8) is the smallest group
