@@ -80,32 +80,34 @@ static bool plan_smem(const Geom &g, int narr, int max_smem, TableCfg *tc, Stage
     // round -- 150 bp: kps 2 x 4 stages 0.898 ms, kps 4 x 2 stages 0.912 ms; 76 bp: kps 3 x 3 0.866 ms, kps 4 x 2
     // 0.945 ms; but 250 bp: kps 1 x 7 1.339 ms, kps 2 x 3 0.989 ms -- while the apply kernel still prefers four
     // groups per round: 0.809 against 0.889 ms with two.)  So: rules in order of preference, each a minimum of bytes
-    // in flight behind the stage being consumed and a minimum of groups per round; 0 bytes = whatever fits.
-    struct Rule { int in_flight, kmin; };
-    const Rule build_rules[] = {{60000, 2}, {40000, 2}, {0, 2}, {40000, 1}, {0, 1}};
-    const Rule apply_rules[] = {{40000, 2}, {0, 2}, {40000, 1}, {0, 1}};
+    // in flight behind the stage being consumed, a minimum of groups per round and a number of dinuc replicas; 0 bytes
+    // = whatever fits.
+    struct Rule { int in_flight, kmin, drep; };
+    // Conflict-free dinuc replicas (32) before the ring rules (16 replicas cost 10 % at 150 bp), but two groups per
+    // round with 16 replicas before one group per round with 32 (250 bp rows in read order, apply: 4.79 against 5.18 ms)
+    const Rule build_rules[] = {{60000, 2, 32}, {40000, 2, 32}, {0, 2, 32}, {40000, 2, 16}, {0, 2, 16},
+                                {40000, 1, 32}, {0, 1, 32}, {40000, 1, 16}, {0, 1, 16}, {0, 1, 8}};
+    const Rule apply_rules[] = {{40000, 2, 32}, {0, 2, 32}, {40000, 2, 16}, {0, 2, 16},
+                                {40000, 1, 32}, {0, 1, 32}, {40000, 1, 16}, {0, 1, 16}, {0, 1, 8}};
     const Rule *rules = narr == 3 ? build_rules : apply_rules;
-    const int nrules = narr == 3 ? 5 : 4;
+    const int nrules = narr == 3 ? 10 : 9;
     const char *f = getenv("KBBQ_IN_FLIGHT");   // tuning hook: replaces the first rule's bytes
-    // conflict-free dinuc replicas first (16 replicas cost 10 % at 150 bp), then the ring rules
-    for (int drep = 32; drep >= 8; drep >>= 1) {
-        if (drep == 8 && dmax > 8) continue;   // 8 replicas only on request
-        if (drep > dmax) continue;
-        for (int r = 0; r < nrules; ++r) {
-            const int in_flight_min = (r == 0 && f) ? std::max(0, atoi(f)) : rules[r].in_flight;
-            for (int k = kmax; k >= rules[r].kmin; --k) {
-                if (g.nprod > 1 && g.ng * k > 32) continue;  // one producer lane per group of a stage
-                if (!make_table_cfg(g, k, drep, narr == 2, tc)) return false;   // narr 2: the apply kernel
-                for (int s = smax; s >= want; --s) {
-                    // several producer warps take the iterations round-robin: a stage must always be
-                    // refilled by the same warp (its waits are only one phase deep), so the ring
-                    // depth has to be a multiple of their number
-                    if (s % g.nprod) continue;
-                    *sl = make_stage_layout(g, narr, s, k, tc->table_bytes);
-                    if (sl->total > max_smem) continue;
-                    if ((s - 1) * narr * sl->abytes < in_flight_min) break;  // deepest ring that fits is too shallow
-                    return true;
-                }
+    for (int r = 0; r < nrules; ++r) {
+        const int drep = rules[r].drep;
+        if (drep > dmax || (drep == 8 && dmax > 8)) continue;   // 8 replicas only on request
+        const int in_flight_min = (r == 0 && f) ? std::max(0, atoi(f)) : rules[r].in_flight;
+        for (int k = kmax; k >= rules[r].kmin; --k) {
+            if (g.nprod > 1 && g.ng * k > 32) continue;  // one producer lane per group of a stage
+            if (!make_table_cfg(g, k, drep, narr == 2, tc)) return false;   // narr 2: the apply kernel
+            for (int s = smax; s >= want; --s) {
+                // several producer warps take the iterations round-robin: a stage must always be
+                // refilled by the same warp (its waits are only one phase deep), so the ring
+                // depth has to be a multiple of their number
+                if (s % g.nprod) continue;
+                *sl = make_stage_layout(g, narr, s, k, tc->table_bytes);
+                if (sl->total > max_smem) continue;
+                if ((s - 1) * narr * sl->abytes < in_flight_min) break;  // deepest ring that fits is too shallow
+                return true;
             }
         }
     }
