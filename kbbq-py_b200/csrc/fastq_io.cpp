@@ -499,6 +499,7 @@ int kbbq_fastq_infer(kbbq_fastq *f, int infer_rg, uint16_t *rg, uint8_t *second,
     parallel_for(T, [&](int t) {
         const int64_t a = n * t / T, b = n * (t + 1) / T;
         std::unordered_map<std::string, uint32_t> seen;
+        struct Memo { const char *p = nullptr; size_t len = 0; uint32_t id = 0; } memo[64];
         for (int64_t i = a; i < b; ++i) {
             // one header line per ~2 L bytes of file: the loop waits for memory, not for the scan -- fetch ahead
             if (i + 16 < b) __builtin_prefetch(f->data + f->rec[(size_t)i + 16]);
@@ -517,12 +518,20 @@ int kbbq_fastq_infer(kbbq_fastq *f, int infer_rg, uint16_t *rg, uint8_t *second,
             if (f1e - f1 < 2 || f1[0] != 'R' || f1[1] != 'G') { err[t] |= 2; return; }  // AssertionError
             const char *k = f1e;
             while (k > f1 && k[-1] != ':') --k;
-            std::string key(k, (size_t)(f1e - k));
+            // a file has a handful of read groups: a small direct-mapped memo in front of the map (no string is built,
+            // nothing is hashed twice) answers all but the first read of each
+            const size_t klen = (size_t)(f1e - k);
+            uint32_t h = 2166136261u;
+            for (size_t c = 0; c < klen; ++c) h = (h ^ (uint8_t)k[c]) * 16777619u;
+            Memo &m = memo[(h ^ (h >> 16)) & 63u];
+            if (m.p && m.len == klen && memcmp(m.p, k, klen) == 0) { local[(size_t)i] = m.id; continue; }
+            std::string key(k, klen);
             auto it = seen.find(key);
             if (it == seen.end()) {
                 it = seen.emplace(key, (uint32_t)keys[t].size()).first;
                 keys[t].push_back(key);
             }
+            m.p = k; m.len = klen; m.id = it->second;
             local[(size_t)i] = it->second;
         }
     });
