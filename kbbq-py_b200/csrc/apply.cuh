@@ -202,9 +202,15 @@ __device__ __forceinline__ void apply_consume(const ApplyArgs &a, unsigned char 
                         hgrp = first + m.grp + k * g.ng;
                     } else {
                         uint32_t flo, fhi;
-                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                     : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
-                                     : "r"(shdr + k * krec));
+                        if (g.contig) {   // the identity list, read where it lies; past the span: no rows
+                            const uint32_t e = first + (uint32_t)m.grp + (uint32_t)(k * g.ng);
+                            const uint4 rec = e < s_hi ? __ldg(a.entries + e) : make_uint4(0u, 0u, 0u, 0u);
+                            soff = rec.x; hgrp = rec.y; flo = rec.z; fhi = rec.w;
+                        } else {
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
+                                         : "r"(shdr + k * krec));
+                        }
                         // cycle-table addresses are kept for the last row flag seen (see build.cuh)
                         const uint32_t flag = prmt(flo, fhi, rowsel) & lanemask;
                         if (flag != cur_flag) {

@@ -485,9 +485,15 @@ __device__ __forceinline__ void build_consume(const BuildArgs &a, unsigned char 
                         } else {
                             // this thread-group's k-th record of the stage
                             uint32_t hgrp, flo, fhi;
-                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                                         : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
-                                         : "r"(shdr + k * krec));
+                            if (g.contig) {   // the identity list, read where it lies; past the span: no rows
+                                const uint32_t e = first + (uint32_t)m.grp + (uint32_t)(k * g.ng);
+                                const uint4 rec = e < s_hi ? __ldg(a.entries + e) : make_uint4(0u, 0u, 0u, 0u);
+                                soff = rec.x; hgrp = rec.y; flo = rec.z; fhi = rec.w;
+                            } else {
+                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(soff), "=r"(hgrp), "=r"(flo), "=r"(fhi)
+                                             : "r"(shdr + k * krec));
+                            }
                             // flag byte of this thread's row: 0 = not in this segment (or a padding lane), 1 = read 1,
                             // 3 = read 2.  A row usually keeps its flag from group to group, so the cycle-table
                             // addresses are kept ready for the last flag seen and only re-based when it changes.

@@ -78,6 +78,8 @@ struct Geom {
     int ng;           // thread-groups (groups in flight) per CTA
     int threads;      // consumer threads: ng * lps rounded up to whole warps
     int nprod;        // producer warps behind the consumers (1 with one read group or a segmented batch, up to 8 otherwise)
+    int contig;       // one read group or a segmented batch: a stage is one contiguous span of groups and the work list,
+                      // if one is needed at all, is the identity (its records are read where they lie, not staged)
     int sj;           // plane stride (words)
     int row;          // words per quality row = 4 * sj
     int minscore;     // first tallied quality
@@ -122,6 +124,7 @@ inline bool make_geom(int L, int minscore, bool single_rg, int nprod, Geom *g, b
     g->lanes = best_lanes;
     g->lps = best_lanes;
     g->nprod = nprod;
+    g->contig = single_rg ? 1 : 0;
     // several read groups: a stage holds at most 32 groups (one per producer lane)
     g->ng = single_rg ? budget / g->lps : std::min(32, budget / g->lps);
     g->threads = (g->ng * g->lps + 31) / 32 * 32;

@@ -97,7 +97,7 @@ static bool plan_smem(const Geom &g, int narr, int max_smem, TableCfg *tc, Stage
         if (drep > dmax || (drep == 8 && dmax > 8)) continue;   // 8 replicas only on request
         const int in_flight_min = (r == 0 && f) ? std::max(0, atoi(f)) : rules[r].in_flight;
         for (int k = kmax; k >= rules[r].kmin; --k) {
-            if (g.nprod > 1 && g.ng * k > 32) continue;  // one producer lane per group of a stage
+            if (!g.contig && g.ng * k > 32) continue;  // gathered groups: one producer lane per group of a stage
             if (!make_table_cfg(g, k, drep, narr == 2, tc)) return false;   // narr 2: the apply kernel
             for (int s = smax; s >= want; --s) {
                 // several producer warps take the iterations round-robin: a stage must always be

@@ -30,16 +30,18 @@ struct StageLayout {
     int kps;          // groups every thread-group takes out of one stage
     int ngs;          // groups per stage = ng * kps
     int narr;         // arrays staged (3 for build, 2 for apply)
-    int abytes;       // bytes of one array inside a stage (multiple of 128)
+    int abytes;       // bytes of one array inside a stage (multiple of 16: bulk-copy destinations)
     int slot;         // bytes reserved per group when the groups of a stage are not contiguous
     int data_off;     // byte offsets from the start of dynamic shared memory
-    int hdr_off;      // stages x ng work-list records (entry_t)
+    int hdr_off;      // stages x ng work-list records (entry_t); none with contiguous spans (Geom::contig)
     int bar_off;      // full[stages], empty[stages] (8 bytes each)
     int total;        // dynamic shared memory bytes including the tables in front
 };
 
-// With one producer warp (one read group) a stage is always one contiguous span, so the per-group
-// slots with their alignment slack are not needed.
+// With contiguous spans (one read group, a segmented batch) a stage is one span per array -- no per-group slots with
+// their alignment slack -- and no work-list records are staged: the uniform walk needs none and the rare batch whose
+// groups differ (unpaired mates in no order) reads the identity list from global memory.  Every byte counts here: at
+// 150 bp this is what lets a third stage of three groups per thread-group fit next to the tables.
 inline StageLayout make_stage_layout(const Geom &g, int narr, int stages, int kps, size_t table_bytes) {
     StageLayout s;
     s.stages = stages;
@@ -47,10 +49,10 @@ inline StageLayout make_stage_layout(const Geom &g, int narr, int stages, int kp
     s.ngs = g.ng * kps;
     s.narr = narr;
     s.slot = (g.gbytes + 15 + 15) / 16 * 16;           // group + worst-case misalignment, 16-byte units
-    s.abytes = ((g.nprod == 1 ? s.ngs * g.gbytes + 32 : s.ngs * s.slot) + 127) / 128 * 128;
+    s.abytes = g.contig ? (s.ngs * g.gbytes + 32 + 15) / 16 * 16 : (s.ngs * s.slot + 127) / 128 * 128;
     s.data_off = (int)((table_bytes + 127) / 128 * 128);
     s.hdr_off = s.data_off + stages * narr * s.abytes;
-    s.bar_off = s.hdr_off + stages * s.ngs * 16;
+    s.bar_off = (s.hdr_off + (g.contig ? 0 : stages * s.ngs * 16) + 15) / 16 * 16;
     s.total = s.bar_off + 2 * stages * 8;
     return s;
 }
@@ -133,18 +135,14 @@ __device__ __forceinline__ void producer_loop(const ProducerArgs &p, const Stage
                 // the last group of a batch may be partial: stop at the end of the arrays
                 bytes = src >= end16 ? 0u : (uint32_t)min((unsigned long long)bytes, end16 - src);
                 mbar_wait(empty, phase ^ 1);
-                // a short last stage: the slots past the list must read as "no rows"
-                if (!p.uniform)
-                    for (uint32_t j = n; j < (uint32_t)p.ng; ++j)
-                        asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(hdr0 + (stage * p.ng + j) * 16u), "r"(0u) : "memory");
-                mbar_arrive_expect_tx(full, bytes * sl.narr + (p.uniform ? 0u : n * 16u));
+                // (no records are staged: a batch whose groups differ reads the identity list from global memory)
+                mbar_arrive_expect_tx(full, bytes * sl.narr);
                 const uint32_t dst = data0 + stage * sl.narr * sl.abytes;
                 if (bytes) {
 #pragma unroll
                     for (int k = 0; k < 3; ++k)
                         if (k < sl.narr) bulk_g2s(dst + k * sl.abytes, p.arr[k] + src, bytes, full);
                 }
-                if (!p.uniform) bulk_g2s(hdr0 + stage * p.ng * 16u, p.entries + first, n * 16u, full);
                 if (++stage == (uint32_t)sl.stages) { stage = 0; phase ^= 1; }
             }
         }
