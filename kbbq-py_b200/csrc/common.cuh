@@ -80,6 +80,9 @@ struct Geom {
     int nprod;        // producer warps behind the consumers (1 with one read group or a segmented batch, up to 8 otherwise)
     int contig;       // one read group or a segmented batch: a stage is one contiguous span of groups and the work list,
                       // if one is needed at all, is the identity (its records are read where they lie, not staged)
+    int pad_[3];      // keeps what follows this struct in the kernel parameters (TableCfg: the factors of the address
+                      // dot products) where it was modulo 16 bytes: ptxas fetches four of them with one LDCU.128 per
+                      // word when they are 16-byte aligned, and with four LDC (+ 5 % instructions) when they are not
     int sj;           // plane stride (words)
     int row;          // words per quality row = 4 * sj
     int minscore;     // first tallied quality
