@@ -38,6 +38,9 @@ struct ApplyArgs {
     int *status;
 };
 
+static_assert((offsetof(ApplyArgs, t) + offsetof(TableCfg, ohe)) % 16 == 0,
+              "ApplyArgs: TableCfg::ohe has to be 16-byte aligned in the kernel parameters (build.cuh); pad Geom");
+
 // bytes of shared memory the apply tables take
 __host__ __device__ inline int apply_table_bytes(const TableCfg &t) { return t.table_bytes; }
 

@@ -33,6 +33,7 @@
 //   * tables are per-CTA u32 in shared memory, flushed per read-group segment to the global int64
 //     tables with 64-bit reductions (zero cells skipped).
 #pragma once
+#include <cstddef>
 #include "common.cuh"
 #include "prepare.cuh"
 #include "stage.cuh"
@@ -156,6 +157,11 @@ struct BuildArgs {
     unsigned long long *pos_errs, *pos_total, *din_errs, *din_total;
     int *status;
 };
+
+// ohe[0..3] must start a 16-byte unit of the parameter bank (one LDCU.128 per word instead of four LDC:
+// see Geom::pad_ in common.cuh) -- a field added in front of them must keep that
+static_assert((offsetof(BuildArgs, t) + offsetof(TableCfg, ohe)) % 16 == 0,
+              "BuildArgs: TableCfg::ohe has to be 16-byte aligned in the kernel parameters; pad Geom");
 
 __device__ __forceinline__ void red_shared_add(uint32_t saddr, uint32_t v) {
     asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(saddr), "r"(v) : "memory");
